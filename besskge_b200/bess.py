@@ -1,0 +1,838 @@
+"""BESS distribution modules — drop-in for reference `besskge/bess.py`
+(`EmbeddingMovingBessKGE`, `ScoreMovingBessKGE`, `TopKQueryBessKGE`), built
+B200-first.
+
+What the reference expresses as torch ops traced by PopTorch for IPUs
+(`entity_embedding[cat(head, tail, negative)]` -> `all_to_all` -> score ->
+loss, bess.py:322-468) is here one stream-ordered sequence of hand-written
+sm_100a kernels per micro-batch, called through the C-ABI:
+
+  routed gather  ->  (exchange)  ->  score_triple  ->  query prologue +
+  negative scoring  ->  masks  ->  fused loss / dL/dscore  ->  backward
+  kernels  ->  (reverse exchange)  ->  radix sort + deterministic segmented
+  scatter-add fused with the optimizer.
+
+Replica placement (the reference is single-controller with PopTorch replicas):
+  * local mode      — all `n_shard` shards live on THIS process's GPU; the
+    AllToAll is folded into the gather, which writes every row straight into
+    the receive buffer of the replica that scores it;
+  * distributed mode — one process per GPU (`torch.distributed`, NCCL); this
+    process owns shard `rank`; the gather fills the send buffer and
+    `all_to_all_single` transposes the blocks over NVLink.
+Inputs keep the reference layout: a leading `batches_per_step * n_shard` axis
+(step-major, shard-minor); outputs are concatenated in the same order
+(tests/test_bess.py:181-196 of the reference).
+"""
+from __future__ import annotations
+
+import dataclasses
+from abc import ABC, abstractmethod
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import kernels as K
+from .kernels import BAD_NEGATIVE_SCORE
+from .loss import BaseLossFunction
+from .metric import Evaluation
+from .negative_sampler import (
+    PlaceholderNegativeSampler,
+    ShardedNegativeSampler,
+    TripleBasedShardedNegativeSampler,
+)
+from .optim import SGD, AdamW
+from .scoring import BaseScoreFunction
+
+__all__ = [
+    "BAD_NEGATIVE_SCORE",
+    "BessKGE",
+    "EmbeddingMovingBessKGE",
+    "ScoreMovingBessKGE",
+    "TopKQueryBessKGE",
+    "training_model",
+]
+
+
+# ---------------------------------------------------------------------------
+# replica placement
+# ---------------------------------------------------------------------------
+class _Placement:
+    """Which shards this process computes and how blocks are exchanged."""
+
+    def __init__(self, n_shard: int) -> None:
+        self.n_shard = n_shard
+        dist = torch.distributed
+        self.distributed = bool(
+            dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        )
+        if self.distributed:
+            if dist.get_world_size() != n_shard:
+                raise ValueError(
+                    f"distributed BESS needs world_size == n_shard ({dist.get_world_size()} vs {n_shard})"
+                )
+            self.rank = dist.get_rank()
+            self.shards = [self.rank]
+        else:
+            self.rank = 0
+            self.shards = list(range(n_shard))
+
+    @property
+    def n_local(self) -> int:
+        return len(self.shards)
+
+    def all_to_all(self, recv: torch.Tensor, send: torch.Tensor) -> None:
+        """recv[j] <- send_j[rank]: equal-split AllToAll (bess.py:348-350)."""
+        torch.distributed.all_to_all_single(recv.view(-1), send.view(-1))
+
+
+@dataclasses.dataclass
+class _Pass:
+    """One launch group of score_heads / score_tails (bess.py:368-466)."""
+
+    mode: int
+    n_query: int
+    qmap: L.RowMap  # query q -> position in the [S] micro-batch order
+    fixed_from_head: bool  # fixed entity rows come from H (else from received tails)
+    fixed_map: L.RowMap
+    shared: bool
+    n_cand: int  # shared: size of the candidate list; else candidates per query
+    cand_map: L.RowMap
+    q_stride: int
+    col0: int
+    cand_from_head: bool = False  # candidates live in the local head buffer
+    aug: bool = False  # candidates are the micro-batch's own heads / tails
+
+
+def _as_i32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.int32 else t.to(torch.int32)
+
+
+class BessKGE(torch.nn.Module, ABC):
+    """Base class (reference: bess.py:34-305): validation, input staging, masks,
+    loss, metrics.  Subclasses define how negatives are scored."""
+
+    def __init__(
+        self,
+        negative_sampler: ShardedNegativeSampler,
+        score_fn: BaseScoreFunction,
+        loss_fn: Optional[BaseLossFunction] = None,
+        evaluation: Optional[Evaluation] = None,
+        return_scores: bool = False,
+        augment_negative: bool = False,
+    ) -> None:
+        super().__init__()
+        self.sharding = score_fn.sharding
+        self.negative_sampler = negative_sampler
+        self.score_fn = score_fn
+        self.loss_fn = loss_fn
+        self.evaluation = evaluation
+        self.return_scores = return_scores
+        self.augment_negative = augment_negative
+        if not (loss_fn or evaluation or return_scores):
+            raise ValueError(
+                "Nothing to return. At least one of loss_fn,"
+                " evaluation or return_scores needs to be != None"
+            )
+        if self.augment_negative:
+            assert (
+                score_fn.negative_sample_sharing
+            ), "Negative augmentation requires negative sample sharing"
+            assert not isinstance(
+                self, ScoreMovingBessKGE
+            ), "ScoreMovingBessKGE does not support negative augmentation"
+        if negative_sampler.flat_negative_format:
+            assert (
+                score_fn.negative_sample_sharing
+            ), "Using flat negative format requires negative sample sharing"
+        elif score_fn.negative_sample_sharing and isinstance(
+            self.negative_sampler, TripleBasedShardedNegativeSampler
+        ):
+            raise ValueError(
+                "Negative sample sharing cannot be used with non-flat triple-specific negatives"
+            )
+        self.entity_embedding = self.score_fn.entity_embedding
+        self.entity_embedding_size: int = self.score_fn.entity_embedding.shape[-1]
+        self._ws: Optional[K.Workspace] = None
+        self._placement: Optional[_Placement] = None
+        self._opt_state: Dict[str, Any] = {}
+
+    # ------------------------------------------------------------------ misc
+    @property
+    def n_embedding_parameters(self) -> int:
+        return self.score_fn.entity_embedding.numel() + self.score_fn.relation_embedding.numel()
+
+    def _device(self) -> torch.device:
+        dev = self.score_fn.entity_embedding.device
+        if dev.type != "cuda":
+            raise L.BessLibraryError(
+                "besskge_b200 has no CPU path: move the module to a CUDA device first "
+                "(model.cuda()); on a machine without a GPU only the host-side samplers run"
+            )
+        return dev
+
+    def _tables(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        ent = self.score_fn.entity_embedding.data
+        rel = self.score_fn.relation_embedding.data
+        if rel.dtype != ent.dtype:
+            raise TypeError("entity and relation tables must share one dtype")
+        return ent, rel
+
+    def _setup(self) -> Tuple[K.Workspace, _Placement]:
+        dev = self._device()
+        if self._ws is None or self._ws.device != dev:
+            self._ws = K.Workspace(dev)
+        if self._placement is None:
+            self._placement = _Placement(self.sharding.n_shard)
+        return self._ws, self._placement
+
+    # -------------------------------------------------------------- forward
+    def forward(
+        self,
+        head: torch.Tensor,
+        relation: torch.Tensor,
+        tail: torch.Tensor,
+        negative: torch.Tensor,
+        triple_mask: Optional[torch.Tensor] = None,
+        triple_weight: Optional[torch.Tensor] = None,
+        negative_mask: Optional[torch.Tensor] = None,
+    ) -> Dict[str, Any]:
+        """Score (and, under `training_model`, train on) `batches_per_step`
+        micro-batches.  Shapes as the reference (bess.py:117-161) with a leading
+        `bps * n_shard` axis: head/relation/tail [L, n, p], negative [L, n, B, Nn],
+        triple_weight [L, S], negative_mask [L, B, n, Nn], triple_mask [L, n, p]."""
+        return self._run(head, relation, tail, negative, triple_mask, triple_weight,
+                         negative_mask, optimizer=None)
+
+    @abstractmethod
+    def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
+             optimizer) -> Dict[str, Any]:
+        raise NotImplementedError
+
+    # ------------------------------------------------------ shared plumbing
+    def _stage(self, name: str, t: Optional[torch.Tensor], dtype: torch.dtype,
+               dev: torch.device) -> Optional[torch.Tensor]:
+        """Host->device copy into a persistent buffer (no per-step allocation)."""
+        if t is None:
+            return None
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        buf = self._ws.get("in_" + name, tuple(t.shape), dtype)
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def _step_rows(self, placement: _Placement, bps: int) -> List[List[int]]:
+        """rows of the leading axis used at each step, one per local replica."""
+        n = placement.n_shard
+        return [[s * n + r for r in placement.shards] for s in range(bps)]
+
+    def _finish_metrics(self, out: Dict[str, Any], pos: torch.Tensor, neg: torch.Tensor,
+                        triple_mask: Optional[torch.Tensor], acc: Dict[str, List]) -> None:
+        if self.evaluation is None:
+            return
+        rank = self.evaluation.ranks_from_scores(pos, neg)
+        if self.evaluation.return_ranks:
+            acc.setdefault("ranks", []).append(rank)
+        acc.setdefault("metrics", []).append(
+            self.evaluation.stacked_metrics_from_ranks(rank, triple_mask)
+        )
+
+
+# ---------------------------------------------------------------------------
+# EmbeddingMoving
+# ---------------------------------------------------------------------------
+class EmbeddingMovingBessKGE(BessKGE):
+    """Negative (and tail) embeddings travel to the shard that scores the
+    positive triple (reference: bess.py:308-468).  One balanced AllToAll of
+    `[n, p + B*Nn, D]` per micro-batch; in local mode it is folded into the
+    gather kernel."""
+
+    # ---- plan --------------------------------------------------------------
+    def _plan(self, n: int, p: int, B: int, Nn: int) -> Tuple[List[_Pass], int]:
+        scheme = self.negative_sampler.corruption_scheme
+        flat = self.negative_sampler.flat_negative_format
+        shared = bool(self.score_fn.negative_sample_sharing)
+        local = bool(self.negative_sampler.local_sampling)
+        S = n * p
+        per = p if local else p + B * Nn
+        # where negative block (j, b, k) lives: received buffer TN[j][p + b*Nn + k] or,
+        # with local sampling, the local buffer after the S head rows
+        if local:
+            neg_off, neg_stride = S, B * Nn
+        else:
+            neg_off, neg_stride = p, per
+        rm = L.rowmap
+        passes: List[_Pass] = []
+        if scheme in ("h", "t"):
+            mode = L.MODE_TAILS if scheme == "t" else L.MODE_HEADS
+            from_head = scheme == "t"
+            fixed_map = L.IDENT if from_head else rm(p, per, 0)
+            if flat:
+                passes.append(_Pass(mode, S, L.IDENT, from_head, fixed_map, True, n * Nn,
+                                    rm(Nn, neg_stride, neg_off), 0, 0))
+                n_col = n * Nn
+            elif shared:
+                passes.append(_Pass(mode, S, L.IDENT, from_head, fixed_map, True, S * n * Nn,
+                                    rm(Nn, neg_stride, neg_off, n * Nn, Nn), 0, 0))
+                n_col = S * n * Nn
+            else:
+                passes.append(_Pass(mode, S, L.IDENT, from_head, fixed_map, False, n * Nn,
+                                    rm(Nn, neg_stride, neg_off), Nn, 0))
+                n_col = n * Nn
+        elif scheme == "ht":
+            half = p // 2
+            if not flat and shared:
+                raise NotImplementedError(
+                    "'ht' corruption with non-flat shared negatives is not implemented"
+                )
+            for k, (mode, from_head) in enumerate(((L.MODE_HEADS, False), (L.MODE_TAILS, True))):
+                qmap = rm(half, p, k * half)
+                fixed_map = rm(half, p, k * half) if from_head else rm(half, per, k * half)
+                if flat:
+                    passes.append(_Pass(mode, n * half, qmap, from_head, fixed_map, True, n * Nn,
+                                        rm(Nn, neg_stride, neg_off + k * Nn), 0, 0))
+                else:
+                    passes.append(_Pass(mode, n * half, qmap, from_head, fixed_map, False, n * Nn,
+                                        rm(Nn, neg_stride, neg_off), Nn, 0))
+            n_col = n * Nn
+        else:
+            raise ValueError(f"unknown corruption scheme {scheme}")
+        if self.augment_negative:
+            if not flat or local:
+                raise NotImplementedError(
+                    "augment_negative needs flat_negative_format=True and local_sampling=False"
+                )
+            if self.score_fn._family == L.PAIRRE and getattr(self.score_fn, "normalize", False):
+                raise NotImplementedError("augment_negative with normalised PairRE")
+            # the micro-batch's own heads / tails come first (bess.py:369-394, 430-448)
+            aug: List[_Pass] = []
+            for ps in passes:
+                g = ps.qmap.group
+                if ps.mode == L.MODE_TAILS:  # candidates: received tails of the same queries
+                    cmap = rm(g, per, ps.qmap.offset) if g > 0 else rm(p, per, 0)
+                    aug.append(_Pass(ps.mode, ps.n_query, ps.qmap, ps.fixed_from_head,
+                                     ps.fixed_map, True, ps.n_query, cmap, 0, 0, False, True))
+                else:  # candidates: local heads of the same queries
+                    aug.append(_Pass(ps.mode, ps.n_query, ps.qmap, ps.fixed_from_head,
+                                     ps.fixed_map, True, ps.n_query, ps.qmap, 0, 0, True, True))
+                ps.col0 = ps.n_query
+            n_col = passes[0].n_query + n * Nn
+            passes = aug + passes
+        return passes, n_col
+
+    # ---- run ---------------------------------------------------------------
+    def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
+             optimizer) -> Dict[str, Any]:
+        ws, pl = self._setup()
+        dev = ws.device
+        ent, rel_table = self._tables()
+        n = self.sharding.n_shard
+        L_rows = head.shape[0]
+        if L_rows % n != 0:
+            raise ValueError(f"leading axis {L_rows} is not a multiple of n_shard={n}")
+        bps = L_rows // n
+        p = head.shape[-1]
+        B, Nn = negative.shape[-2], negative.shape[-1]
+        S = n * p
+        local = bool(self.negative_sampler.local_sampling)
+        per = p if local else p + B * Nn
+        n_loc_rows = S + (n * B * Nn if local else 0)
+        passes, N = self._plan(n, p, B, Nn)
+        W, Wr = ent.shape[-1], rel_table.shape[-1]
+        cfg = self.score_fn.kernel_cfg()
+        dt = L.dtype_code(ent.dtype)
+        tdt = ent.dtype
+        train = optimizer is not None
+        if train and self.loss_fn is None:
+            raise ValueError("training needs a loss_fn")
+
+        # ---- pack + stage inputs: gidx = [heads | (neg if local) | per dst: tails, negs]
+        h2 = _as_i32(head).reshape(L_rows, S)
+        t3 = _as_i32(tail).reshape(L_rows, n, p)
+        n3 = _as_i32(negative).reshape(L_rows, n, B * Nn)
+        if local:
+            gidx_h = torch.cat([h2, n3.reshape(L_rows, -1), t3.reshape(L_rows, -1)], dim=1)
+        else:
+            gidx_h = torch.cat([h2, torch.cat([t3, n3], dim=2).reshape(L_rows, -1)], dim=1)
+        gidx = self._stage("gidx", gidx_h, torch.int32, dev)
+        rel = self._stage("rel", relation.reshape(L_rows, S), torch.int32, dev)
+        tw = self._stage("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
+                         torch.float32, dev)
+        nmask = None
+        if negative_mask is not None:
+            nmask = self._stage("nmask", negative_mask.reshape(L_rows, negative_mask.shape[1], -1),
+                                torch.uint8 if negative_mask.dtype != torch.bool else torch.bool,
+                                dev)
+        tmask = self._stage("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
+                            torch.bool, dev)
+        one = ws.get("one", (1,), torch.float32)
+        one.fill_(1.0)
+
+        R = pl.n_local
+        G = gidx.shape[1]
+        # ---- persistent buffers
+        H = ws.get("H", (R, n_loc_rows, W), tdt)
+        TN = ws.get("TN", (R, n, per, W), tdt)
+        SEND = ws.get("SEND", (n, per, W), tdt) if pl.distributed else None
+        pos_ws = ws.get("pos", (R, S), torch.float32)
+        nvec = K.call("bess_query_nvec", L.C.byref(cfg))
+        qv = ws.get("qv", (S, nvec, W), torch.float32)
+        need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
+        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        aux = ws.get("aux", (R, S, N), torch.float32) if need_aux else None
+
+        n_out = bps * R
+        want_scores = self.return_scores
+        pos_out = torch.empty(n_out * S, dtype=torch.float32, device=dev) if want_scores else None
+        neg_out = (torch.empty(n_out * S, N, dtype=torch.float32, device=dev)
+                   if want_scores else None)
+        neg_ws = None if want_scores else ws.get("neg", (R, S, N), torch.float32)
+        loss_out = (torch.empty(n_out, dtype=torch.float32, device=dev)
+                    if self.loss_fn is not None else None)
+        acc: Dict[str, List] = {}
+
+        if self.loss_fn is not None:
+            lp = self.loss_fn.kernel_params()
+            row_loss = ws.get("row_loss", (S,), torch.float32)
+            d_pos = ws.get("d_pos", (R, S), torch.float32)
+            d_neg = ws.get("d_neg", (R, S, N), torch.float32)
+            ce_copy = lp["kind"] == L.LOSS_SOFTMAX_CE and train and cfg.norm_p == 2 and \
+                cfg.family in (L.TRANSE, L.ROTATE, L.PAIRRE, L.BOXE)
+            neg_l = ws.get("neg_l", (S, N), torch.float32) if ce_copy else None
+        if train:
+            dH = ws.get("dH", (R, n_loc_rows, W), torch.float32)
+            dTN = ws.get("dTN", (R, n, per, W), torch.float32)
+            dBACK = ws.get("dBACK", (n, per, W), torch.float32) if pl.distributed else None
+            dRq = ws.get("dRq", (R, S, Wr), torch.float32)
+            d_qv = ws.get("d_qv", (S, nvec, W), torch.float32)
+            max_cand = max(ps.n_cand for ps in passes if ps.shared) if any(
+                ps.shared for ps in passes) else 0
+            cand_ws = None
+            if max_cand:
+                nbytes = max(K.shared_bwd_cand_workspace(cfg, ps.n_query, ps.n_cand)
+                             for ps in passes if ps.shared)
+                cand_ws = ws.get("cand_ws", (max(nbytes // 4, 1),), torch.float32)
+            sk = ws.get("sort_keys", (G,), torch.int32)
+            sp = ws.get("sort_perm", (G,), torch.int32)
+            sort_ws = ws.get("sort_ws", (K.sort_workspace(max(G, R * S)) // 4 + 64,), torch.int32)
+            rk = ws.get("rel_keys", (R * S,), torch.int32)
+            rp = ws.get("rel_perm", (R * S,), torch.int32)
+            d_rel_table = ws.get("d_rel_table", tuple(rel_table.shape), torch.float32)
+            key_bits = max(1, int(ent.shape[1] - 1).bit_length())
+            rel_bits = max(1, int(rel_table.shape[0] - 1).bit_length())
+        scale_buf = ws.get("cand_scale", (max(ps.n_cand for ps in passes),), torch.float32) \
+            if need_scale else None
+
+        flat = self.negative_sampler.flat_negative_format
+        scheme = self.negative_sampler.corruption_scheme
+
+        for s, step_rows in enumerate(self._step_rows(pl, bps)):
+            # ================= gather (+ exchange) =================
+            for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
+                table = ent[shard]
+                if pl.distributed:
+                    dst = [SEND[j].data_ptr() for j in range(n)]
+                    slot = 0
+                else:
+                    dst = [TN[j].data_ptr() for j in range(n)]
+                    slot = li
+                K.gather_route(table, gidx[row], n_loc_rows, per, H[li], dst, slot)
+            if pl.distributed:
+                pl.all_to_all(TN[0], SEND)
+
+            for li, row in enumerate(step_rows):
+                o = s * R + li
+                pos = pos_out[o * S:(o + 1) * S] if want_scores else pos_ws[li]
+                neg = neg_out[o * S:(o + 1) * S] if want_scores else neg_ws[li]
+                Hl, TNl = H[li], TN[li].view(n * per, W)
+                head_rows = L.rows(Hl)
+                tail_rows = L.rows(TNl, rmap=L.rowmap(p, per, 0))
+                # ================= positive scores =================
+                K.triple_fwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S, pos,
+                             L.IDENT)
+                # ================= negative scores =================
+                for ps in passes:
+                    fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
+                             else L.rows(TNl, rmap=ps.fixed_map))
+                    K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                   ps.n_query, qv)
+                    cand = self._cand_rows(ps, Hl, TNl, local)
+                    if ps.shared:
+                        scale = None
+                        if need_scale:
+                            scale = scale_buf[:ps.n_cand]
+                            K.cand_inv_norm(dt, cand, ps.n_cand, W, scale)
+                        K.shared_fwd(cfg, dt, ps.mode, qv, ps.n_query, cand, scale, ps.n_cand,
+                                     neg, ps.qmap, N, ps.col0, None if aux is None else aux[li])
+                    else:
+                        K.pertriple_fwd(cfg, dt, ps.mode, qv, ps.n_query, cand, ps.q_stride,
+                                        ps.n_cand, neg, ps.qmap, N, ps.col0,
+                                        None if aux is None else aux[li])
+                # ================= masks (bess.py:182-245) =================
+                self._apply_masks(neg, S, N, p, B, Nn, n, nmask[row] if nmask is not None else None,
+                                  flat, scheme)
+                # ================= loss =================
+                if self.loss_fn is not None:
+                    w = tw[row] if tw is not None else one
+                    neg_for_loss = neg
+                    if ce_copy:
+                        neg_l.copy_(neg)
+                        neg_for_loss = neg_l
+                    K.loss_fwd_bwd(lp["kind"], lp["margin"], lp["adversarial"], lp["adv_scale"],
+                                   lp["loss_scale"], lp["n_entity"], pos, neg_for_loss, S, N, N, w,
+                                   row_loss, d_pos[li], d_neg[li])
+                    K.sum_f32(row_loss, S, loss_out[o:o + 1])
+                    if ce_copy and want_scores:
+                        neg_saved = ws.get("neg_unshift", (R, S, N), torch.float32)
+                        neg_saved[li].copy_(neg)
+                        neg.copy_(neg_l)
+                if self.evaluation is not None:
+                    self._finish_metrics({}, pos, neg, tmask[row] if tmask is not None else None,
+                                         acc)
+
+                # ================= backward =================
+                if train:
+                    score_for_bwd = neg
+                    if ce_copy and want_scores:
+                        score_for_bwd = ws.get("neg_unshift", (R, S, N), torch.float32)[li]
+                    dHl, dTNl = dH[li], dTN[li].view(n * per, W)
+                    K.triple_bwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S,
+                                 pos, d_pos[li], L.IDENT, L.rows(dHl),
+                                 L.rows(dTNl, rmap=L.rowmap(p, per, 0)), dRq[li], False, False,
+                                 False)
+                    for ps in passes:
+                        fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
+                                 else L.rows(TNl, rmap=ps.fixed_map))
+                        d_fixed = (L.rows(dHl, rmap=ps.fixed_map) if ps.fixed_from_head
+                                   else L.rows(dTNl, rmap=ps.fixed_map))
+                        K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                       ps.n_query, qv)
+                        cand = self._cand_rows(ps, Hl, TNl, local)
+                        d_cand = self._cand_rows(ps, dHl, dTNl, local)
+                        a = None if aux is None else aux[li]
+                        if ps.shared:
+                            scale = None
+                            if need_scale:
+                                scale = scale_buf[:ps.n_cand]
+                                K.cand_inv_norm(dt, cand, ps.n_cand, W, scale)
+                            K.shared_bwd_query(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
+                                               ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
+                                               ps.col0, a, d_qv)
+                            K.shared_bwd_cand(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
+                                              ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
+                                              ps.col0, a, d_cand, cand_ws, add=ps.aug)
+                            if need_scale:
+                                K.cand_norm_bwd(dt, cand, ps.n_cand, W, scale, d_cand)
+                        else:
+                            K.pertriple_bwd(cfg, dt, ps.mode, qv, ps.n_query, cand, ps.q_stride,
+                                            ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
+                                            ps.col0, a, d_qv, d_cand)
+                        K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                       ps.n_query, d_qv, d_fixed, dRq[li], True, True)
+                    if cfg.family == L.BOXE:
+                        K.boxe_rel_finalize(cfg, dt, rel_table, rel[row], S, dRq[li])
+
+            # ================= reverse exchange + update =================
+            if train:
+                if pl.distributed:
+                    pl.all_to_all(dBACK, dTN[0])
+                self._opt_state.setdefault("step", 0)
+                self._opt_state["step"] += 1
+                step_no = self._opt_state["step"]
+                for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
+                    K.sort_keys(gidx[row], G, key_bits, sk, sp, sort_ws)
+                    if pl.distributed:
+                        g_dst, stride_rows = dBACK.data_ptr(), per
+                    else:
+                        g_dst = dTN.data_ptr() + li * per * W * 4
+                        stride_rows = n * per
+                    self._update_entity(optimizer, ent[shard], shard, sk, sp, G, n_loc_rows, per,
+                                        dH[li], g_dst, stride_rows, step_no, ws)
+                # relation table (replicated): reduce per-query rows of all local replicas
+                rows_this_step = rel[step_rows[0]:step_rows[-1] + 1]
+                if not rows_this_step.is_contiguous() or len(step_rows) != R:
+                    rows_this_step = rows_this_step.contiguous()
+                K.sort_keys(rows_this_step.view(-1), R * S, rel_bits, rk, rp, sort_ws)
+                K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
+                                       rel_table.shape[0], d_rel_table)
+                if pl.distributed:
+                    torch.distributed.all_reduce(d_rel_table)
+                if getattr(optimizer, "relation_grad_reduction", "mean") == "mean" and n > 1:
+                    d_rel_table.mul_(1.0 / n)
+                self._update_relation(optimizer, rel_table, d_rel_table, step_no, ws)
+
+        out: Dict[str, Any] = {}
+        if want_scores:
+            out["positive_score"] = pos_out if tdt == torch.float32 else pos_out.to(tdt)
+            out["negative_score"] = neg_out if tdt == torch.float32 else neg_out.to(tdt)
+        if loss_out is not None:
+            out["loss"] = loss_out
+        if "ranks" in acc:
+            out["ranks"] = torch.cat(acc["ranks"])
+        if "metrics" in acc:
+            out["metrics"] = torch.cat(acc["metrics"], dim=0)
+        return out
+
+    # ---- helpers -------------------------------------------------------------
+    @staticmethod
+    def _cand_rows(ps: _Pass, Hl: torch.Tensor, TNl: torch.Tensor, local: bool) -> L.Rows:
+        if ps.cand_from_head or (local and not ps.aug):
+            return L.rows(Hl, rmap=ps.cand_map)
+        return L.rows(TNl, rmap=ps.cand_map)
+
+    def _apply_masks(self, neg: torch.Tensor, S: int, N: int, p: int, B: int, Nn: int, n: int,
+                     nmask: Optional[torch.Tensor], flat: bool, scheme: str) -> None:
+        """BAD_NEGATIVE_SCORE on padding negatives and, with augment_negative, on
+        each triple's own head/tail column (bess.py:182-245)."""
+        if self.augment_negative:
+            half = p // 2 if scheme == "ht" else 0
+            n_aug = N - n * Nn
+            K.mask_diag(neg, S, N, 1, half, p if scheme == "ht" else 0, BAD_NEGATIVE_SCORE)
+            if nmask is not None:
+                self._mask_block(neg, S, N, p, n, Nn, nmask, flat, scheme, n_aug)
+        elif nmask is not None:
+            self._mask_block(neg, S, N, p, n, Nn, nmask, flat, scheme, 0)
+
+    @staticmethod
+    def _mask_block(neg: torch.Tensor, S: int, N: int, p: int, n: int, Nn: int,
+                    nmask: torch.Tensor, flat: bool, scheme: str, col_off: int) -> None:
+        # nmask: [Bm, n*Nn] uint8/bool, True = real negative
+        m = nmask.view(torch.uint8) if nmask.dtype == torch.bool else nmask
+        width = n * Nn
+        if flat and scheme == "ht":
+            # row 0 masks the first half of every partition, row 1 the second half
+            half = p // 2
+            for k in range(2):
+                rows_k = neg.view(n, p, N)[:, k * half:(k + 1) * half]
+                # strided row blocks: launch per partition (n is small)
+                for j in range(n):
+                    K.mask_add(rows_k[j], half, width, N, m[k], width, 1, False,
+                               BAD_NEGATIVE_SCORE, col_off)
+        else:
+            K.mask_add(neg, S, width, N, m, width, m.shape[0], False, BAD_NEGATIVE_SCORE, col_off)
+
+    def _update_entity(self, opt, table: torch.Tensor, shard: int, sk, sp, G: int, n_local: int,
+                       per: int, dH_l: torch.Tensor, g_dst: int, stride_rows: int, step_no: int,
+                       ws: K.Workspace) -> None:
+        W = table.shape[1]
+        if opt.sparse_exact:
+            K.scatter_sgd(table, sk, sp, G, n_local, per, dH_l, g_dst, stride_rows, opt.lr)
+            return
+        seg = ws.get("seg_grad", (G, W), torch.float32)
+        r2s = ws.get(f"row_to_seg", (table.shape[0],), torch.int32)
+        K.fill_i32(r2s, -1)
+        K.scatter_collect(W, sk, sp, G, n_local, per, dH_l, g_dst, stride_rows, seg, r2s)
+        st = self._opt_state
+        key0, key1 = f"ent_s0_{shard}", f"ent_s1_{shard}"
+        if key0 not in st:
+            st[key0] = torch.zeros(table.shape[0], W, dtype=torch.float32, device=table.device)
+            if opt.kind == L.OPT_ADAMW:
+                st[key1] = torch.zeros_like(st[key0])
+        b1, b2 = getattr(opt, "betas", (0.0, 0.0))
+        K.opt_dense(opt.kind, table, seg, r2s, st[key0], st.get(key1), opt.lr, opt.momentum,
+                    opt.dampening, b1, b2, getattr(opt, "eps", 0.0), opt.weight_decay, step_no)
+
+    def _update_relation(self, opt, rel_table: torch.Tensor, d_rel: torch.Tensor, step_no: int,
+                         ws: K.Workspace) -> None:
+        st = self._opt_state
+        if opt.kind != L.OPT_SGD and "rel_s0" not in st:
+            st["rel_s0"] = torch.zeros_like(d_rel)
+            if opt.kind == L.OPT_ADAMW:
+                st["rel_s1"] = torch.zeros_like(d_rel)
+        b1, b2 = getattr(opt, "betas", (0.0, 0.0))
+        K.opt_dense(opt.kind, rel_table, d_rel, None, st.get("rel_s0"), st.get("rel_s1"), opt.lr,
+                    opt.momentum, opt.dampening, b1, b2, getattr(opt, "eps", 0.0),
+                    opt.weight_decay, step_no)
+
+
+# ---------------------------------------------------------------------------
+# ScoreMoving
+# ---------------------------------------------------------------------------
+class ScoreMovingBessKGE(BessKGE):
+    """Negatives are scored on the shard that stores them; queries are
+    replicated (AllGather) and the SCORES travel back (AllToAll) — reference
+    bess.py:471-603.  The candidate rows are read in place from the shard
+    through the index list (fused gather + score), so the [Q, Nn, D] negative
+    tensor of the reference is never materialised.  Inference only."""
+
+    def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
+             optimizer) -> Dict[str, Any]:
+        if optimizer is not None:
+            raise NotImplementedError("ScoreMovingBessKGE is inference-only in this build")
+        ws, pl = self._setup()
+        if pl.distributed:
+            raise NotImplementedError("ScoreMovingBessKGE: distributed mode not implemented yet")
+        dev = ws.device
+        ent, rel_table = self._tables()
+        n = self.sharding.n_shard
+        L_rows = head.shape[0]
+        bps = L_rows // n
+        p = head.shape[-1]
+        B, Nn = negative.shape[-2], negative.shape[-1]
+        S = n * p
+        W = ent.shape[-1]
+        cfg = self.score_fn.kernel_cfg()
+        dt = L.dtype_code(ent.dtype)
+        tdt = ent.dtype
+        scheme = self.negative_sampler.corruption_scheme
+        flat = self.negative_sampler.flat_negative_format
+        triple_based = isinstance(self.negative_sampler, TripleBasedShardedNegativeSampler)
+        shared = bool(self.score_fn.negative_sample_sharing)
+
+        h2 = _as_i32(head).reshape(L_rows, S)
+        t2 = _as_i32(tail).reshape(L_rows, S)
+        gidx = self._stage("gidx", torch.cat([h2, t2], dim=1), torch.int32, dev)
+        rel = self._stage("rel", relation.reshape(L_rows, S), torch.int32, dev)
+        nidx = self._stage("nidx", negative.reshape(L_rows, n, B, Nn), torch.int32, dev)
+        tw = self._stage("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
+                         torch.float32, dev)
+        nmask = None
+        if negative_mask is not None:
+            nmask = self._stage("nmask", negative_mask.reshape(L_rows, negative_mask.shape[1], -1),
+                                torch.bool, dev)
+        tmask = self._stage("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
+                            torch.bool, dev)
+        one = ws.get("one", (1,), torch.float32)
+        one.fill_(1.0)
+
+        # candidates per (scoring shard r): X columns contributed to every query
+        if flat and triple_based:
+            X = Nn  # one replicated list (bess.py:511-517)
+        elif flat:
+            X = n * Nn if scheme != "ht" else n * Nn  # all destinations' lists are shared
+        else:
+            X = Nn
+        N = n * X
+        H = ws.get("H", (n, S, W), tdt)
+        T = ws.get("TN", (n, n, p, W), tdt)  # received tails [replica][src][p]
+        nvec = K.call("bess_query_nvec", L.C.byref(cfg))
+        qv = ws.get("qv", (n * S, nvec, W), torch.float32)
+        need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
+        aux = ws.get("aux", (n * S, N), torch.float32) if need_aux else None
+        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+
+        n_out = bps * n
+        pos_out = torch.empty(n_out * S, dtype=torch.float32, device=dev)
+        neg_out = torch.empty(n_out * S, N, dtype=torch.float32, device=dev)
+        loss_out = (torch.empty(n_out, dtype=torch.float32, device=dev)
+                    if self.loss_fn is not None else None)
+        acc: Dict[str, List] = {}
+        half = p // 2
+
+        for s in range(bps):
+            base = s * n
+            for r in range(n):
+                K.gather_route(ent[r], gidx[base + r], S, p, H[r], [T[j].data_ptr() for j in range(n)], r)
+            pos = pos_out[base * S:(base + n) * S]
+            neg = neg_out[base * S:(base + n) * S]  # [n*S, N] rows ordered (replica j, q)
+            rel_all = rel[base:base + n].reshape(-1)  # [n*S]
+            Hall = H.view(n * S, W)
+            Tall = T.view(n * S, W)
+            K.triple_fwd(cfg, dt, L.rows(Hall), L.rows(Tall), rel_table, rel_all, L.IDENT, n * S,
+                         pos, L.IDENT)
+            # (mode, query map over the n*S queries, fixed source)
+            if scheme == "t":
+                groups = [(L.MODE_TAILS, L.IDENT, n * S, Hall, 0)]
+            elif scheme == "h":
+                groups = [(L.MODE_HEADS, L.IDENT, n * S, Tall, 0)]
+            else:
+                groups = [
+                    (L.MODE_HEADS, L.rowmap(half, p, 0), n * n * half, Tall, 0),
+                    (L.MODE_TAILS, L.rowmap(half, p, half), n * n * half, Hall, 1),
+                ]
+            for mode, qmap, nq, fixed_buf, bsel in groups:
+                K.prologue_fwd(cfg, dt, mode, L.rows(fixed_buf, rmap=qmap), rel_table, rel_all,
+                               qmap, nq, qv)
+                for r in range(n):
+                    idx_r = nidx[base + r]  # [n(dst), B, Nn]
+                    table = ent[r]
+                    if flat:
+                        if triple_based:
+                            # replicated list; "ht": b selects heads / tails list
+                            sel = idx_r[0, bsel if scheme == "ht" else 0]
+                            n_c = Nn
+                        elif scheme == "ht":
+                            sel = idx_r[:, bsel].contiguous().view(-1)
+                            n_c = n * Nn
+                        else:
+                            sel = idx_r.reshape(-1)
+                            n_c = n * Nn
+                        cand = L.rows(table, idx=sel)
+                        scale = None
+                        if need_scale:
+                            scale = ws.get("cand_scale", (n_c,), torch.float32)
+                            K.cand_inv_norm(dt, cand, n_c, W, scale)
+                        K.shared_fwd(cfg, dt, mode, qv, nq, cand, scale, n_c, neg, qmap, N, r * X,
+                                     aux)
+                    else:
+                        if shared:
+                            raise NotImplementedError(
+                                "ScoreMoving with non-flat shared negatives is not implemented"
+                            )
+                        # query at position (j, q): its Nn candidates are idx_r[j, q, :]
+                        cand = L.rows(table, idx=idx_r.reshape(-1))
+                        K.pertriple_fwd(cfg, dt, mode, qv, nq, cand, Nn, Nn, neg, qmap, N, r * X,
+                                        aux)
+            for r in range(n):
+                o = base + r
+                pos_r, neg_r = pos[r * S:(r + 1) * S], neg[r * S:(r + 1) * S]
+                if nmask is not None:
+                    EmbeddingMovingBessKGE._mask_block(neg_r, S, N, p, n, X, nmask[o], flat,
+                                                       scheme, 0)
+                if self.loss_fn is not None:
+                    w = tw[o] if tw is not None else one
+                    loss, _, _ = self.loss_fn.fwd_bwd(pos_r, neg_r, w)
+                    loss_out[o] = loss
+                if self.evaluation is not None:
+                    self._finish_metrics({}, pos_r, neg_r, tmask[o] if tmask is not None else None,
+                                         acc)
+        out: Dict[str, Any] = {}
+        if self.return_scores:
+            out["positive_score"] = pos_out if tdt == torch.float32 else pos_out.to(tdt)
+            out["negative_score"] = neg_out if tdt == torch.float32 else neg_out.to(tdt)
+        if loss_out is not None:
+            out["loss"] = loss_out
+        if "ranks" in acc:
+            out["ranks"] = torch.cat(acc["ranks"])
+        if "metrics" in acc:
+            out["metrics"] = torch.cat(acc["metrics"], dim=0)
+        return out
+
+
+# ---------------------------------------------------------------------------
+# training wrapper (the B200 counterpart of poptorch.trainingModel)
+# ---------------------------------------------------------------------------
+class TrainingModel:
+    """Callable returned by `training_model`: one call = `batches_per_step`
+    fused forward + backward + optimizer steps; returns the forward dict."""
+
+    def __init__(self, model: BessKGE, optimizer: Union[SGD, AdamW],
+                 relation_grad_reduction: str = "mean") -> None:
+        if relation_grad_reduction not in ("mean", "sum"):
+            raise ValueError("relation_grad_reduction must be 'mean' or 'sum'")
+        self.model = model
+        self.optimizer = optimizer
+        self.optimizer.relation_grad_reduction = relation_grad_reduction
+
+    def __call__(self, head, relation, tail, negative, triple_mask=None, triple_weight=None,
+                 negative_mask=None) -> Dict[str, Any]:
+        return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
+                               negative_mask, optimizer=self.optimizer)
+
+
+def training_model(model: BessKGE, optimizer: Union[SGD, AdamW],
+                   relation_grad_reduction: str = "mean") -> TrainingModel:
+    """Counterpart of `poptorch.trainingModel(model, options, optimizer)`
+    (reference notebooks, e.g. 1_biokg cell 28).  `relation_grad_reduction`:
+    how the replicated relation table's gradient is combined over replicas
+    ("mean" = PopTorch default, "sum")."""
+    return TrainingModel(model, optimizer, relation_grad_reduction)
+
+
+class TopKQueryBessKGE(torch.nn.Module):
+    """Placeholder until the top-k path is wired (next milestone)."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__()
+        raise NotImplementedError("TopKQueryBessKGE is not implemented yet in this build")

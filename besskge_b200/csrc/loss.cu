@@ -1,0 +1,337 @@
+// Score post-processing: BAD_NEGATIVE_SCORE masks, fused loss forward +
+// score-gradient, ranks, deterministic sums, small utilities.
+// One CTA per query row of the [S, N] negative-score matrix.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace bess {
+
+constexpr int L_THREADS = 256;
+
+// logsigmoid(x) = min(x, 0) - log1p(exp(-|x|))
+BESS_D float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+BESS_D float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(L_THREADS) mask_add_kernel(float* score, int n_row, int n_col,
+                                                              int64_t ld, const uint8_t* mask,
+                                                              int64_t ld_mask, int mask_rows,
+                                                              int flag, float value) {
+  const int r = blockIdx.x;
+  const uint8_t* m = mask + (int64_t)(mask_rows == 1 ? 0 : r) * ld_mask;
+  float* s = score + (int64_t)r * ld;
+  for (int c = threadIdx.x; c < n_col; c += blockDim.x)
+    if ((m[c] != 0) == (flag != 0)) s[c] += value;
+}
+
+// augment_negative: column hit for row r (bess.py:201-226).  Rows are grouped in
+// blocks of `group` (= positive_per_partition for "ht", else all rows); inside a
+// block the pattern of the first `half_group` rows repeats ("ht": both halves
+// use the mask of the first half).  col = step * ((r / group) * half_group + (r % group) % half_group)
+__global__ void mask_diag_kernel(float* score, int n_row, int64_t ld, int step, int half_group,
+                                 int group, float value, int n_col) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_row) return;
+  int base = r;
+  if (group > 0) base = (r / group) * half_group + (r % group) % half_group;
+  const int64_t col = (int64_t)step * base;
+  if (col < n_col) score[(int64_t)r * ld + col] += value;
+}
+
+// ---------------------------------------------------------------------------
+// Loss forward + gradient w.r.t. scores.
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(L_THREADS) loss_kernel(float margin, int adversarial,
+                                                          float adv_scale, float loss_scale,
+                                                          float ce_shift, const float* pos,
+                                                          float* neg, int n, int n_neg, int64_t ld,
+                                                          const float* weight, int weight_n,
+                                                          float* row_loss, float* d_pos,
+                                                          float* d_neg) {
+  __shared__ float red[L_THREADS / 32];
+  const int r = blockIdx.x;
+  const float* nrow = neg + (int64_t)r * ld;
+  float* grow = d_neg + (int64_t)r * ld;
+  const float w = weight_n == 1 ? weight[0] : weight[r];
+  const float p = pos[r];
+
+  if (KIND == BESS_LOSS_SOFTMAX_CE) {
+    // scores adjusted in place by log(E-1) - log(N) (loss.py:233-237), then
+    // cross entropy of [pos, neg...] against class 0
+    float mx = p;
+    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) {
+      const float v = nrow[c] + ce_shift;
+      neg[(int64_t)r * ld + c] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = block_max<L_THREADS>(mx, red);
+    float se = 0.f;
+    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) se += expf(neg[(int64_t)r * ld + c] - mx);
+    se = block_sum<L_THREADS>(se, red) + expf(p - mx);
+    const float lse = mx + logf(se);
+    for (int c = threadIdx.x; c < n_neg; c += L_THREADS)
+      grow[c] = loss_scale * w * expf(neg[(int64_t)r * ld + c] - lse);
+    if (threadIdx.x == 0) {
+      row_loss[r] = loss_scale * w * (lse - p);
+      d_pos[r] = loss_scale * w * (expf(p - lse) - 1.f);
+    }
+    return;
+  }
+
+  // negative weights: softmax(adv_scale * neg) (detached) or 1/N (loss.py:28-51)
+  float mx = 0.f, inv_se = 1.f / (float)n_neg;
+  if (adversarial) {
+    mx = -CUDART_INF_F;
+    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) mx = fmaxf(mx, adv_scale * nrow[c]);
+    mx = block_max<L_THREADS>(mx, red);
+    float se = 0.f;
+    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) se += expf(adv_scale * nrow[c] - mx);
+    se = block_sum<L_THREADS>(se, red);
+    inv_se = 1.f / se;
+  }
+  float part = 0.f, dp = 0.f;
+  for (int c = threadIdx.x; c < n_neg; c += L_THREADS) {
+    const float s = nrow[c];
+    const float wj = adversarial ? expf(adv_scale * s - mx) * inv_se : inv_se;
+    if (KIND == BESS_LOSS_LOGSIGMOID) {
+      part += wj * log_sigmoid(-s - margin);
+      // d/ds [-0.5 w wj logsigmoid(-s-m)] = 0.5 w wj sigmoid(s+m)
+      grow[c] = loss_scale * 0.5f * w * wj * sigmoidf_(s + margin);
+    } else {  // margin ranking: relu(s - pos + m)
+      const float a = s - p + margin;
+      const float on = a > 0.f ? 1.f : 0.f;
+      part += wj * fmaxf(a, 0.f);
+      const float g = loss_scale * w * wj * on;
+      grow[c] = g;
+      dp -= g;
+    }
+  }
+  part = block_sum<L_THREADS>(part, red);
+  if (KIND == BESS_LOSS_MARGIN_RANKING) dp = block_sum<L_THREADS>(dp, red);
+  if (threadIdx.x == 0) {
+    if (KIND == BESS_LOSS_LOGSIGMOID) {
+      row_loss[r] = loss_scale * (-0.5f) * w * (log_sigmoid(p + margin) + part);
+      d_pos[r] = loss_scale * (-0.5f) * w * sigmoidf_(-(p + margin));
+    } else {
+      row_loss[r] = loss_scale * w * part;
+      d_pos[r] = dp;
+    }
+  }
+}
+
+// single-CTA fixed-order sum
+__global__ void __launch_bounds__(1024) sum_kernel(const float* x, int n, float* out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) s += x[i];
+  s = block_sum<1024>(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// ranks_from_scores (metric.py:129-183)
+__global__ void __launch_bounds__(L_THREADS) rank_kernel(const float* pos, const float* neg, int n,
+                                                          int n_neg, int64_t ld, int mode,
+                                                          int worst_inf, float* rank) {
+  __shared__ float red[L_THREADS / 32];
+  const int r = blockIdx.x;
+  float p = pos[r];
+  if (isnan(p)) p = -CUDART_INF_F;  // pos_score.nan_to_num_(-inf)
+  const float* row = neg + (int64_t)r * ld;
+  float gt = 0.f, ge = 0.f;
+  for (int c = threadIdx.x; c < n_neg; c += L_THREADS) {
+    const float v = row[c];
+    gt += v > p ? 1.f : 0.f;
+    ge += v >= p ? 1.f : 0.f;
+  }
+  gt = block_sum<L_THREADS>(gt, red);
+  ge = block_sum<L_THREADS>(ge, red);
+  if (threadIdx.x == 0) {
+    float better;
+    bool worst;
+    if (mode == 0) { better = gt; worst = gt == (float)n_neg; }
+    else if (mode == 1) { better = ge; worst = ge == (float)n_neg; }
+    else { better = 0.5f * (gt + ge); worst = gt == (float)n_neg || ge == (float)n_neg; }
+    rank[r] = (worst_inf && worst) ? CUDART_INF_F : 1.f + better;
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+template <typename T>
+__global__ void cast_kernel(const float* src, T* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = Elem<T>::from_f(src[i]);
+}
+
+// running top-k merge (bess.py:807-814): one warp per query keeps its sorted
+// best list in shared memory and inserts the window's scores one lane-batch at
+// a time.  Ordering: score descending; ties keep the entry that came first
+// (current list before the new window, lower window column first), which is
+// the stable order of a descending sort of cat([window, current]) restricted
+// to ... see DESIGN.md (tie order of torch.topk is unspecified).
+constexpr int TK_MAXK = 64;
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* win_score, int64_t ld,
+                                                          int n_query, int n_win,
+                                                          const int32_t* win_ids, int64_t ld_ids,
+                                                          int win_id0, float* best_score,
+                                                          int32_t* best_id, int k) {
+  __shared__ float s_sc[4][TK_MAXK];
+  __shared__ int32_t s_id[4][TK_MAXK];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= n_query) return;
+  float* sc = s_sc[w];
+  int32_t* id = s_id[w];
+  for (int i = lane; i < k; i += 32) {
+    sc[i] = best_score[(int64_t)q * k + i];
+    id[i] = best_id[(int64_t)q * k + i];
+  }
+  __syncwarp();
+  const float* row = win_score + (int64_t)q * ld;
+  for (int c0 = 0; c0 < n_win; c0 += 32) {
+    const int c = c0 + lane;
+    float v = c < n_win ? row[c] : -CUDART_INF_F;
+    int32_t vid = 0;
+    if (c < n_win) vid = win_ids != nullptr ? win_ids[(ld_ids == 0 ? 0 : (int64_t)q * ld_ids) + c] : win_id0 + c;
+    // candidates that can enter the list (strictly better than the current worst)
+    unsigned pending = __ballot_sync(0xffffffffu, c < n_win && v > sc[k - 1]);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const float nv = __shfl_sync(0xffffffffu, v, src);
+      const int32_t nid = __shfl_sync(0xffffffffu, vid, src);
+      if (!(nv > sc[k - 1])) continue;  // list may have tightened since the ballot
+      // insertion position: first i with sc[i] < nv (ties stay behind existing entries)
+      int posn = k;
+      for (int i0 = 0; i0 < k; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, i < k && sc[i] < nv);
+        if (m) { posn = i0 + __ffs(m) - 1; break; }
+      }
+      // shift [posn, k-1) down by one (from the back), lanes cooperate in chunks
+      for (int i0 = ((k - 1 - posn + 31) / 32 - 1) * 32; i0 >= 0; i0 -= 32) {
+        const int i = posn + i0 + lane;  // element to move to i+1
+        float t = 0.f; int32_t ti = 0;
+        const bool act = i < k - 1;
+        if (act) { t = sc[i]; ti = id[i]; }
+        __syncwarp();
+        if (act) { sc[i + 1] = t; id[i + 1] = ti; }
+        __syncwarp();
+      }
+      if (lane == 0) { sc[posn] = nv; id[posn] = nid; }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < k; i += 32) {
+    best_score[(int64_t)q * k + i] = sc[i];
+    best_id[(int64_t)q * k + i] = id[i];
+  }
+}
+
+}  // namespace bess
+
+using namespace bess;
+
+extern "C" int bess_mask_add(float* score, int n_row, int n_col, int64_t ld, const uint8_t* mask,
+                             int64_t ld_mask, int mask_rows, int flag, float value, void* stream) {
+  if (n_row == 0 || n_col == 0) return BESS_OK;
+  BESS_CHECK_ARG(mask_rows == 1 || mask_rows == n_row, "mask rows %d vs %d", mask_rows, n_row);
+  mask_add_kernel<<<n_row, L_THREADS, 0, (cudaStream_t)stream>>>(score, n_row, n_col, ld, mask,
+                                                                 ld_mask, mask_rows, flag, value);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_mask_diag(float* score, int n_row, int64_t ld, int step, int half_group,
+                              int group, float value, void* stream) {
+  if (n_row == 0) return BESS_OK;
+  mask_diag_kernel<<<ceil_div(n_row, 256), 256, 0, (cudaStream_t)stream>>>(
+      score, n_row, ld, step, half_group, group, value, (int)ld);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float adv_scale,
+                                 float loss_scale, int64_t n_entity, const float* pos, float* neg,
+                                 int n, int n_neg, int64_t ld, const float* weight, int weight_n,
+                                 float* row_loss, float* d_pos, float* d_neg, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(n_neg > 0, "loss needs at least one negative");
+  BESS_CHECK_ARG(weight_n == 1 || weight_n == n, "triple_weight has %d entries, need 1 or %d", weight_n, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kind) {
+    case BESS_LOSS_LOGSIGMOID:
+      loss_kernel<BESS_LOSS_LOGSIGMOID><<<n, L_THREADS, 0, st>>>(margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg);
+      break;
+    case BESS_LOSS_MARGIN_RANKING:
+      loss_kernel<BESS_LOSS_MARGIN_RANKING><<<n, L_THREADS, 0, st>>>(margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg);
+      break;
+    case BESS_LOSS_SOFTMAX_CE: {
+      const float shift = (float)(log((double)(n_entity - 1)) - log((double)n_neg));
+      loss_kernel<BESS_LOSS_SOFTMAX_CE><<<n, L_THREADS, 0, st>>>(0.f, 0, 0.f, loss_scale, shift, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg);
+      break;
+    }
+    default:
+      bess_set_error("unknown loss kind %d", kind);
+      return BESS_ERR_INVALID_ARG;
+  }
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_sum_f32(const float* x, int n, float* out, void* stream) {
+  sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_rank_from_scores(const float* pos, const float* neg, int n, int n_neg,
+                                     int64_t ld, int mode, int worst_rank_infty, float* rank,
+                                     void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(mode >= 0 && mode <= 2, "rank mode %d", mode);
+  rank_kernel<<<n, L_THREADS, 0, (cudaStream_t)stream>>>(pos, neg, n, n_neg, ld, mode,
+                                                          worst_rank_infty, rank);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_fill_f32(float* p, int64_t n, float v, void* stream) {
+  if (n == 0) return BESS_OK;
+  fill_f32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+extern "C" int bess_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream) {
+  if (n == 0) return BESS_OK;
+  fill_i32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+extern "C" int bess_cast_from_f32(const float* src, void* dst, int dtype, int64_t n, void* stream) {
+  if (n == 0) return BESS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BESS_F16) cast_kernel<__half><<<ceil_div(n, 256), 256, 0, st>>>(src, (__half*)dst, n);
+  else if (dtype == BESS_BF16) cast_kernel<__nv_bfloat16><<<ceil_div(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, n);
+  else cast_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(src, (float*)dst, n);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_topk_merge(const float* win_score, int64_t ld, int n_query, int n_win,
+                               const int32_t* win_ids, int64_t ld_ids, int win_id0,
+                               float* best_score, int32_t* best_id, int k, void* stream) {
+  if (n_query == 0 || n_win == 0) return BESS_OK;
+  BESS_CHECK_ARG(k >= 1 && k <= TK_MAXK, "k=%d out of range (max %d)", k, TK_MAXK);
+  topk_merge_kernel<<<ceil_div(n_query, 4), 128, 0, (cudaStream_t)stream>>>(
+      win_score, ld, n_query, n_win, win_ids, ld_ids, win_id0, best_score, best_id, k);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}

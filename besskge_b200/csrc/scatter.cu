@@ -1,0 +1,379 @@
+// Backward tail of the BESS step: deterministic segmented scatter-add of the
+// gathered-row gradients into the shard, fused with the optimizer update.
+//
+// The reference has no such code: `entity_embedding[gather_idx]` (bess.py:333)
+// is differentiated by (Pop)Torch autograd, which materialises a DENSE
+// [Es, D] gradient (index_put_ accumulate) that the dense optimizer then
+// consumes.  Here the gradient never becomes dense:
+//   1. stable LSD radix sort of the step's gather indices (key = local row);
+//   2. one warp per run of equal keys sums its fp32 gradient rows in sorted
+//      (= gather) order -> bit-reproducible, no atomics;
+//   3. plain SGD updates the touched rows in place (identical to the dense
+//      update, untouched rows see g = 0); momentum / AdamW run a dense
+//      streaming pass with the segment sums scattered in (dense semantics).
+#include "common.cuh"
+
+namespace bess {
+
+// ---------------------------------------------------------------------------
+// Stable LSD radix sort, 8 bits per pass, (key, position) pairs.
+// ---------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // keys per block
+constexpr int RS_RADIX = 256;
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const int32_t* keys, int n, int shift,
+                                                              int n_blocks, int32_t* block_hist) {
+  __shared__ int hist[RS_RADIX];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const int i = base + it * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&hist[(keys[i] >> shift) & (RS_RADIX - 1)], 1);
+  }
+  __syncthreads();
+  block_hist[threadIdx.x * n_blocks + blockIdx.x] = hist[threadIdx.x];  // digit-major
+}
+
+// exclusive scan of m ints in one CTA (m = 256 * n_blocks)
+__global__ void __launch_bounds__(1024) rs_scan_kernel(int32_t* data, int m) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < m; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < m ? data[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      warp_tot[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int warp_off = w == 0 ? 0 : warp_tot[w - 1];
+    if (i < m) data[i] = carry + warp_off + x - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_off + x;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(
+    const int32_t* keys_in, const int32_t* vals_in /* null: identity */, int n, int shift,
+    int n_blocks, const int32_t* block_off, int32_t* keys_out, int32_t* vals_out) {
+  __shared__ int warp_cnt[RS_THREADS / 32][RS_RADIX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_RADIX; i += RS_THREADS)
+    (&warp_cnt[0][0])[i] = 0;
+  __syncthreads();
+  // warp w owns the contiguous keys [base + w*256, base + (w+1)*256), 32 at a time
+  const int base = blockIdx.x * RS_TILE + w * (RS_ITEMS * 32);
+  int key[RS_ITEMS], digit[RS_ITEMS];
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const int i = base + it * 32 + lane;
+    key[it] = i < n ? keys_in[i] : 0;
+    digit[it] = i < n ? ((key[it] >> shift) & (RS_RADIX - 1)) : RS_RADIX;  // RS_RADIX = inactive
+  }
+  // pass A: per-warp digit counts
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const unsigned peers = __match_any_sync(0xffffffffu, digit[it]);
+    if (digit[it] < RS_RADIX && lane == __ffs(peers) - 1) warp_cnt[w][digit[it]] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // pass B: thread d turns the counts of digit d into running global offsets
+  {
+    const int d = threadIdx.x;
+    int run = block_off[d * n_blocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_THREADS / 32; ++ww) {
+      const int c = warp_cnt[ww][d];
+      warp_cnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // pass C: stable placement
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const int i = base + it * 32 + lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit[it]);
+    if (digit[it] < RS_RADIX) {
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int pos = warp_cnt[w][digit[it]] + rank;
+      keys_out[pos] = key[it];
+      vals_out[pos] = vals_in != nullptr ? vals_in[i] : i;
+    }
+    __syncwarp();
+    if (digit[it] < RS_RADIX && lane == __ffs(peers) - 1) warp_cnt[w][digit[it]] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Segmented reduce over sorted keys.  Warp per sorted position; only the
+// first position of each run works.
+// ---------------------------------------------------------------------------
+struct GradSrc {
+  const float* local;
+  const float* dst;
+  int n_local;
+  int per_dst;
+  int64_t dst_stride_rows;
+  int row_elems;
+};
+BESS_D const float* grad_row(const GradSrc& g, int pos) {
+  if (pos < g.n_local) return g.local + (int64_t)pos * g.row_elems;
+  const int y = pos - g.n_local;
+  const int d = y / g.per_dst;
+  const int i = y - d * g.per_dst;
+  return g.dst + ((int64_t)d * g.dst_stride_rows + i) * g.row_elems;
+}
+
+// MODE 0: SGD update of the table row; MODE 1: store the segment sum
+template <int MODE, typename T>
+__global__ void __launch_bounds__(256) segment_kernel(T* table, int64_t pitch,
+                                                       const int32_t* sorted_keys,
+                                                       const int32_t* perm, int n, GradSrc g,
+                                                       float lr, float* seg_grad,
+                                                       int32_t* row_to_seg) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int key = sorted_keys[wid];
+  if (wid > 0 && sorted_keys[wid - 1] == key) return;  // not a run head
+  int end = wid + 1;
+  while (end < n && sorted_keys[end] == key) ++end;
+  const int W = g.row_elems;
+  if (MODE == 1 && lane == 0) row_to_seg[key] = wid;
+  for (int k0 = lane * 4; k0 < W; k0 += 128) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = wid; i < end; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(grad_row(g, perm[i]) + k0);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    if (MODE == 0) {
+      T* row = table + (int64_t)key * pitch + k0;
+      row[0] = Elem<T>::from_f(Elem<T>::to_f(row[0]) - lr * s.x);
+      row[1] = Elem<T>::from_f(Elem<T>::to_f(row[1]) - lr * s.y);
+      row[2] = Elem<T>::from_f(Elem<T>::to_f(row[2]) - lr * s.z);
+      row[3] = Elem<T>::from_f(Elem<T>::to_f(row[3]) - lr * s.w);
+    } else {
+      *reinterpret_cast<float4*>(seg_grad + (int64_t)wid * W + k0) = s;
+    }
+  }
+}
+
+// Dense optimizer pass (torch.optim.SGD with momentum / AdamW semantics).
+template <typename T>
+__global__ void __launch_bounds__(256) opt_dense_kernel(int kind, T* table, int64_t pitch,
+                                                         int n_rows, int W, const float* seg_grad,
+                                                         const int32_t* row_to_seg, float* state0,
+                                                         float* state1, float lr, float momentum,
+                                                         float dampening, float beta1, float beta2,
+                                                         float eps, float wd, float bc1, float bc2,
+                                                         int first_step) {
+  const int64_t total = (int64_t)n_rows * W;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(t / W), k = (int)(t - (int64_t)row * W);
+    const int seg = row_to_seg != nullptr ? row_to_seg[row] : row;
+    float gval = seg >= 0 ? seg_grad[(int64_t)seg * W + k] : 0.f;
+    T* pw = table + (int64_t)row * pitch + k;
+    float wv = Elem<T>::to_f(*pw);
+    if (kind == BESS_OPT_SGD) {
+      gval += wd * wv;
+      wv -= lr * gval;
+    } else if (kind == BESS_OPT_SGDM) {
+      gval += wd * wv;
+      float b = first_step ? gval : momentum * state0[t] + (1.f - dampening) * gval;
+      state0[t] = b;
+      wv -= lr * b;
+    } else {  // AdamW (decoupled weight decay), torch.optim.AdamW
+      wv *= 1.f - lr * wd;
+      const float m = beta1 * state0[t] + (1.f - beta1) * gval;
+      const float v = beta2 * state1[t] + (1.f - beta2) * gval * gval;
+      state0[t] = m; state1[t] = v;
+      const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+      wv -= (lr / bc1) * (m / denom);
+    }
+    *pw = Elem<T>::from_f(wv);
+  }
+}
+
+// Relation-table gradient: CTA (relation r, 128-column block) reduces the sorted
+// run of per-query rows with 8 warps in a fixed interleaved order.
+__global__ void __launch_bounds__(256) relation_reduce_kernel(const float* rows, int width,
+                                                               const int32_t* sorted_rel,
+                                                               const int32_t* perm, int n,
+                                                               float* d_table) {
+  __shared__ float part[8][128];
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // run [lo, hi) of relation r by binary search (warp-uniform)
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_rel[mid] < r) lo = mid + 1; else hi = mid; }
+  const int start = lo;
+  hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted_rel[mid] <= r) lo = mid + 1; else hi = mid; }
+  const int end = lo;
+  const int k0 = blockIdx.y * 128 + lane * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k0 < width) {
+    for (int i = start + w; i < end; i += 8) {
+      const float* row = rows + (int64_t)perm[i] * width + k0;
+      if ((width & 3) == 0) {  // rows 16-byte aligned
+        const float4 v = *reinterpret_cast<const float4*>(row);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      } else {
+        s.x += row[0];
+        if (k0 + 1 < width) s.y += row[1];
+        if (k0 + 2 < width) s.z += row[2];
+        if (k0 + 3 < width) s.w += row[3];
+      }
+    }
+  }
+  part[w][lane * 4 + 0] = s.x; part[w][lane * 4 + 1] = s.y;
+  part[w][lane * 4 + 2] = s.z; part[w][lane * 4 + 3] = s.w;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int k = blockIdx.y * 128 + threadIdx.x;
+    if (k < width) {
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) t += part[ww][threadIdx.x];
+      d_table[(int64_t)r * width + k] = t;
+    }
+  }
+}
+
+}  // namespace bess
+
+using namespace bess;
+
+extern "C" int64_t bess_sort_workspace(int n) {
+  const int n_blocks = ceil_div(n > 0 ? n : 1, RS_TILE);
+  // block histogram + two ping-pong (key, value) buffers
+  return (int64_t)RS_RADIX * n_blocks * 4 + 4 * (int64_t)(n > 0 ? n : 1) * 4 + 256;
+}
+
+extern "C" int bess_sort_keys(const int32_t* keys, int n, int key_bits, int32_t* keys_out,
+                              int32_t* perm_out, void* workspace, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(key_bits >= 1 && key_bits <= 31, "key_bits %d", key_bits);
+  BESS_CHECK_ARG(workspace != nullptr, "workspace required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_blocks = ceil_div(n, RS_TILE);
+  int32_t* hist = static_cast<int32_t*>(workspace);
+  int32_t* buf = hist + (((int64_t)RS_RADIX * n_blocks + 63) / 64) * 64;
+  int32_t* kA = buf; int32_t* vA = buf + n; int32_t* kB = buf + 2 * (int64_t)n; int32_t* vB = buf + 3 * (int64_t)n;
+  const int passes = (key_bits + 7) / 8;
+  const int32_t* kin = keys; const int32_t* vin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const bool last = p == passes - 1;
+    int32_t* kout = last ? keys_out : ((p & 1) ? kB : kA);
+    int32_t* vout = last ? perm_out : ((p & 1) ? vB : vA);
+    rs_hist_kernel<<<n_blocks, RS_THREADS, 0, st>>>(kin, n, 8 * p, n_blocks, hist);
+    rs_scan_kernel<<<1, 1024, 0, st>>>(hist, RS_RADIX * n_blocks);
+    rs_scatter_kernel<<<n_blocks, RS_THREADS, 0, st>>>(kin, vin, n, 8 * p, n_blocks, hist, kout, vout);
+    kin = kout; vin = vout;
+  }
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+static GradSrc make_src(int row_elems, int n_local, int per_dst, const float* grad_local,
+                        const float* grad_dst, int64_t dst_stride_rows) {
+  GradSrc g;
+  g.local = grad_local; g.dst = grad_dst; g.n_local = n_local; g.per_dst = per_dst > 0 ? per_dst : 1;
+  g.dst_stride_rows = dst_stride_rows; g.row_elems = row_elems;
+  return g;
+}
+
+extern "C" int bess_scatter_sgd(void* table, int64_t table_pitch, int dtype, int row_elems,
+                                const int32_t* sorted_keys, const int32_t* perm, int n, int n_local,
+                                int per_dst, const float* grad_local, const float* grad_dst,
+                                int64_t dst_stride_rows, float lr, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(row_elems % 4 == 0, "row_elems must be a multiple of 4");
+  const GradSrc g = make_src(row_elems, n_local, per_dst, grad_local, grad_dst, dst_stride_rows);
+  const int blocks = ceil_div((int64_t)n * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case BESS_F32: segment_kernel<0, float><<<blocks, 256, 0, st>>>((float*)table, table_pitch, sorted_keys, perm, n, g, lr, nullptr, nullptr); break;
+    case BESS_F16: segment_kernel<0, __half><<<blocks, 256, 0, st>>>((__half*)table, table_pitch, sorted_keys, perm, n, g, lr, nullptr, nullptr); break;
+    case BESS_BF16: segment_kernel<0, __nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)table, table_pitch, sorted_keys, perm, n, g, lr, nullptr, nullptr); break;
+    default: bess_set_error("unknown dtype %d", dtype); return BESS_ERR_INVALID_ARG;
+  }
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_scatter_collect(int row_elems, const int32_t* sorted_keys, const int32_t* perm,
+                                    int n, int n_local, int per_dst, const float* grad_local,
+                                    const float* grad_dst, int64_t dst_stride_rows, float* seg_grad,
+                                    int32_t* row_to_seg, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(row_elems % 4 == 0, "row_elems must be a multiple of 4");
+  const GradSrc g = make_src(row_elems, n_local, per_dst, grad_local, grad_dst, dst_stride_rows);
+  const int blocks = ceil_div((int64_t)n * 32, 256);
+  segment_kernel<1, float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      nullptr, 0, sorted_keys, perm, n, g, 0.f, seg_grad, row_to_seg);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_opt_dense(int kind, void* table, int64_t table_pitch, int dtype, int n_rows,
+                              int row_elems, const float* seg_grad, const int32_t* row_to_seg,
+                              float* state0, float* state1, float lr, float momentum,
+                              float dampening, float beta1, float beta2, float eps,
+                              float weight_decay, int step, void* stream) {
+  if (n_rows == 0) return BESS_OK;
+  BESS_CHECK_ARG(kind >= BESS_OPT_SGD && kind <= BESS_OPT_ADAMW, "optimizer kind %d", kind);
+  if (kind != BESS_OPT_SGD) BESS_CHECK_ARG(state0 != nullptr, "optimizer state missing");
+  if (kind == BESS_OPT_ADAMW) BESS_CHECK_ARG(state1 != nullptr, "optimizer state missing");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const int64_t total = (int64_t)n_rows * row_elems;
+  int blocks = ceil_div(total, 256);
+  if (blocks > kNumSM * 16) blocks = kNumSM * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int first = step <= 1 ? 1 : 0;
+  switch (dtype) {
+    case BESS_F32: opt_dense_kernel<float><<<blocks, 256, 0, st>>>(kind, (float*)table, table_pitch, n_rows, row_elems, seg_grad, row_to_seg, state0, state1, lr, momentum, dampening, beta1, beta2, eps, weight_decay, bc1, bc2, first); break;
+    case BESS_F16: opt_dense_kernel<__half><<<blocks, 256, 0, st>>>(kind, (__half*)table, table_pitch, n_rows, row_elems, seg_grad, row_to_seg, state0, state1, lr, momentum, dampening, beta1, beta2, eps, weight_decay, bc1, bc2, first); break;
+    case BESS_BF16: opt_dense_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(kind, (__nv_bfloat16*)table, table_pitch, n_rows, row_elems, seg_grad, row_to_seg, state0, state1, lr, momentum, dampening, beta1, beta2, eps, weight_decay, bc1, bc2, first); break;
+    default: bess_set_error("unknown dtype %d", dtype); return BESS_ERR_INVALID_ARG;
+  }
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_relation_grad_reduce(const float* d_rel_rows, int width,
+                                         const int32_t* sorted_rel, const int32_t* perm, int n,
+                                         int n_rel, float* d_table, void* stream) {
+  if (n_rel == 0) return BESS_OK;
+  dim3 grid(n_rel, ceil_div(width, 128));
+  relation_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_rel_rows, width, sorted_rel,
+                                                                 perm, n, d_table);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}

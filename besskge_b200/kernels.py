@@ -1,0 +1,247 @@
+"""Pythonic launchers over the C-ABI (`_lib`).  Every function enqueues CUDA
+work on torch's current stream of the tensors' device and returns immediately.
+Inputs must be CUDA tensors; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import IDENT, RowMap, Rows, ScoreCfg, call, dtype_code, ptr, require_cuda, rowmap, rows
+
+BAD_NEGATIVE_SCORE = -50000.0
+
+
+def _st(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class Workspace:
+    """Persistent device buffers keyed by name (grown on demand, never shrunk),
+    so the steady-state step performs no allocation."""
+
+    def __init__(self, device: torch.device) -> None:
+        self.device = device
+        self._buf: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        n = int(math.prod(shape)) if len(shape) else 1
+        cur = self._buf.get(name)
+        if cur is None or cur.dtype != dtype or cur.numel() < n:
+            cur = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._buf[name] = cur
+        return cur[:n].view(*shape)
+
+    def bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self._buf.values())
+
+
+# ------------------------------------------------------------------ gather --
+def gather_route(table: torch.Tensor, idx: torch.Tensor, n_local: int, per_dst: int,
+                 local_out: Optional[torch.Tensor], dst_ptrs: Sequence[int], slot: int) -> None:
+    """table [Es, W]; idx int32 [n_local + len(dst_ptrs) * per_dst]."""
+    require_cuda(table, idx)
+    n_dst = len(dst_ptrs)
+    arr = (C.c_void_p * max(n_dst, 1))(*[C.c_void_p(p) for p in dst_ptrs])
+    call("bess_gather_route", table.data_ptr(), table.stride(0), dtype_code(table.dtype),
+         table.shape[1], idx.data_ptr(), n_local, n_dst, per_dst, ptr(local_out), arr, slot,
+         _st(table))
+
+
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor) -> None:
+    require_cuda(table, idx, out)
+    call("bess_gather_rows", table.data_ptr(), table.stride(0), dtype_code(table.dtype),
+         table.shape[1], idx.data_ptr(), idx.numel(), out.data_ptr(), _st(table))
+
+
+# ------------------------------------------------------------- score ops ----
+def triple_fwd(cfg: ScoreCfg, dt: int, head: Rows, tail: Rows, rel_table: torch.Tensor,
+               rel_id: torch.Tensor, rel_map: RowMap, n: int, score: torch.Tensor,
+               score_map: RowMap) -> None:
+    call("bess_score_triple_fwd", C.byref(cfg), dt, head, tail, rel_table.data_ptr(),
+         rel_id.data_ptr(), rel_map, n, score.data_ptr(), score_map, _st(score))
+
+
+def triple_bwd(cfg: ScoreCfg, dt: int, head: Rows, tail: Rows, rel_table: torch.Tensor,
+               rel_id: torch.Tensor, rel_map: RowMap, n: int, score: torch.Tensor,
+               d_score: torch.Tensor, score_map: RowMap, d_head: Rows, d_tail: Rows,
+               d_rel: torch.Tensor, add_head: bool, add_tail: bool, add_rel: bool) -> None:
+    call("bess_score_triple_bwd", C.byref(cfg), dt, head, tail, rel_table.data_ptr(),
+         rel_id.data_ptr(), rel_map, n, score.data_ptr(), d_score.data_ptr(), score_map, d_head,
+         d_tail, d_rel.data_ptr(), int(add_head), int(add_tail), int(add_rel), _st(score))
+
+
+def prologue_fwd(cfg: ScoreCfg, dt: int, mode: int, fixed: Rows, rel_table: torch.Tensor,
+                 rel_id: torch.Tensor, rel_map: RowMap, n: int, qv: torch.Tensor) -> None:
+    call("bess_query_prologue_fwd", C.byref(cfg), dt, mode, fixed, rel_table.data_ptr(),
+         rel_id.data_ptr(), rel_map, n, qv.data_ptr(), _st(qv))
+
+
+def prologue_bwd(cfg: ScoreCfg, dt: int, mode: int, fixed: Rows, rel_table: torch.Tensor,
+                 rel_id: torch.Tensor, rel_map: RowMap, n: int, d_qv: torch.Tensor, d_fixed: Rows,
+                 d_rel: torch.Tensor, add_fixed: bool, add_rel: bool) -> None:
+    call("bess_query_prologue_bwd", C.byref(cfg), dt, mode, fixed, rel_table.data_ptr(),
+         rel_id.data_ptr(), rel_map, n, d_qv.data_ptr(), d_fixed, d_rel.data_ptr(), int(add_fixed),
+         int(add_rel), _st(d_qv))
+
+
+def boxe_rel_finalize(cfg: ScoreCfg, dt: int, rel_table: torch.Tensor, rel_id: torch.Tensor,
+                      n: int, d_rel: torch.Tensor) -> None:
+    call("bess_boxe_rel_finalize", C.byref(cfg), dt, rel_table.data_ptr(), rel_id.data_ptr(), n,
+         d_rel.data_ptr(), _st(d_rel))
+
+
+def cand_inv_norm(dt: int, cand: Rows, n: int, width: int, out: torch.Tensor) -> None:
+    call("bess_cand_inv_norm", dt, cand, n, width, out.data_ptr(), _st(out))
+
+
+def cand_norm_bwd(dt: int, cand: Rows, n: int, width: int, inv_norm: torch.Tensor,
+                  d_cand: Rows) -> None:
+    call("bess_cand_norm_bwd", dt, cand, n, width, inv_norm.data_ptr(), d_cand, _st(inv_norm))
+
+
+def shared_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
+               cand_scale: Optional[torch.Tensor], n_cand: int, out: torch.Tensor,
+               score_map: RowMap, ld: int, col0: int, aux: Optional[torch.Tensor]) -> None:
+    call("bess_score_shared_fwd", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
+         ptr(cand_scale), n_cand, out.data_ptr(), score_map, ld, col0, ptr(aux), _st(out))
+
+
+def shared_bwd_query(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
+                     cand_scale: Optional[torch.Tensor], n_cand: int, score: torch.Tensor,
+                     d_score: torch.Tensor, score_map: RowMap, ld: int, col0: int,
+                     aux: Optional[torch.Tensor], d_qv: torch.Tensor) -> None:
+    call("bess_score_shared_bwd_query", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
+         ptr(cand_scale), n_cand, score.data_ptr(), d_score.data_ptr(), score_map, ld, col0,
+         ptr(aux), d_qv.data_ptr(), _st(d_qv))
+
+
+def shared_bwd_cand_workspace(cfg: ScoreCfg, n_query: int, n_cand: int) -> int:
+    return int(call("bess_shared_bwd_cand_workspace", C.byref(cfg), n_query, n_cand))
+
+
+def shared_bwd_cand(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
+                    cand_scale: Optional[torch.Tensor], n_cand: int, score: torch.Tensor,
+                    d_score: torch.Tensor, score_map: RowMap, ld: int, col0: int,
+                    aux: Optional[torch.Tensor], d_cand: Rows, workspace: torch.Tensor,
+                    add: bool = False) -> None:
+    call("bess_score_shared_bwd_cand", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
+         ptr(cand_scale), n_cand, score.data_ptr(), d_score.data_ptr(), score_map, ld, col0,
+         ptr(aux), d_cand, int(add), workspace.data_ptr(), _st(score))
+
+
+def pertriple_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
+                  q_stride: int, n_per: int, out: torch.Tensor, score_map: RowMap, ld: int,
+                  col0: int, aux: Optional[torch.Tensor]) -> None:
+    call("bess_score_pertriple_fwd", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
+         q_stride, n_per, out.data_ptr(), score_map, ld, col0, ptr(aux), _st(out))
+
+
+def pertriple_bwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
+                  q_stride: int, n_per: int, score: torch.Tensor, d_score: torch.Tensor,
+                  score_map: RowMap, ld: int, col0: int, aux: Optional[torch.Tensor],
+                  d_qv: torch.Tensor, d_cand: Rows) -> None:
+    call("bess_score_pertriple_bwd", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
+         q_stride, n_per, score.data_ptr(), d_score.data_ptr(), score_map, ld, col0, ptr(aux),
+         d_qv.data_ptr(), d_cand, _st(d_qv))
+
+
+# ---------------------------------------------------------- masks / loss ----
+def mask_add(score: torch.Tensor, n_row: int, n_col: int, ld: int, mask: torch.Tensor,
+             ld_mask: int, mask_rows: int, flag: bool, value: float, col_offset: int = 0) -> None:
+    """score[r, col_offset + c] += value where (mask[r or 0, c] != 0) == flag."""
+    call("bess_mask_add", score.data_ptr() + 4 * col_offset, n_row, n_col, ld, mask.data_ptr(),
+         ld_mask, mask_rows, int(flag), float(value), _st(score))
+
+
+def mask_diag(score: torch.Tensor, n_row: int, ld: int, step: int, half_group: int, group: int,
+              value: float) -> None:
+    call("bess_mask_diag", score.data_ptr(), n_row, ld, step, half_group, group, float(value),
+         _st(score))
+
+
+def loss_fwd_bwd(kind: int, margin: float, adversarial: bool, adv_scale: float, loss_scale: float,
+                 n_entity: int, pos: torch.Tensor, neg: torch.Tensor, n: int, n_neg: int, ld: int,
+                 weight: torch.Tensor, row_loss: torch.Tensor, d_pos: torch.Tensor,
+                 d_neg: torch.Tensor) -> None:
+    call("bess_loss_fwd_bwd", kind, float(margin), int(adversarial), float(adv_scale),
+         float(loss_scale), int(n_entity), pos.data_ptr(), neg.data_ptr(), n, n_neg, ld,
+         weight.data_ptr(), weight.numel(), row_loss.data_ptr(), d_pos.data_ptr(),
+         d_neg.data_ptr(), _st(pos))
+
+
+def sum_f32(x: torch.Tensor, n: int, out: torch.Tensor) -> None:
+    call("bess_sum_f32", x.data_ptr(), n, out.data_ptr(), _st(x))
+
+
+def rank_from_scores(pos: torch.Tensor, neg: torch.Tensor, n: int, n_neg: int, ld: int, mode: int,
+                     worst_inf: bool, rank: torch.Tensor) -> None:
+    call("bess_rank_from_scores", pos.data_ptr(), neg.data_ptr(), n, n_neg, ld, mode,
+         int(worst_inf), rank.data_ptr(), _st(pos))
+
+
+# ------------------------------------------------------- sort / scatter -----
+def sort_workspace(n: int) -> int:
+    return int(call("bess_sort_workspace", n))
+
+
+def sort_keys(keys: torch.Tensor, n: int, key_bits: int, keys_out: torch.Tensor,
+              perm_out: torch.Tensor, workspace: torch.Tensor) -> None:
+    call("bess_sort_keys", keys.data_ptr(), n, key_bits, keys_out.data_ptr(), perm_out.data_ptr(),
+         workspace.data_ptr(), _st(keys))
+
+
+def scatter_sgd(table: torch.Tensor, sorted_keys: torch.Tensor, perm: torch.Tensor, n: int,
+                n_local: int, per_dst: int, grad_local: torch.Tensor, grad_dst_ptr: int,
+                dst_stride_rows: int, lr: float) -> None:
+    call("bess_scatter_sgd", table.data_ptr(), table.stride(0), dtype_code(table.dtype),
+         table.shape[1], sorted_keys.data_ptr(), perm.data_ptr(), n, n_local, per_dst,
+         grad_local.data_ptr(), grad_dst_ptr, dst_stride_rows, float(lr), _st(table))
+
+
+def scatter_collect(row_elems: int, sorted_keys: torch.Tensor, perm: torch.Tensor, n: int,
+                    n_local: int, per_dst: int, grad_local: torch.Tensor, grad_dst_ptr: int,
+                    dst_stride_rows: int, seg_grad: torch.Tensor, row_to_seg: torch.Tensor) -> None:
+    call("bess_scatter_collect", row_elems, sorted_keys.data_ptr(), perm.data_ptr(), n, n_local,
+         per_dst, grad_local.data_ptr(), grad_dst_ptr, dst_stride_rows, seg_grad.data_ptr(),
+         row_to_seg.data_ptr(), _st(seg_grad))
+
+
+def opt_dense(kind: int, table: torch.Tensor, seg_grad: torch.Tensor,
+              row_to_seg: Optional[torch.Tensor], state0: Optional[torch.Tensor],
+              state1: Optional[torch.Tensor], lr: float, momentum: float, dampening: float,
+              beta1: float, beta2: float, eps: float, weight_decay: float, step: int) -> None:
+    call("bess_opt_dense", kind, table.data_ptr(), table.stride(0), dtype_code(table.dtype),
+         table.shape[0], table.shape[1], seg_grad.data_ptr(), ptr(row_to_seg), ptr(state0),
+         ptr(state1), float(lr), float(momentum), float(dampening), float(beta1), float(beta2),
+         float(eps), float(weight_decay), int(step), _st(table))
+
+
+def relation_grad_reduce(rows_: torch.Tensor, width: int, sorted_rel: torch.Tensor,
+                         perm: torch.Tensor, n: int, n_rel: int, d_table: torch.Tensor) -> None:
+    call("bess_relation_grad_reduce", rows_.data_ptr(), width, sorted_rel.data_ptr(),
+         perm.data_ptr(), n, n_rel, d_table.data_ptr(), _st(d_table))
+
+
+def topk_merge(win_score: torch.Tensor, ld: int, n_query: int, n_win: int,
+               win_ids: Optional[torch.Tensor], ld_ids: int, win_id0: int,
+               best_score: torch.Tensor, best_id: torch.Tensor, k: int) -> None:
+    call("bess_topk_merge", win_score.data_ptr(), ld, n_query, n_win, ptr(win_ids), ld_ids,
+         win_id0, best_score.data_ptr(), best_id.data_ptr(), k, _st(win_score))
+
+
+def fill_f32(t: torch.Tensor, v: float) -> None:
+    call("bess_fill_f32", t.data_ptr(), t.numel(), float(v), _st(t))
+
+
+def fill_i32(t: torch.Tensor, v: int) -> None:
+    call("bess_fill_i32", t.data_ptr(), t.numel(), int(v), _st(t))
+
+
+def cast_from_f32(src: torch.Tensor, dst: torch.Tensor) -> None:
+    call("bess_cast_from_f32", src.data_ptr(), dst.data_ptr(), dtype_code(dst.dtype), src.numel(),
+         _st(src))

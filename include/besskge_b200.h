@@ -1,0 +1,275 @@
+/* besskge_b200 — C-ABI of the B200-native BESS-KGE hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers, sizes and a
+ * CUDA stream (as void*), is stream-ordered, never allocates, never throws and
+ * returns 0 on success or a negative bess_status (message: bess_last_error()).
+ * All pointers are BORROWED device pointers that must stay alive until the
+ * enqueued work has finished.  No torch types appear in any signature.
+ *
+ * The reference (graphcore-research/bess-kge) has no arithmetic FFI: its only
+ * native symbol is a PopART pattern registration loaded with
+ * ctypes.cdll.LoadLibrary (besskge/__init__.py:30,
+ * custom_ops/remove_all_reduce_pattern.cpp:45-47).  The functions below are
+ * what a CUDA back-end of that library binds instead; each one cites the
+ * reference torch expression (file:line under besskge/) it replaces.
+ */
+#ifndef BESSKGE_B200_H
+#define BESSKGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  BESS_OK = 0,
+  BESS_ERR_INVALID_ARG = -1,
+  BESS_ERR_CUDA = -2,
+  BESS_ERR_UNSUPPORTED = -3
+} bess_status;
+
+typedef enum { BESS_F32 = 0, BESS_F16 = 1, BESS_BF16 = 2 } bess_dtype;
+
+/* score-function families (scoring.py) */
+typedef enum {
+  BESS_TRANSE = 0, BESS_ROTATE = 1, BESS_DISTMULT = 2,
+  BESS_COMPLEX = 3, BESS_PAIRRE = 4, BESS_BOXE = 5
+} bess_family;
+
+/* which entity the candidates replace: score_tails / score_heads */
+typedef enum { BESS_MODE_TAILS = 0, BESS_MODE_HEADS = 1 } bess_mode;
+
+/* losses (loss.py) */
+typedef enum {
+  BESS_LOSS_LOGSIGMOID = 0, BESS_LOSS_MARGIN_RANKING = 1, BESS_LOSS_SOFTMAX_CE = 2
+} bess_loss_kind;
+
+typedef enum { BESS_OPT_SGD = 0, BESS_OPT_SGDM = 1, BESS_OPT_ADAMW = 2 } bess_opt_kind;
+
+/* Row addressing (up to three nested levels, outer level optional):
+ *   x' = x % group1, a = x / group1          (skipped when group1 <= 0)
+ *   row(x) = a * stride1 + (x' / group) * stride + x' % group + offset
+ * group <= 0: row(x) = x + offset.  Lets kernels walk the reference's
+ * [n_shard, p + B*Nn, D] exchange layout (bess.py:333-360) and its
+ * transposed views in place. */
+typedef struct {
+  int32_t group, stride, offset, group1, stride1;
+} bess_rowmap_t;
+
+/* A set of rows: storage row = idx ? idx[row(x)] : row(x); address =
+ * base + storage_row * pitch (pitch in ELEMENTS of the table dtype). */
+typedef struct {
+  const void* base;
+  const int32_t* idx;
+  bess_rowmap_t map;
+  int64_t pitch;
+} bess_rows_t;
+
+/* score-function configuration (constructor arguments of scoring.py classes) */
+typedef struct {
+  int32_t family;      /* bess_family */
+  int32_t norm_p;      /* scoring_norm, 1 or 2 (distance families) */
+  int32_t d;           /* embedding_size as passed to the constructor */
+  int32_t normalize;   /* PairRE normalize_entities */
+  int32_t apply_tanh;  /* BoxE */
+  int32_t per_dim;     /* BoxE dist_func_per_dim */
+  float eps;           /* BoxE */
+} bess_score_cfg_t;
+
+#define BESS_MAX_SHARD 16
+
+const char* bess_last_error(void);
+int bess_version(void);
+/* entity / relation row widths (elements) implied by a config */
+int bess_entity_width(const bess_score_cfg_t* cfg);
+int bess_relation_width(const bess_score_cfg_t* cfg);
+/* number of query-side vectors of entity width the negative kernels consume */
+int bess_query_nvec(const bess_score_cfg_t* cfg);
+
+/* ---------------------------------------------------------------- gather --
+ * replaces `self.entity_embedding[gather_idx]` + torch.split + the data
+ * movement of all_to_all (bess.py:331-355, 501-507) for ONE source shard.
+ * idx = [n_local | n_dst * per_dst] local rows of `table`.  The first n_local
+ * rows (heads) go to local_out row i.  Row y of the second part goes to
+ * dst_out[y / per_dst] + (slot * per_dst + y % per_dst) * row_elems, i.e. into
+ * destination replica (y / per_dst)'s receive buffer [n_src, per_dst, D] at
+ * source slot `slot`.  dst_out[] may be local buffers, peer-mapped pointers
+ * (NVLink stores) or slices of one NCCL send buffer. */
+int bess_gather_route(const void* table, int64_t table_pitch, int dtype, int row_elems,
+                      const int32_t* idx, int n_local, int n_dst, int per_dst, void* local_out,
+                      void* const* dst_out /* host array [n_dst] */, int slot, void* stream);
+
+/* plain gather out[i] = table[idx[i]] (bess.py:765,768,787) */
+int bess_gather_rows(const void* table, int64_t table_pitch, int dtype, int row_elems,
+                     const int32_t* idx, int n_idx, void* out, void* stream);
+
+/* ---------------------------------------------------------- score_triple --
+ * BaseScoreFunction.score_triple (scoring.py:45-65 and per family). */
+int bess_score_triple_fwd(const bess_score_cfg_t* cfg, int dtype, bess_rows_t head,
+                          bess_rows_t tail, const void* rel_table, const int32_t* rel_id,
+                          bess_rowmap_t rel_map, int n, float* score, bess_rowmap_t score_map,
+                          void* stream);
+/* backward of the above given dL/dscore; fp32 gradient rows.  d_head / d_tail
+ * rows are addressed like head / tail (base = fp32 buffer, pitch in floats);
+ * d_rel is a per-query row buffer [n, rel_width] (reduced by relation later).
+ * add_* != 0 accumulates. */
+int bess_score_triple_bwd(const bess_score_cfg_t* cfg, int dtype, bess_rows_t head,
+                          bess_rows_t tail, const void* rel_table, const int32_t* rel_id,
+                          bess_rowmap_t rel_map, int n, const float* score,
+                          const float* d_score, bess_rowmap_t score_map, bess_rows_t d_head,
+                          bess_rows_t d_tail, float* d_rel, int add_head, int add_tail,
+                          int add_rel, void* stream);
+
+/* ---------------------------------------------------- query prologue ------
+ * The relation-dependent half of score_heads / score_tails, e.g. h + r,
+ * h o r, h (x) r, rotate(h, r) (scoring.py:342,354,446-448,460-462,825,837,
+ * 928-932,944-946, 565-573, 1372-1389): fixed entity rows + relation ids ->
+ * query vectors qv [n, nvec, W] fp32. */
+int bess_query_prologue_fwd(const bess_score_cfg_t* cfg, int dtype, int mode, bess_rows_t fixed,
+                            const void* rel_table, const int32_t* rel_id, bess_rowmap_t rel_map,
+                            int n, float* qv, void* stream);
+int bess_query_prologue_bwd(const bess_score_cfg_t* cfg, int dtype, int mode, bess_rows_t fixed,
+                            const void* rel_table, const int32_t* rel_id, bess_rowmap_t rel_map,
+                            int n, const float* d_qv, bess_rows_t d_fixed, float* d_rel,
+                            int add_fixed, int add_rel, void* stream);
+/* BoxE only: turn accumulated pre-chain relation gradients into gradients of
+ * the raw relation row, in place (chain rule of scoring.py:1279-1309). */
+int bess_boxe_rel_finalize(const bess_score_cfg_t* cfg, int dtype, const void* rel_table,
+                           const int32_t* rel_id, int n, float* d_rel, void* stream);
+/* PairRE candidate normalisation: inv_norm[i] = 1 / max(||cand_i||, 1e-12) */
+int bess_cand_inv_norm(int dtype, bess_rows_t cand, int n, int width, float* inv_norm,
+                       void* stream);
+/* ... and its backward: d_cand_i = (g_i - c^_i (c^_i . g_i)) * inv_norm_i, in place on the
+ * fp32 gradient rows g (addressed by d_cand). */
+int bess_cand_norm_bwd(int dtype, bess_rows_t cand, int n, int width, const float* inv_norm,
+                       bess_rows_t d_cand, void* stream);
+
+/* -------------------------------------------- shared-negative scoring -----
+ * broadcasted_distance / broadcasted_dot_product with negative_sample_sharing
+ * (scoring.py:176-200, 231-255; pea.distance_matrix scoring.py:195-197) and
+ * the PairRE / BoxE broadcast forms: scores[q, c] for every query q against
+ * ONE shared candidate list.  out[(score_map(q)) * ld_out + col0 + c].
+ * cand_scale: optional per-candidate factor (PairRE inv norms) or NULL.
+ * aux: BoxE p=2 only, per-pair norm of the first box (needed by backward). */
+int bess_score_shared_fwd(const bess_score_cfg_t* cfg, int dtype, int mode, const float* qv,
+                          int n_query, bess_rows_t cand, const float* cand_scale, int n_cand,
+                          float* out, bess_rowmap_t score_map, int64_t ld_out, int col0,
+                          float* aux, void* stream);
+/* backward w.r.t. the query vectors: d_qv [n_query, nvec, W] (overwritten) */
+int bess_score_shared_bwd_query(const bess_score_cfg_t* cfg, int dtype, int mode, const float* qv,
+                                int n_query, bess_rows_t cand, const float* cand_scale,
+                                int n_cand, const float* score, const float* d_score,
+                                bess_rowmap_t score_map, int64_t ld, int col0, const float* aux,
+                                float* d_qv, void* stream);
+/* backward w.r.t. the candidate rows: fp32 rows addressed by d_cand
+ * (overwritten, or accumulated when add_cand != 0).  workspace: >=
+ * bess_shared_bwd_cand_workspace() bytes. */
+int64_t bess_shared_bwd_cand_workspace(const bess_score_cfg_t* cfg, int n_query, int n_cand);
+int bess_score_shared_bwd_cand(const bess_score_cfg_t* cfg, int dtype, int mode, const float* qv,
+                               int n_query, bess_rows_t cand, const float* cand_scale,
+                               int n_cand, const float* score, const float* d_score,
+                               bess_rowmap_t score_map, int64_t ld, int col0, const float* aux,
+                               bess_rows_t d_cand, int add_cand, void* workspace, void* stream);
+
+/* ------------------------------------------ per-triple negative scoring ---
+ * negative_sample_sharing == False: reduce_embedding(v1.unsqueeze(1) - v2)
+ * (scoring.py:199, 254): query q against its OWN n_per candidates; candidate
+ * c of the query at position qpos = score_map(q) is logical row
+ * cand.map(c) + qpos * cand_q_stride of `cand` (then cand.idx, if any), so the
+ * table can be read in place: fused gather + score.  d_cand is addressed the
+ * same way. */
+int bess_score_pertriple_fwd(const bess_score_cfg_t* cfg, int dtype, int mode, const float* qv,
+                             int n_query, bess_rows_t cand, int64_t cand_q_stride, int n_per,
+                             float* out, bess_rowmap_t score_map, int64_t ld_out, int col0,
+                             float* aux, void* stream);
+int bess_score_pertriple_bwd(const bess_score_cfg_t* cfg, int dtype, int mode, const float* qv,
+                             int n_query, bess_rows_t cand, int64_t cand_q_stride, int n_per,
+                             const float* score, const float* d_score, bess_rowmap_t score_map,
+                             int64_t ld, int col0, const float* aux, float* d_qv,
+                             bess_rows_t d_cand, void* stream);
+
+/* ------------------------------------------------------- masks and loss ---
+ * score[r, c] += value where mask[r * ld_mask + c] == flag
+ * (BAD_NEGATIVE_SCORE handling, bess.py:201-245, 802-806). */
+int bess_mask_add(float* score, int n_row, int n_col, int64_t ld, const uint8_t* mask,
+                  int64_t ld_mask, int mask_rows, int flag, float value, void* stream);
+/* augment_negative diagonal mask (bess.py:201-226): score[r, diag_col(r)] += value */
+int bess_mask_diag(float* score, int n_row, int64_t ld, int step, int half_group, int group,
+                   float value, void* stream);
+
+/* loss forward + gradient w.r.t. the scores (loss.py:115-134, 179-195,
+ * 226-251).  weight: [n] or single value (weight_n == 1).  Outputs: row_loss
+ * [n] partials and, via bess_sum_f32, the replica loss; d_pos [n], d_neg
+ * [n, n_neg] (may alias neg for in-place).  For SOFTMAX_CE `neg` is adjusted
+ * in place first like the reference (loss.py:233-237). */
+int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float adv_scale, float loss_scale,
+                      int64_t n_entity, const float* pos, float* neg, int n, int n_neg,
+                      int64_t ld, const float* weight, int weight_n, float* row_loss,
+                      float* d_pos, float* d_neg, void* stream);
+/* deterministic sum of n floats (fixed order) -> out[0] */
+int bess_sum_f32(const float* x, int n, float* out, void* stream);
+
+/* ranks_from_scores (metric.py:129-183): mode 0 optimistic, 1 pessimistic,
+ * 2 average.  rank[n] fp32 (inf when worst_rank_infty and nothing is beaten). */
+int bess_rank_from_scores(const float* pos, const float* neg, int n, int n_neg, int64_t ld,
+                          int mode, int worst_rank_infty, float* rank, void* stream);
+
+/* ------------------------------------------------- backward: scatter ------
+ * Stable LSD radix sort of n (key, position) pairs; keys in [0, 2^key_bits).
+ * workspace >= bess_sort_workspace(n) bytes.  perm_out[i] = original position
+ * of the i-th smallest key (ties keep input order -> deterministic sums). */
+int64_t bess_sort_workspace(int n);
+int bess_sort_keys(const int32_t* keys, int n, int key_bits, int32_t* keys_out,
+                   int32_t* perm_out, void* workspace, void* stream);
+
+/* Deterministic segmented scatter-add + optimizer on one shard (implicit in the
+ * reference: autograd of bess.py:333-337 followed by the optimizer step).
+ * For each run of equal sorted keys, the fp32 gradient rows grad[perm[.]] are
+ * summed in sorted (= input) order and applied to table row `key`.
+ *   SGD   (no momentum / weight decay): sparse update, exact.
+ *   SGDM / ADAMW: the segment sums are stored to seg_grad[first position of the
+ *   run] and row_to_seg[key]; bess_opt_dense then updates EVERY row (dense
+ *   torch.optim semantics: rows without gradient still decay / coast).
+ * grad rows: position x < n_local -> grad_local row x; else y = x - n_local ->
+ * grad_dst row (y / per_dst) * dst_stride_rows + y % per_dst  (mirror of
+ * bess_gather_route's routing). */
+int bess_scatter_sgd(void* table, int64_t table_pitch, int dtype, int row_elems,
+                     const int32_t* sorted_keys, const int32_t* perm, int n, int n_local,
+                     int per_dst, const float* grad_local, const float* grad_dst,
+                     int64_t dst_stride_rows, float lr, void* stream);
+int bess_scatter_collect(int row_elems, const int32_t* sorted_keys, const int32_t* perm, int n,
+                         int n_local, int per_dst, const float* grad_local,
+                         const float* grad_dst, int64_t dst_stride_rows, float* seg_grad,
+                         int32_t* row_to_seg, void* stream);
+/* dense optimizer pass over [n_rows, row_elems]; row_to_seg[row] < 0: zero grad.
+ * state0: momentum buffer / Adam m; state1: Adam v (fp32).  step: 1-based. */
+int bess_opt_dense(int kind, void* table, int64_t table_pitch, int dtype, int n_rows,
+                   int row_elems, const float* seg_grad, const int32_t* row_to_seg, float* state0,
+                   float* state1, float lr, float momentum, float dampening, float beta1,
+                   float beta2, float eps, float weight_decay, int step, void* stream);
+/* relation table: deterministic reduce of per-query gradient rows by relation
+ * id -> d_table [n_rel, width] fp32 (overwritten).  sorted_rel/perm from
+ * bess_sort_keys over the relation ids. */
+int bess_relation_grad_reduce(const float* d_rel_rows, int width, const int32_t* sorted_rel,
+                              const int32_t* perm, int n, int n_rel, float* d_table,
+                              void* stream);
+
+/* ------------------------------------------------------------ top-k -------
+ * Running top-k over a window of candidates (bess.py:771-822): merges the
+ * scores of `n_win` new candidates (ids win_ids or win_id0 + c) into the
+ * per-query best lists best_score/best_id [n_query, k] (sorted descending,
+ * ties keep the earlier entry). */
+int bess_topk_merge(const float* win_score, int64_t ld, int n_query, int n_win,
+                    const int32_t* win_ids, int64_t ld_ids, int win_id0, float* best_score,
+                    int32_t* best_id, int k, void* stream);
+
+/* utility */
+int bess_fill_f32(float* p, int64_t n, float v, void* stream);
+int bess_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);
+int bess_cast_from_f32(const float* src, void* dst, int dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BESSKGE_B200_H */
