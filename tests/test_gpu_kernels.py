@@ -1,0 +1,192 @@
+"""-m gpu: individual CUDA kernels through the C-ABI vs the oracle / reference goldens."""
+import numpy as np
+import pytest
+import torch
+from numpy.testing import assert_array_equal
+from torch.testing import assert_close
+
+from oracle import besskge_oracle as O
+
+from .conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE"]
+
+
+def _imports():
+    from besskge_b200 import _lib as L, kernels as K
+    from . import gpu_helpers as H
+    return L, K, H
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("W", [16, 64, 256, 1000])
+def test_gather_route_bit_exact(dtype, W):
+    L, K, H = _imports()
+    if (W * torch.finfo(dtype).bits // 8) % 16:
+        W = W + 8 - W % 8
+    g = torch.Generator().manual_seed(0)
+    Es, n, n_local, per = 3000, 4, 37, 53
+    table = torch.randn(Es, W, generator=g).to(dtype).cuda()
+    idx = torch.randint(Es, (n_local + n * per,), generator=g, dtype=torch.int32).cuda()
+    local = torch.zeros(n_local, W, dtype=dtype, device="cuda")
+    recv = torch.zeros(n, 3, per, W, dtype=dtype, device="cuda")  # [dst][slot][per]
+    slot = 2
+    K.gather_route(table, idx, n_local, per, local, [recv[j].data_ptr() for j in range(n)], slot)
+    torch.cuda.synchronize()
+    ref = table[idx.long()]
+    assert torch.equal(local, ref[:n_local])
+    assert torch.equal(recv[:, slot], ref[n_local:].view(n, per, W))
+    assert torch.count_nonzero(recv[:, 0]) == 0 and torch.count_nonzero(recv[:, 1]) == 0
+    out = torch.empty(idx.numel(), W, dtype=dtype, device="cuda")
+    K.gather_rows(table, idx, out)
+    assert torch.equal(out, ref)
+
+
+def test_gather_empty_and_alignment_error():
+    L, K, H = _imports()
+    table = torch.randn(10, 16, device="cuda")
+    out = torch.empty(0, 16, device="cuda")
+    K.gather_rows(table, torch.empty(0, dtype=torch.int32, device="cuda"), out)  # no-op
+    bad = torch.randn(10, 6, device="cuda")  # 24-byte rows
+    with pytest.raises(L.BessLibraryError):
+        K.gather_rows(bad, torch.zeros(2, dtype=torch.int32, device="cuda"),
+                      torch.empty(2, 6, device="cuda"))
+
+
+@pytest.mark.parametrize("n,bits", [(1, 5), (31, 3), (2048, 11), (2049, 17), (100_003, 22),
+                                    (300_000, 8)])
+def test_radix_sort_stable(n, bits):
+    L, K, H = _imports()
+    rng = np.random.default_rng(n)
+    keys = rng.integers(1 << bits, size=n).astype(np.int32)
+    if n > 1000:
+        keys[: n // 3] = keys[0]  # a heavy hitter
+    kd = torch.from_numpy(keys).cuda()
+    ko = torch.empty_like(kd)
+    po = torch.empty_like(kd)
+    ws = torch.empty(K.sort_workspace(n) // 4 + 64, dtype=torch.int32, device="cuda")
+    K.sort_keys(kd, n, bits, ko, po, ws)
+    torch.cuda.synchronize()
+    order = np.argsort(keys, kind="stable")
+    assert_array_equal(po.cpu().numpy(), order.astype(np.int32))
+    assert_array_equal(ko.cpu().numpy(), keys[order])
+
+
+@pytest.mark.parametrize("fam", FAMS)
+def test_score_functions_vs_reference_golden(fam):
+    L, K, H = _imports()
+    from besskge_b200.sharding import Sharding
+    cfg, g = load_golden(f"scores_{fam}")
+    d = cfg["d"]
+    sh = Sharding.create(60, 1, seed=1234)
+    ent, rel = H.T(g["ent"]), H.T(g["rel"])
+    h, t, r = H.T(g["h"]).cuda(), H.T(g["t"]).cuda(), H.T(g["r"]).cuda()
+    for vi, v in enumerate(cfg["variants"]):
+        kw = {}
+        if "normalize_entities" in v:
+            kw["normalize_entities"] = v["normalize_entities"]
+        if "apply_tanh" in v:
+            kw["apply_tanh"] = v["apply_tanh"]
+        if "dist_func_per_dim" in v:
+            kw["dist_func_per_dim"] = v["dist_func_per_dim"]
+        for sharing in (True, False):
+            sf = H.make_score_fn(fam, sharing, v["p"], sh, cfg["n_rel"], d, ent, rel, **kw)
+            assert_close(sf.score_triple(h, r, t).cpu(), H.T(g[f"v{vi}_triple"]), rtol=1e-5,
+                         atol=2e-5)
+            key = f"v{vi}_s{int(sharing)}_heads"
+            if key not in g:
+                continue
+            cand = H.T(g["c_shared"] if sharing else g["c_per"]).cuda()
+            assert_close(sf.score_heads(cand, r, t).cpu(), H.T(g[key]), rtol=1e-5, atol=2e-5)
+            assert_close(sf.score_tails(h, r, cand).cpu(), H.T(g[f"v{vi}_s{int(sharing)}_tails"]),
+                         rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("fam,p", [("TransE", 1), ("TransE", 2), ("RotatE", 1), ("DistMult", 2),
+                                   ("ComplEx", 2), ("PairRE", 2), ("BoxE", 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_score_shared_tiles_vs_oracle(fam, p, dtype):
+    """multi-tile shapes (ragged edges) in every table dtype; 1e-5 (fp32) / 1e-2 (half)."""
+    L, K, H = _imports()
+    from besskge_b200.sharding import Sharding
+    d, nq, nc, n_rel = 48, 300, 517, 9
+    sh = Sharding.create(64, 1, seed=1)
+    g = torch.Generator().manual_seed(5)
+    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
+    rw = {"TransE": d, "RotatE": d, "DistMult": d, "ComplEx": 2 * d, "PairRE": 2 * d,
+          "BoxE": 4 * d + 2}[fam]
+    ent = torch.randn(1, 64, ew * d, generator=g)
+    rel = (torch.randn(n_rel, rw, generator=g)).to(dtype).float()
+    h = torch.randn(nq, ew * d, generator=g).to(dtype)
+    cand = torch.randn(1, nc, ew * d, generator=g).to(dtype)
+    r = torch.randint(n_rel, (nq,), generator=g)
+    sf = H.make_score_fn(fam, True, p, sh, n_rel, d, ent, rel, dtype=dtype)
+    oc = H.score_cfg(fam, d, p)
+    tol = dict(rtol=1e-5, atol=1e-4) if dtype == torch.float32 else dict(rtol=1e-2, atol=5e-2)
+    for mode in ("t", "h"):
+        want = O.score_candidates(oc, mode, h.float(), rel, r, cand.float(), True)
+        got = (sf.score_tails(h.cuda(), r.cuda(), cand.cuda()) if mode == "t"
+               else sf.score_heads(cand.cuda(), r.cuda(), h.cuda()))
+        assert got.dtype == dtype
+        assert_close(got.float().cpu(), want, **tol)
+
+
+def test_loss_vs_reference_golden():
+    L, K, H = _imports()
+    cfg, g = load_golden("loss")
+    pos, neg = H.T(g["pos"]).cuda(), H.T(g["neg"]).cuda()
+    for i, case in enumerate(cfg["cases"]):
+        fn = H.make_loss(case)
+        for wi, w in enumerate((H.T(g["w"]).cuda(), torch.tensor([1.0], device="cuda"))):
+            lossv, dpos, dneg = fn.fwd_bwd(pos.clone(), neg.clone(), w)
+            assert_close(lossv.cpu(), H.T(g[f"c{i}_w{wi}_loss"]), rtol=1e-5, atol=1e-5)
+            assert_close(dpos.cpu(), H.T(g[f"c{i}_w{wi}_dpos"]), rtol=1e-5, atol=1e-6)
+            assert_close(dneg.cpu(), H.T(g[f"c{i}_w{wi}_dneg"]), rtol=1e-5, atol=1e-6)
+
+
+def test_loss_wide_rows_vs_oracle():
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(9)
+    S, N = 70, 3001
+    pos = torch.randn(S, generator=g) * 4
+    neg = torch.randn(S, N, generator=g) * 4
+    w = torch.rand(S, generator=g)
+    for case in (dict(kind="logsigmoid", margin=6.0, negative_adversarial_sampling=True),
+                 dict(kind="margin_ranking", margin=1.0, negative_adversarial_sampling=True,
+                      negative_adversarial_scale=0.3),
+                 dict(kind="softmax_ce", n_entity=93773)):
+        p_, n_ = pos.clone().requires_grad_(True), neg.clone().requires_grad_(True)
+        want = O.loss_value(H.oracle_loss_cfg(case), p_, n_, w)
+        want.backward()
+        lossv, dpos, dneg = H.make_loss(case).fwd_bwd(pos.cuda(), neg.clone().cuda(), w.cuda())
+        assert_close(lossv.cpu(), want.detach(), rtol=1e-5, atol=1e-4)
+        assert_close(dpos.cpu(), p_.grad, rtol=1e-4, atol=1e-6)
+        assert_close(dneg.cpu(), n_.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_metrics_vs_reference_golden():
+    L, K, H = _imports()
+    from besskge_b200.metric import Evaluation
+    _, g = load_golden("metric")
+    pos, neg = H.T(g["pos"]).cuda(), H.T(g["neg"]).cuda()
+    for mode in ("optimistic", "pessimistic", "average"):
+        for winf in (False, True):
+            ev = Evaluation(["mrr", "hits@1", "hits@5"], mode=mode, worst_rank_infty=winf)
+            rk = ev.ranks_from_scores(pos, neg)
+            assert_close(rk.cpu(), H.T(g[f"rank_{mode}_{int(winf)}"]))
+            for k, v in ev.dict_metrics_from_ranks(rk).items():
+                assert_close(v.cpu(), H.T(g[f"m_{mode}_{int(winf)}_{k}"]))
+    for winf in (False, True):
+        ev = Evaluation(["mrr"], worst_rank_infty=winf)
+        assert_close(ev.ranks_from_indices(H.T(g["truth"]).cuda(), H.T(g["ids"]).cuda()).cpu(),
+                     H.T(g[f"idrank_{int(winf)}"]))
+    # reference's hand-written vectors (tests/test_metric.py:13-49)
+    pos = torch.tensor([2.1, 5.0, 5.9, 2.0]).cuda()
+    neg = torch.tensor([[2.1, 3.1, 2.1, 5.2, 8.4], [9.8, 5.0, 1.0, 3.2, 5.0],
+                        [4.0, 2.3, 5.9, 3.1, 4.5], [4.0, 2.3, 5.9, 3.1, 4.5]]).cuda()
+    ev = Evaluation(["mrr", "hits@1", "hits@5"], mode="pessimistic", worst_rank_infty=True)
+    res = ev.dict_metrics_from_ranks(ev.ranks_from_scores(pos, neg))
+    assert_close(res["hits@5"].cpu(), torch.tensor([0.0, 1.0, 1.0, 0.0]))
+    assert_close(res["mrr"].cpu(), torch.tensor([0.0, 1 / 4, 1 / 2, 0.0]))
