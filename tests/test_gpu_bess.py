@@ -37,14 +37,22 @@ def test_bess_forward_vs_reference_golden(name):
     torch.cuda.synchronize()
     assert_close(res["positive_score"].cpu(), H.T(g["positive_score"]), rtol=1e-5, atol=1e-4)
     assert_close(res["negative_score"].cpu(), H.T(g["negative_score"]), rtol=1e-5, atol=1e-4)
-    # ranks can flip only on exact ties / rounding-level gaps: compare where the decisive
-    # gap is above the score tolerance, and require full equality of the rest in aggregate
+    # ranks: exact wherever the decisive score gap exceeds the score tolerance — the
+    # product rank must lie in the band allowed by the reference scores +- tol
     ranks, want = res["ranks"].cpu(), H.T(g["ranks"])
-    assert (ranks != want).float().mean() < 0.01
-    keys = list(ev.metrics.keys())
-    got_m = dict(zip(keys, res["metrics"].cpu().unbind(1)))
-    ev_ref_order = ["hits@3", "mrr"]  # the fixtures were written with this python's set order
+    pos_g, neg_g = H.T(g["positive_score"]).reshape(-1, 1), H.T(g["negative_score"])
+    tol = 1e-4 + 1e-5 * pos_g.abs()
+    lower = 1.0 + (neg_g > pos_g + tol).sum(-1).float()
+    upper = 1.0 + (neg_g >= pos_g - tol).sum(-1).float()
+    assert bool(((ranks >= lower) & (ranks <= upper)).all())
+    # exact equality except where the reference itself saw an EXACT tie (a candidate that
+    # is the true entity scores bit-identically there; here positive and negative scores
+    # come from different reduction trees and may differ in the last ulp)
+    tie = (neg_g == pos_g).any(-1)
+    assert bool((ranks[~tie] == want[~tie]).all())
     assert res["metrics"].shape == tuple(g["metrics"].shape)
+    mrr_row = list(ev.metrics.keys()).index("mrr")
+    assert_close(res["metrics"][:, mrr_row].cpu().sum(), (1.0 / want).sum(), rtol=0.05, atol=0.05)
 
 
 @pytest.mark.parametrize("name", golden_names("train_"))
