@@ -87,6 +87,18 @@ class _Placement:
         torch.distributed.all_to_all_single(recv.view(-1), send.view(-1))
 
 
+class _Staged:
+    """Device-resident inputs of one call (see EmbeddingMovingBessKGE.stage)."""
+
+    dims: Tuple[int, int, int, int, int]
+    gidx: torch.Tensor
+    rel: torch.Tensor
+    tw: Optional[torch.Tensor]
+    nmask: Optional[torch.Tensor]
+    tmask: Optional[torch.Tensor]
+    h2d_bytes: int
+
+
 @dataclasses.dataclass
 class _Pass:
     """One launch group of score_heads / score_tails (bess.py:368-466)."""
@@ -223,8 +235,11 @@ class BessKGE(torch.nn.Module, ABC):
         return buf
 
     def _step_rows(self, placement: _Placement, bps: int) -> List[List[int]]:
-        """rows of the leading axis used at each step, one per local replica."""
+        """rows of the STAGED inputs used at each step, one per local replica
+        (distributed mode stages only this rank's rows)."""
         n = placement.n_shard
+        if placement.distributed:
+            return [[s] for s in range(bps)]
         return [[s * n + r for r in placement.shards] for s in range(bps)]
 
     def _finish_metrics(self, out: Dict[str, Any], pos: torch.Tensor, neg: torch.Tensor,
@@ -322,18 +337,66 @@ class EmbeddingMovingBessKGE(BessKGE):
         return passes, n_col
 
     # ---- run ---------------------------------------------------------------
-    def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
-             optimizer) -> Dict[str, Any]:
+    def stage(self, head, relation, tail, negative, triple_mask=None, triple_weight=None,
+              negative_mask=None, persistent: bool = False) -> "_Staged":
+        """Pack the step's index tensors and copy them to the device (one H2D copy
+        per tensor from the caller's — ideally pinned — host memory).  With
+        `persistent=True` the device copies are owned by the returned object and
+        can be replayed any number of times (inputs resident in HBM)."""
         ws, pl = self._setup()
         dev = ws.device
-        ent, rel_table = self._tables()
         n = self.sharding.n_shard
         L_rows = head.shape[0]
         if L_rows % n != 0:
             raise ValueError(f"leading axis {L_rows} is not a multiple of n_shard={n}")
-        bps = L_rows // n
         p = head.shape[-1]
         B, Nn = negative.shape[-2], negative.shape[-1]
+        S = n * p
+        local = bool(self.negative_sampler.local_sampling)
+        h2 = _as_i32(head).reshape(L_rows, S)
+        t3 = _as_i32(tail).reshape(L_rows, n, p)
+        n3 = _as_i32(negative).reshape(L_rows, n, B * Nn)
+        if local:
+            gidx_h = torch.cat([h2, n3.reshape(L_rows, -1), t3.reshape(L_rows, -1)], dim=1)
+        else:
+            gidx_h = torch.cat([h2, torch.cat([t3, n3], dim=2).reshape(L_rows, -1)], dim=1)
+
+        def put(name, t, dtype):
+            if t is None:
+                return None
+            if pl.distributed:  # this rank only needs (and copies) its own rows
+                t = t[pl.rank::n]
+            if persistent:
+                return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+            return self._stage(name, t, dtype, dev)
+
+        st = _Staged()
+        st.dims = (L_rows, n, p, B, Nn)
+        st.gidx = put("gidx", gidx_h, torch.int32)
+        st.rel = put("rel", relation.reshape(L_rows, S), torch.int32)
+        st.tw = put("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
+                    torch.float32)
+        st.nmask = None
+        if negative_mask is not None:
+            st.nmask = put("nmask", negative_mask.reshape(L_rows, negative_mask.shape[1], -1),
+                           torch.bool if negative_mask.dtype == torch.bool else torch.uint8)
+        st.tmask = put("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
+                       torch.bool)
+        st.h2d_bytes = sum(t.numel() * t.element_size()
+                           for t in (st.gidx, st.rel, st.tw, st.nmask, st.tmask) if t is not None)
+        return st
+
+    def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
+             optimizer, staged: Optional["_Staged"] = None) -> Dict[str, Any]:
+        ws, pl = self._setup()
+        dev = ws.device
+        ent, rel_table = self._tables()
+        n = self.sharding.n_shard
+        if staged is None:
+            staged = self.stage(head, relation, tail, negative, triple_mask, triple_weight,
+                                negative_mask)
+        L_rows, _, p, B, Nn = staged.dims
+        bps = L_rows // n
         S = n * p
         local = bool(self.negative_sampler.local_sampling)
         per = p if local else p + B * Nn
@@ -347,25 +410,12 @@ class EmbeddingMovingBessKGE(BessKGE):
         if train and self.loss_fn is None:
             raise ValueError("training needs a loss_fn")
 
-        # ---- pack + stage inputs: gidx = [heads | (neg if local) | per dst: tails, negs]
-        h2 = _as_i32(head).reshape(L_rows, S)
-        t3 = _as_i32(tail).reshape(L_rows, n, p)
-        n3 = _as_i32(negative).reshape(L_rows, n, B * Nn)
-        if local:
-            gidx_h = torch.cat([h2, n3.reshape(L_rows, -1), t3.reshape(L_rows, -1)], dim=1)
-        else:
-            gidx_h = torch.cat([h2, torch.cat([t3, n3], dim=2).reshape(L_rows, -1)], dim=1)
-        gidx = self._stage("gidx", gidx_h, torch.int32, dev)
-        rel = self._stage("rel", relation.reshape(L_rows, S), torch.int32, dev)
-        tw = self._stage("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
-                         torch.float32, dev)
-        nmask = None
-        if negative_mask is not None:
-            nmask = self._stage("nmask", negative_mask.reshape(L_rows, negative_mask.shape[1], -1),
-                                torch.uint8 if negative_mask.dtype != torch.bool else torch.bool,
-                                dev)
-        tmask = self._stage("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
-                            torch.bool, dev)
+        # ---- inputs: packed gather list gidx = [heads | (negs if local) | per dst: tails, negs]
+        if staged is None:
+            staged = self.stage(head, relation, tail, negative, triple_mask, triple_weight,
+                                negative_mask)
+        gidx, rel, tw, nmask, tmask = (staged.gidx, staged.rel, staged.tw, staged.nmask,
+                                       staged.tmask)
         one = ws.get("one", (1,), torch.float32)
         one.fill_(1.0)
 
@@ -819,6 +869,15 @@ class TrainingModel:
                  negative_mask=None) -> Dict[str, Any]:
         return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
                                negative_mask, optimizer=self.optimizer)
+
+    def stage(self, **batch) -> _Staged:
+        """Copy a batch to the device once; see `run_staged`."""
+        return self.model.stage(persistent=True, **batch)
+
+    def run_staged(self, staged: _Staged) -> Dict[str, Any]:
+        """Training step(s) on inputs that are already resident in HBM."""
+        return self.model._run(None, None, None, None, None, None, None,
+                               optimizer=self.optimizer, staged=staged)
 
 
 def training_model(model: BessKGE, optimizer: Union[SGD, AdamW],
