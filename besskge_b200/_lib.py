@@ -77,6 +77,9 @@ SIGNATURES = {
     "bess_shared_bwd_cand_workspace": [_CFG, _I, _I],
     "bess_score_shared_bwd_cand": [_CFG, _I, _I, _P, _I, Rows, _P, _I, _P, _P, RowMap, _L, _I, _P,
                                    Rows, _I, _P, _P],
+    "bess_dot_gemm_workspace": [_I, _I, _I],
+    "bess_dot_gemm": [_I, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P],
+    "bess_split_operand": [_I, Rows, _I, _I, _P, _I, _P, _P, _L, _P, _P, _L, _P],
     "bess_score_pertriple_fwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, RowMap, _L, _I, _P, _P],
     "bess_score_pertriple_bwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, _P, RowMap, _L, _I, _P, _P,
                                  Rows, _P],
@@ -100,9 +103,10 @@ _RESTYPE = {
     "bess_last_error": C.c_char_p,
     "bess_shared_bwd_cand_workspace": C.c_int64,
     "bess_sort_workspace": C.c_int64,
+    "bess_dot_gemm_workspace": C.c_int64,
 }
 _NO_STATUS = {"bess_version", "bess_entity_width", "bess_relation_width", "bess_query_nvec",
-              "bess_shared_bwd_cand_workspace", "bess_sort_workspace"}
+              "bess_shared_bwd_cand_workspace", "bess_sort_workspace", "bess_dot_gemm_workspace"}
 
 _lib: Optional[C.CDLL] = None
 

@@ -1,0 +1,629 @@
+// Tensor-core (tcgen05) contraction used by the shared-negative DOT scorers
+// (DistMult / ComplEx: broadcasted_dot_product, scoring.py:231-255, the
+// `torch.matmul(v1, v2.T)` at :252) and by their two backward contractions
+// (dQ = dS * C over candidates, dC = dS^T * Q over queries).
+//
+//   out[map(m) * ld + col0 + n] (+)= sum_k A[m, k] * B[n, k]
+//
+// Both operands are K-major in global memory and reach shared memory through
+// TMA (cp.async.bulk.tensor, hardware swizzle); tcgen05.mma accumulates in
+// TMEM; a 4-warp epilogue drains TMEM with tcgen05.ld while the MMA warp works
+// on the next tile (two 256-column accumulator buffers = all 512 TMEM columns).
+//
+// Precision modes (the table dtype decides):
+//   * fp32 tables -> "3xTF32": every operand is split on the fly-side pre-pass
+//     (bess_split_operand) into hi = rna_tf32(x) and lo = rna_tf32(x - hi); the
+//     kernel issues hi*hi + hi*lo + lo*hi per k-step, which restores fp32-grade
+//     products (dropped term ~2^-22) so the 1e-5 fp32 parity bar holds.
+//   * bf16 / fp16 tables -> one kind::f16 MMA per k-step, fp32 accumulate.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM allocator + MMA issuer (one lane)
+//   warps 2..5  epilogue (TMEM lane quarter = warp_idx % 4)
+#include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace bess {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kAccCols = kBlockN;        // fp32 accumulator columns per buffer
+constexpr int kTmemCols = 2 * kAccCols;  // double-buffered
+
+enum GemmMode { GEMM_TF32X3 = 0, GEMM_F16 = 1, GEMM_BF16 = 2 };
+
+template <int MODE>
+struct ModeTraits {
+  static constexpr int kOperandTiles = MODE == GEMM_TF32X3 ? 2 : 1;  // hi (+ lo)
+  static constexpr int kRowBytes = MODE == GEMM_TF32X3 ? 64 : 128;   // bytes of K per smem row
+  static constexpr int kElemBytes = MODE == GEMM_TF32X3 ? 4 : 2;
+  static constexpr int kBlockK = kRowBytes / kElemBytes;              // elements of K per stage
+  static constexpr int kKSteps = kRowBytes / 32;                      // one MMA consumes 32 B of K
+  static constexpr int kATile = kBlockM * kRowBytes;
+  static constexpr int kBTile = kBlockN * kRowBytes;
+  static constexpr int kStageBytes = kOperandTiles * (kATile + kBTile);
+  // UMMA smem-descriptor layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  static constexpr uint64_t kLayoutType = MODE == GEMM_TF32X3 ? 4 : 2;
+  // instruction-descriptor operand format: 0 = F16, 1 = BF16, 2 = TF32
+  static constexpr uint32_t kFmt = MODE == GEMM_TF32X3 ? 2u : (MODE == GEMM_BF16 ? 1u : 0u);
+};
+
+constexpr int kBarrierBytes = 256;
+template <int MODE>
+constexpr int smem_bytes() {
+  return kStages * ModeTraits<MODE>::kStageBytes + kBarrierBytes + 1024 /* alignment slack */;
+}
+
+// ------------------------------------------------------------------ PTX ----
+BESS_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+BESS_D void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+BESS_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+BESS_D void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+BESS_D bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch (CUDA error),
+// never as a hung GPU.
+BESS_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+      printf("besskge_b200 gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+BESS_D void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+BESS_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+BESS_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+BESS_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+BESS_D void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+BESS_D void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+BESS_D void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+BESS_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+BESS_D void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+template <int MODE>
+BESS_D void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == GEMM_TF32X3) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (tile row)
+BESS_D void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+BESS_D void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major swizzled shared-memory matrix descriptor (UMMA SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for
+//   swizzled K-major: 1), [32,46) stride byte offset >> 4 (8 rows), [46,48)
+//   version = 1, [61,64) swizzle mode.
+template <int MODE>
+BESS_D uint64_t smem_desc(uint32_t addr) {
+  using T = ModeTraits<MODE>;
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * T::kRowBytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= T::kLayoutType << 61;
+  return d;
+}
+
+struct GemmParams {
+  int M, N, K;
+  int k_per_split;  // multiple of kBlockK; split count = ceil(K / k_per_split)
+  int n_split;
+  float* out;       // final output (n_split == 1) ...
+  bess_rowmap_t out_map;
+  int64_t ld_out;
+  int col0;
+  int accumulate;
+  float* partial;   // ... or [n_split, M, ld_partial] partial sums
+  int64_t ld_partial;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const GemmParams p) {
+  using T = ModeTraits<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * T::kStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int n_blocks = (p.N + kBlockN - 1) / kBlockN;
+  const int tiles_per_split = m_blocks * n_blocks;
+  const int n_tiles = tiles_per_split * p.n_split;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (MODE == GEMM_TF32X3) {
+      tma_prefetch_desc(&map_a_lo);
+      tma_prefetch_desc(&map_b_lo);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int split = t / tiles_per_split, r = t - split * tiles_per_split;
+        const int m0 = (r / n_blocks) * kBlockM, n0 = (r % n_blocks) * kBlockN;
+        const int k_begin = split * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        for (int k = k_begin; k < k_end; k += T::kBlockK) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * T::kStageBytes;
+          const uint32_t sb = sa + T::kOperandTiles * T::kATile;
+          mbar_expect_tx(full_bar(stage), T::kStageBytes);
+          tma_load_2d(sa, &map_a_hi, full_bar(stage), k, m0);
+          tma_load_2d(sb, &map_b_hi, full_bar(stage), k, n0);
+          if (MODE == GEMM_TF32X3) {
+            tma_load_2d(sa + T::kATile, &map_a_lo, full_bar(stage), k, m0);
+            tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================= MMA issuer =============================
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A/B format, K-major both, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (T::kFmt << 7) | (T::kFmt << 10) |
+                             ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+        const int split = t / tiles_per_split;
+        const int k_begin = split * p.k_per_split;
+        const int k_end = min(p.K, k_begin + p.k_per_split);
+        const int buf = local & 1;
+        const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccCols);
+        uint32_t first = 1;
+        for (int k = k_begin; k < k_end; k += T::kBlockK) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * T::kStageBytes;
+          const uint32_t sb = sa + T::kOperandTiles * T::kATile;
+#pragma unroll
+          for (int ks = 0; ks < T::kKSteps; ++ks) {
+            const uint64_t a_hi = smem_desc<MODE>(sa + ks * 32);
+            const uint64_t b_hi = smem_desc<MODE>(sb + ks * 32);
+            if (MODE == GEMM_TF32X3) {
+              const uint64_t a_lo = smem_desc<MODE>(sa + T::kATile + ks * 32);
+              const uint64_t b_lo = smem_desc<MODE>(sb + T::kBTile + ks * 32);
+              umma<MODE>(tmem_d, a_lo, b_hi, idesc, first ? 0u : 1u);
+              umma<MODE>(tmem_d, a_hi, b_lo, idesc, 1u);
+              umma<MODE>(tmem_d, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma<MODE>(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
+            }
+            first = 0;
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));  // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int quarter = warp & 3;  // TMEM lanes [32 * quarter, +32)
+    int local = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+      const int split = t / tiles_per_split, r = t - split * tiles_per_split;
+      const int m0 = (r / n_blocks) * kBlockM, n0 = (r % n_blocks) * kBlockN;
+      const int buf = local & 1;
+      const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      float* dst;
+      int64_t ld;
+      bool accumulate = false;
+      if (p.n_split > 1) {
+        ld = p.ld_partial;
+        dst = p.partial + ((int64_t)split * p.M + row) * ld + n0;
+      } else {
+        ld = p.ld_out;
+        dst = p.out + (int64_t)map_row(p.out_map, row < p.M ? row : 0) * ld + p.col0 + n0;
+        accumulate = p.accumulate != 0;
+      }
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kAccCols);
+#pragma unroll 1
+      for (int c = 0; c < kBlockN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row < p.M) {
+          const int n_left = p.N - (n0 + c);
+          if (n_left >= 32 && vec_ok && !accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < n_left) {
+                const float x = __uint_as_float(v[j]);
+                dst[c + j] = accumulate ? dst[c + j] + x : x;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// Fixed-order reduction of split-K partials into the mapped output rows.
+__global__ void gemm_reduce_kernel(const float* __restrict__ partial, int n_split, int M, int N,
+                                   int64_t ld_partial, float* __restrict__ out, bess_rowmap_t out_map,
+                                   int64_t ld_out, int col0, int accumulate) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (int64_t)m * N);
+    float acc = 0.f;
+    for (int s = 0; s < n_split; ++s) acc += partial[((int64_t)s * M + m) * ld_partial + n];
+    float* o = out + (int64_t)map_row(out_map, m) * ld_out + col0 + n;
+    *o = accumulate ? *o + acc : acc;
+  }
+}
+
+// --------------------------------------------------------------------------
+// Operand pre-pass: rows (any table dtype, addressed through bess_rows_t, with
+// an optional per-row scale) -> dense K-major operand arrays.
+//   fp32 GEMM : hi = rna_tf32(x), lo = rna_tf32(x - hi)         (fp32 arrays)
+//   half GEMM : hi = round(x) in bf16 / fp16                     (lo unused)
+// Optional transposed copies hiT / loT [width, n_rows] (K-major operands of the
+// backward contractions).
+// --------------------------------------------------------------------------
+BESS_D float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <typename OT>
+struct OutConv;
+template <>
+struct OutConv<float> {
+  static BESS_D void put(float x, float* hi, float* lo, int64_t i) {
+    const float h = rna_tf32(x);
+    hi[i] = h;
+    lo[i] = rna_tf32(x - h);
+  }
+};
+template <>
+struct OutConv<__half> {
+  static BESS_D void put(float x, __half* hi, __half*, int64_t i) { hi[i] = __float2half_rn(x); }
+};
+template <>
+struct OutConv<__nv_bfloat16> {
+  static BESS_D void put(float x, __nv_bfloat16* hi, __nv_bfloat16*, int64_t i) {
+    hi[i] = __float2bfloat16_rn(x);
+  }
+};
+
+// 32 x 32 tiles through shared memory so that both the straight and the
+// transposed stores are coalesced.
+template <typename ST, typename OT>
+__global__ void split_operand_kernel(bess_rows_t src, int n_rows, int width, const float* row_scale,
+                                     OT* hi, OT* lo, int64_t ld, OT* hiT, OT* loT, int64_t ldT) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const ST* base = reinterpret_cast<const ST*>(src.base);
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float x = 0.f;
+    if (r < n_rows && c < width) {
+      x = ldf(base + src_row(src, r) * src.pitch + c);
+      if (row_scale != nullptr) x *= row_scale[r];
+      if (hi != nullptr) OutConv<OT>::put(x, hi, lo, (int64_t)r * ld + c);
+    }
+    tile[i][threadIdx.x] = x;
+  }
+  if (hiT == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < n_rows && c < width) OutConv<OT>::put(tile[threadIdx.x][i], hiT, loT, (int64_t)c * ldT + r);
+  }
+}
+
+// ----------------------------------------------------------------- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// 2-D K-major operand [rows, K] with leading dimension ld (elements).
+template <int MODE>
+static int make_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, int box_rows) {
+  using T = ModeTraits<MODE>;
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    bess_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return BESS_ERR_CUDA;
+  }
+  const CUtensorMapDataType dt = MODE == GEMM_TF32X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : MODE == GEMM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * T::kElemBytes};
+  cuuint32_t box[2] = {(cuuint32_t)T::kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = MODE == GEMM_TF32X3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    bess_set_error("cuTensorMapEncodeTiled failed (%d): base %p rows %d K %d ld %lld", (int)r, base, rows,
+                   K, (long long)ld);
+    return BESS_ERR_CUDA;
+  }
+  return BESS_OK;
+}
+
+static int choose_split(int M, int N, int K, int block_k, int* k_per_split) {
+  const int tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
+  const int kb = ceil_div(K, block_k);
+  int split = 1;
+  if (tiles < kNumSM / 2) split = min(kb, max(1, kNumSM / tiles));
+  int kb_per = ceil_div(kb, split);
+  split = ceil_div(kb, kb_per);
+  *k_per_split = kb_per * block_k;
+  return split;
+}
+
+template <int MODE>
+static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
+                       int64_t ldb, int M, int N, int K, float* out, bess_rowmap_t out_map, int64_t ld_out,
+                       int col0, int accumulate, float* workspace, int64_t workspace_bytes,
+                       cudaStream_t stream) {
+  using T = ModeTraits<MODE>;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  if (int e = make_map<MODE>(&ma_hi, a_hi, M, K, lda, kBlockM)) return e;
+  if (int e = make_map<MODE>(&mb_hi, b_hi, N, K, ldb, kBlockN)) return e;
+  if (MODE == GEMM_TF32X3) {
+    if (int e = make_map<MODE>(&ma_lo, a_lo, M, K, lda, kBlockM)) return e;
+    if (int e = make_map<MODE>(&mb_lo, b_lo, N, K, ldb, kBlockN)) return e;
+  } else {
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.n_split = choose_split(M, N, K, T::kBlockK, &p.k_per_split);
+  p.ld_partial = (N + 3) & ~3;
+  if (p.n_split > 1 && (int64_t)p.n_split * M * p.ld_partial * 4 > workspace_bytes) {
+    // not enough workspace for split-K: fall back to a single pass over K
+    p.n_split = 1;
+    p.k_per_split = ceil_div(K, T::kBlockK) * T::kBlockK;
+  }
+  p.out = out; p.out_map = out_map; p.ld_out = ld_out; p.col0 = col0; p.accumulate = accumulate;
+  p.partial = workspace;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes<MODE>());
+    if (e != cudaSuccess) {
+      bess_set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
+      return BESS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int n_tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN) * p.n_split;
+  const int grid = min(n_tiles, kNumSM);
+  gemm_tc_kernel<MODE><<<grid, kThreads, smem_bytes<MODE>(), stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  BESS_CHECK_LAUNCH();
+  if (p.n_split > 1) {
+    const int64_t total = (int64_t)M * N;
+    const int64_t want = (total + 255) / 256;
+    const int blocks = (int)(want < 8 * kNumSM ? want : 8 * kNumSM);
+    gemm_reduce_kernel<<<blocks, 256, 0, stream>>>(workspace, p.n_split, M, N, p.ld_partial, out, out_map,
+                                                   ld_out, col0, accumulate);
+    BESS_CHECK_LAUNCH();
+  }
+  return BESS_OK;
+}
+
+}  // namespace tc
+}  // namespace bess
+
+using namespace bess;
+using namespace bess::tc;
+
+extern "C" int64_t bess_dot_gemm_workspace(int M, int N, int K) {
+  // worst case of choose_split over both precision modes
+  int kps;
+  const int s0 = choose_split(M, N, K, ModeTraits<GEMM_TF32X3>::kBlockK, &kps);
+  const int s1 = choose_split(M, N, K, ModeTraits<GEMM_BF16>::kBlockK, &kps);
+  const int s = s0 > s1 ? s0 : s1;
+  return s > 1 ? (int64_t)s * M * ((N + 3) & ~3) * 4 : 0;
+}
+
+extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
+                             const void* b_lo, int64_t ldb, int M, int N, int K, float* out,
+                             bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return BESS_OK;
+  const int es = dtype == BESS_F32 ? 4 : 2;
+  BESS_CHECK_ARG(a_hi && b_hi && out, "bess_dot_gemm: null operand");
+  BESS_CHECK_ARG(dtype != BESS_F32 || (a_lo && b_lo), "bess_dot_gemm: fp32 needs the lo operands");
+  BESS_CHECK_ARG((lda * es) % 16 == 0 && (ldb * es) % 16 == 0,
+                 "bess_dot_gemm: operand leading dimensions must be multiples of 16 bytes");
+  BESS_CHECK_ARG(((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) % 16 == 0,
+                 "bess_dot_gemm: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case BESS_F32:
+      return launch_gemm<GEMM_TF32X3>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0,
+                                      accumulate, (float*)workspace, workspace_bytes, st);
+    case BESS_F16:
+      return launch_gemm<GEMM_F16>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0,
+                                   accumulate, (float*)workspace, workspace_bytes, st);
+    case BESS_BF16:
+      return launch_gemm<GEMM_BF16>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0,
+                                    accumulate, (float*)workspace, workspace_bytes, st);
+    default:
+      bess_set_error("bess_dot_gemm: unknown dtype %d", dtype);
+      return BESS_ERR_INVALID_ARG;
+  }
+}
+
+extern "C" int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,
+                                  const float* row_scale, int out_dtype, void* hi, void* lo, int64_t ld,
+                                  void* hiT, void* loT, int64_t ldT, void* stream) {
+  if (n_rows <= 0 || width <= 0) return BESS_OK;
+  BESS_CHECK_ARG(hi != nullptr || hiT != nullptr, "bess_split_operand: no output");
+  BESS_CHECK_ARG(out_dtype != BESS_F32 || ((hi == nullptr || lo != nullptr) && (hiT == nullptr || loT != nullptr)),
+                 "bess_split_operand: fp32 output needs the lo arrays");
+  const dim3 grid(ceil_div(width, 32), ceil_div(n_rows, 32)), block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SPLIT_LAUNCH(ST, OT)                                                                          \
+  split_operand_kernel<ST, OT><<<grid, block, 0, st>>>(src, n_rows, width, row_scale, (OT*)hi, (OT*)lo, \
+                                                       ld, (OT*)hiT, (OT*)loT, ldT)
+#define SPLIT_SRC(OT)                                                           \
+  switch (src_dtype) {                                                          \
+    case BESS_F32: SPLIT_LAUNCH(float, OT); break;                              \
+    case BESS_F16: SPLIT_LAUNCH(__half, OT); break;                             \
+    case BESS_BF16: SPLIT_LAUNCH(__nv_bfloat16, OT); break;                     \
+    default: bess_set_error("bess_split_operand: unknown src dtype %d", src_dtype); \
+             return BESS_ERR_INVALID_ARG;                                       \
+  }
+  switch (out_dtype) {
+    case BESS_F32: SPLIT_SRC(float); break;
+    case BESS_F16: SPLIT_SRC(__half); break;
+    case BESS_BF16: SPLIT_SRC(__nv_bfloat16); break;
+    default: bess_set_error("bess_split_operand: unknown out dtype %d", out_dtype); return BESS_ERR_INVALID_ARG;
+  }
+#undef SPLIT_SRC
+#undef SPLIT_LAUNCH
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}

@@ -134,6 +134,32 @@ def shared_bwd_cand(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query
          ptr(aux), d_cand, int(add), workspace.data_ptr(), _st(score))
 
 
+# ------------------------------------------------ tensor-core DOT path ------
+def dot_gemm_workspace(m: int, n: int, k: int) -> int:
+    return int(call("bess_dot_gemm_workspace", m, n, k))
+
+
+def split_operand(src_dt: int, src: Rows, n_rows: int, width: int,
+                  row_scale: Optional[torch.Tensor], out_dt: int,
+                  hi: Optional[torch.Tensor], lo: Optional[torch.Tensor], ld: int,
+                  hi_t: Optional[torch.Tensor], lo_t: Optional[torch.Tensor], ld_t: int,
+                  device: torch.device) -> None:
+    """rows -> dense K-major GEMM operand(s); see bess_split_operand."""
+    call("bess_split_operand", src_dt, src, n_rows, width, ptr(row_scale), out_dt, ptr(hi), ptr(lo),
+         ld, ptr(hi_t), ptr(lo_t), ld_t, torch.cuda.current_stream(device).cuda_stream)
+
+
+def dot_gemm(dt: int, a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], lda: int,
+             b_hi: torch.Tensor, b_lo: Optional[torch.Tensor], ldb: int, m: int, n: int, k: int,
+             out: torch.Tensor, out_map: RowMap, ld_out: int, col0: int, accumulate: bool,
+             workspace: Optional[torch.Tensor], out_ptr: Optional[int] = None) -> None:
+    """out[out_map(i) * ld_out + col0 + j] (+)= sum_k A[i, k] * B[j, k] on the tcgen05 path."""
+    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    call("bess_dot_gemm", dt, a_hi.data_ptr(), ptr(a_lo), lda, b_hi.data_ptr(), ptr(b_lo), ldb, m, n,
+         k, out.data_ptr() if out_ptr is None else out_ptr, out_map, ld_out, col0, int(accumulate),
+         ptr(workspace), ws_bytes, _st(a_hi))
+
+
 def pertriple_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
                   q_stride: int, n_per: int, out: torch.Tensor, score_map: RowMap, ld: int,
                   col0: int, aux: Optional[torch.Tensor]) -> None:

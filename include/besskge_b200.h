@@ -172,6 +172,32 @@ int bess_score_shared_bwd_cand(const bess_score_cfg_t* cfg, int dtype, int mode,
                                bess_rowmap_t score_map, int64_t ld, int col0, const float* aux,
                                bess_rows_t d_cand, int add_cand, void* workspace, void* stream);
 
+/* ------------------------- tensor-core path of the DOT scorers (tcgen05) ---
+ * `torch.matmul(v1, v2.T)` of broadcasted_dot_product (scoring.py:252) and the
+ * two contractions of its autograd backward, as one TMA + tcgen05.mma + TMEM
+ * kernel:   out[out_map(m) * ld_out + col0 + n] (+)= sum_k A[m, k] * B[n, k].
+ * A [M, K] and B [N, K] are dense K-major arrays (leading dimensions lda / ldb
+ * in elements, 16-byte multiples) produced by bess_split_operand:
+ *   dtype BESS_F32        : fp32 arrays hi / lo (3xTF32: hi*hi + hi*lo + lo*hi,
+ *                           fp32-grade products, fp32 accumulate in TMEM)
+ *   dtype BESS_F16 / BF16 : half arrays in *_hi (one MMA per k-step), *_lo unused
+ * Small output grids are split over K; `workspace` (>= bess_dot_gemm_workspace
+ * bytes, may be NULL when that is 0) holds the partial sums, reduced in a fixed
+ * order (deterministic). */
+int64_t bess_dot_gemm_workspace(int M, int N, int K);
+int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
+                  const void* b_lo, int64_t ldb, int M, int N, int K, float* out,
+                  bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+/* Operand pre-pass for bess_dot_gemm: rows of `src` (dtype src_dtype, addressed
+ * through map / idx / pitch, optionally scaled per row) -> dense operand arrays
+ * hi / lo [n_rows, ld] and / or their transposes hiT / loT [width, ldT].
+ * out_dtype BESS_F32: hi = rna_tf32(x), lo = rna_tf32(x - hi); BESS_F16 / BF16:
+ * hi = x rounded to that type (lo / loT ignored).  Any output may be NULL. */
+int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,
+                       const float* row_scale, int out_dtype, void* hi, void* lo, int64_t ld,
+                       void* hiT, void* loT, int64_t ldT, void* stream);
+
 /* ------------------------------------------ per-triple negative scoring ---
  * negative_sample_sharing == False: reduce_embedding(v1.unsqueeze(1) - v2)
  * (scoring.py:199, 254): query q against its OWN n_per candidates; candidate
