@@ -185,15 +185,36 @@ def kernel_rooflines(model, sf, prob, pk):
     qv = torch.randn(S, nvec, W, device=dev)
     cand = out[2 * S:]
     scores = torch.empty(S, N, device=dev)
-    t_score = time_kernel(lambda: K.shared_fwd(cfg, dt, L.MODE_TAILS, qv, S, L.rows(cand), None, N,
-                                               scores, L.IDENT, N, 0, None))
-    is_gemm = prob["fam"] in ("DistMult", "ComplEx") or prob["p"] == 2
-    if is_gemm:
+    if prob["fam"] in ("DistMult", "ComplEx"):
+        # dominant kernel: the tcgen05 contraction (forward scores = Q C^T; the two backward
+        # contractions have the same flop count)
+        from besskge_b200.bess import _TcOperand
+        ws = K.Workspace(dev)
+        q_op = _TcOperand(ws, "bq", S, W, ent.dtype, False)
+        q_op.fill(L.F32, L.rows(qv.view(S, W)), dt, None, dev)
+        c_op = _TcOperand(ws, "bc", N, W, ent.dtype, False)
+        c_op.fill(dt, L.rows(cand), dt, None, dev)
+        gws = torch.empty(max(K.dot_gemm_workspace(S, N, W) // 4, 1), device=dev)
+        t_score = time_kernel(lambda: K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
+                                                 S, N, W, scores, L.IDENT, N, 0, False, gws))
+        passes = 3 if ent.dtype == torch.float32 else 1
         work = 2.0 * S * N * W
-        roof = dict(kernel="pair_fwd_kernel (shared-negative scoring, CUDA-core fp32 path)",
+        roof = dict(kernel="gemm_tc_kernel (tcgen05 shared-negative scores = Q C^T, "
+                           + ("3xTF32: 3 tf32 MMAs per product = 6 bf16-equivalent passes"
+                              if passes == 3 else "one kind::f16 MMA per product") + ")",
+                    bound="tensor", achieved=work / t_score / 1e12, peak=pk["tensor"],
+                    unit="TFLOP/s", traffic=None, mma_passes=passes,
+                    tensor_pipe_tflops=work * passes * (2 if passes == 3 else 1) / t_score / 1e12)
+    elif prob["p"] == 2:
+        t_score = time_kernel(lambda: K.shared_fwd(cfg, dt, L.MODE_TAILS, qv, S, L.rows(cand), None, N,
+                                                   scores, L.IDENT, N, 0, None))
+        work = 2.0 * S * N * W
+        roof = dict(kernel="pair_fwd_kernel (shared-negative L2 scoring, CUDA-core fp32 path)",
                     bound="tensor", achieved=work / t_score / 1e12, peak=pk["tensor"],
                     unit="TFLOP/s", traffic=None)
     else:
+        t_score = time_kernel(lambda: K.shared_fwd(cfg, dt, L.MODE_TAILS, qv, S, L.rows(cand), None, N,
+                                                   scores, L.IDENT, N, 0, None))
         work = (S * nvec * W * 4) + N * W * es + S * N * 4
         roof = dict(kernel="pair_fwd_kernel (shared-negative L1 scoring)", bound="hbm",
                     achieved=work / t_score / 1e9, peak=pk["hbm"], unit="GB/s", traffic=None)

@@ -117,6 +117,38 @@ class _Pass:
     aug: bool = False  # candidates are the micro-batch's own heads / tails
 
 
+# Shared-negative DistMult / ComplEx contractions run on the tcgen05 GEMM
+# (csrc/gemm_tc.cu).  The exact-fp32 CUDA-core tile kernel (csrc/pair.cu)
+# computes the same thing and is kept selectable for A/B parity tests only.
+USE_TENSOR_CORES = True
+
+
+def _pad8(x: int) -> int:
+    return (x + 7) // 8 * 8
+
+
+class _TcOperand:
+    """Dense K-major operand arrays of one matrix for bess_dot_gemm: hi (+ lo
+    for 3xTF32) [rows, ld] and, when `transpose`, hiT (+ loT) [width, ldt]."""
+
+    def __init__(self, ws: "K.Workspace", tag: str, n_rows: int, width: int,
+                 dtype: torch.dtype, transpose: bool) -> None:
+        two = dtype == torch.float32
+        self.n_rows, self.width = n_rows, width
+        self.ld, self.ldt = _pad8(width), _pad8(n_rows)
+        self.hi = ws.get(f"tc_{tag}_hi", (n_rows, self.ld), dtype)
+        self.lo = ws.get(f"tc_{tag}_lo", (n_rows, self.ld), dtype) if two else None
+        self.hit = self.lot = None
+        if transpose:
+            self.hit = ws.get(f"tc_{tag}_hiT", (width, self.ldt), dtype)
+            self.lot = ws.get(f"tc_{tag}_loT", (width, self.ldt), dtype) if two else None
+
+    def fill(self, src_dt: int, src: L.Rows, out_dt: int, scale: Optional[torch.Tensor],
+             device: torch.device) -> None:
+        K.split_operand(src_dt, src, self.n_rows, self.width, scale, out_dt, self.hi, self.lo,
+                        self.ld, self.hit, self.lot, self.ldt, device)
+
+
 def _as_i32(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.int32 else t.to(torch.int32)
 
@@ -474,6 +506,20 @@ class EmbeddingMovingBessKGE(BessKGE):
         scale_buf = ws.get("cand_scale", (max(ps.n_cand for ps in passes),), torch.float32) \
             if need_scale else None
 
+        use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX)
+        tc_q: Dict[int, _TcOperand] = {}
+        tc_c: Dict[int, _TcOperand] = {}
+        gemm_ws = None
+        if use_tc and any(ps.shared for ps in passes):
+            nbytes = 0
+            for ps in passes:
+                if ps.shared:
+                    nbytes = max(nbytes, K.dot_gemm_workspace(ps.n_query, ps.n_cand, W))
+                    if train:
+                        nbytes = max(nbytes, K.dot_gemm_workspace(ps.n_query, W, ps.n_cand),
+                                     K.dot_gemm_workspace(ps.n_cand, W, ps.n_query))
+            gemm_ws = ws.get("gemm_ws", (max(nbytes // 4, 1),), torch.float32)
+
         flat = self.negative_sampler.flat_negative_format
         scheme = self.negative_sampler.corruption_scheme
 
@@ -502,13 +548,22 @@ class EmbeddingMovingBessKGE(BessKGE):
                 K.triple_fwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S, pos,
                              L.IDENT)
                 # ================= negative scores =================
-                for ps in passes:
+                for pi, ps in enumerate(passes):
                     fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
                              else L.rows(TNl, rmap=ps.fixed_map))
                     K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                    ps.n_query, qv)
                     cand = self._cand_rows(ps, Hl, TNl, local)
-                    if ps.shared:
+                    if ps.shared and use_tc:
+                        # scores = Q C^T on the tensor cores (scoring.py:252)
+                        q_op = tc_q[pi] = _TcOperand(ws, f"q{pi}", ps.n_query, W, tdt, train)
+                        q_op.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
+                        c_op = tc_c[pi] = _TcOperand(ws, f"c{pi}", ps.n_cand, W, tdt, train)
+                        c_op.fill(dt, cand, dt, None, dev)
+                        K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
+                                   ps.n_query, ps.n_cand, W, neg, ps.qmap, N, ps.col0, False,
+                                   gemm_ws)
+                    elif ps.shared:
                         scale = None
                         if need_scale:
                             scale = scale_buf[:ps.n_cand]
@@ -551,16 +606,32 @@ class EmbeddingMovingBessKGE(BessKGE):
                                  pos, d_pos[li], L.IDENT, L.rows(dHl),
                                  L.rows(dTNl, rmap=L.rowmap(p, per, 0)), dRq[li], False, False,
                                  False)
-                    for ps in passes:
+                    for pi, ps in enumerate(passes):
                         fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
                                  else L.rows(TNl, rmap=ps.fixed_map))
                         d_fixed = (L.rows(dHl, rmap=ps.fixed_map) if ps.fixed_from_head
                                    else L.rows(dTNl, rmap=ps.fixed_map))
-                        K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
-                                       ps.n_query, qv)
                         cand = self._cand_rows(ps, Hl, TNl, local)
                         d_cand = self._cand_rows(ps, dHl, dTNl, local)
                         a = None if aux is None else aux[li]
+                        if ps.shared and use_tc:
+                            # dQ = dS C and dC = dS^T Q on the tensor cores; the operand
+                            # arrays of Q and C (and their transposes) survive from forward
+                            q_op, c_op = tc_q[pi], tc_c[pi]
+                            ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True)
+                            ds.fill(L.F32, L.rows(d_neg[li], rmap=ps.qmap, pitch=N,
+                                                  offset_elems=ps.col0), dt, None, dev)
+                            K.dot_gemm(dt, ds.hi, ds.lo, ds.ld, c_op.hit, c_op.lot, c_op.ldt,
+                                       ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
+                                       gemm_ws)
+                            K.dot_gemm(dt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot, q_op.ldt,
+                                       ps.n_cand, W, ps.n_query, d_qv, d_cand.map, d_cand.pitch, 0,
+                                       ps.aug, gemm_ws, out_ptr=d_cand.base)
+                            K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                           ps.n_query, d_qv, d_fixed, dRq[li], True, True)
+                            continue
+                        K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                       ps.n_query, qv)
                         if ps.shared:
                             scale = None
                             if need_scale:

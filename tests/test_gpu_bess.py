@@ -45,11 +45,13 @@ def test_bess_forward_vs_reference_golden(name):
     lower = 1.0 + (neg_g > pos_g + tol).sum(-1).float()
     upper = 1.0 + (neg_g >= pos_g - tol).sum(-1).float()
     assert bool(((ranks >= lower) & (ranks <= upper)).all())
-    # exact equality except where the reference itself saw an EXACT tie (a candidate that
-    # is the true entity scores bit-identically there; here positive and negative scores
-    # come from different reduction trees and may differ in the last ulp)
-    tie = (neg_g == pos_g).any(-1)
-    assert bool((ranks[~tie] == want[~tie]).all())
+    # exact equality wherever the reference's decisive gap exceeds 2e-6 (1 + |score|), i.e. a
+    # few ulp of the products being summed: a candidate that IS the true entity scores within
+    # an ulp or two of the positive in the reference (same numbers, different reduction trees
+    # there and here), so its side of the tie is arbitrary
+    near = ((neg_g - pos_g).abs() <= 2e-6 * (1.0 + pos_g.abs())).any(-1)
+    assert int(near.sum()) < 0.25 * near.numel()
+    assert bool((ranks[~near] == want[~near]).all())
     assert res["metrics"].shape == tuple(g["metrics"].shape)
     mrr_row = list(ev.metrics.keys()).index("mrr")
     assert_close(res["metrics"][:, mrr_row].cpu().sum(), (1.0 / want).sum(), rtol=0.05, atol=0.05)
