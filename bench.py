@@ -218,6 +218,9 @@ def kernel_rooflines(model, sf, prob, pk):
         work = (S * nvec * W * 4) + N * W * es + S * N * 4
         roof = dict(kernel="pair_fwd_kernel (shared-negative L1 scoring)", bound="hbm",
                     achieved=work / t_score / 1e9, peak=pk["hbm"], unit="GB/s", traffic=None)
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists() and prob["fam"] == "DistMult" and (S, N, W) == (16384, 2048, 256) and es == 4:
+        roof["traffic"] = json.loads(tf.read_text()).get("gemm_tc_kernel<TF32X3> fwd S=16384 N=2048 W=256")
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["launch_us"] = t_score * 1e6
     roof["peak_source"] = pk["source"]

@@ -43,6 +43,10 @@ def run(name, dtype, M, N, Kd, iters=20):
 
 if __name__ == "__main__":
     S = 16384
+    if "--one" in sys.argv:  # short run for an ncu capture
+        run("fwd  scores = Q C^T", torch.float32, S, 2048, 256, iters=2)
+        run("bwd  dC = dS^T Q", torch.float32, 2048, 256, S, iters=2)
+        sys.exit(0)
     for dtype in (torch.float32, torch.bfloat16):
         run("fwd  scores = Q C^T", dtype, S, 2048, 256)
         run("bwd  dQ = dS C", dtype, S, 256, 2048)
