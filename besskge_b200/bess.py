@@ -961,8 +961,249 @@ def training_model(model: BessKGE, optimizer: Union[SGD, AdamW],
 
 
 class TopKQueryBessKGE(torch.nn.Module):
-    """Placeholder until the top-k path is wired (next milestone)."""
+    """Top-k completion of (h, r, ?) / (?, r, t) queries against all entities or
+    a given candidate set (reference: bess.py:606-921).  Queries of every shard
+    are replicated (AllGather), scored on the shard that stores the candidates,
+    a running top-(k+1) is kept per (query, scoring shard), the best lists
+    travel back (AllToAll) and the owner merges them.
 
-    def __init__(self, *args, **kwargs) -> None:
+    B200 shape of the loop: the reference's `window_size` sliding window
+    (`poptorch.for_loop`, bess.py:771-853) exists to bound IPU SRAM; the result
+    does not depend on it (top-k is exact), so here the window is a GEMM N-tile
+    of `device_window` candidates: scores of all n*S queries against one window
+    come from the tcgen05 GEMM (DistMult / ComplEx) or the CUDA-core tile kernel
+    (distance families) and `bess_topk_merge` folds them into the best lists.
+    `window_size` is kept for API compatibility.  Inference only."""
+
+    device_window = 4096
+
+    def __init__(
+        self,
+        k: int,
+        candidate_sampler: Union[TripleBasedShardedNegativeSampler, PlaceholderNegativeSampler],
+        score_fn: BaseScoreFunction,
+        evaluation: Optional[Evaluation] = None,
+        return_scores: bool = False,
+        window_size: int = 100,
+    ) -> None:
         super().__init__()
-        raise NotImplementedError("TopKQueryBessKGE is not implemented yet in this build")
+        self.sharding = score_fn.sharding
+        self.negative_sampler = candidate_sampler
+        self.score_fn = score_fn
+        self.evaluation = evaluation
+        self.return_scores = return_scores
+        self.k = k
+        self.window_size = window_size
+        if self.negative_sampler.flat_negative_format:
+            assert (
+                score_fn.negative_sample_sharing
+            ), "Using flat negative format requires negative sample sharing"
+        elif score_fn.negative_sample_sharing:
+            raise ValueError(
+                "Negative sample sharing cannot be used with non-flat triple-specific negatives"
+            )
+        if self.negative_sampler.corruption_scheme not in ["h", "t"]:
+            raise ValueError("TopKQueryBessKGE only support 'h', 't' corruption scheme")
+        if isinstance(self.negative_sampler, TripleBasedShardedNegativeSampler):
+            assert self.negative_sampler.mask_on_gather, (
+                "TopKQueryBessKGE requires setting mask_on_gather=True in the candidate_sampler"
+            )
+        self.entity_embedding = self.score_fn.entity_embedding
+        self.entity_embedding_size: int = self.entity_embedding.shape[-1]
+        self._ws: Optional[K.Workspace] = None
+        self._placement: Optional[_Placement] = None
+        self._maps: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
+    def _setup(self) -> Tuple[K.Workspace, _Placement]:
+        dev = self.score_fn.entity_embedding.device
+        if dev.type != "cuda":
+            raise L.BessLibraryError(
+                "besskge_b200 has no CPU path: move the module to a CUDA device first"
+            )
+        if self._ws is None or self._ws.device != dev:
+            self._ws = K.Workspace(dev)
+            self._maps = None
+        if self._placement is None:
+            self._placement = _Placement(self.sharding.n_shard)
+        if self._maps is None:
+            self._maps = (
+                torch.from_numpy(np.ascontiguousarray(self.sharding.shard_counts)).to(
+                    device=dev, dtype=torch.int32),
+                torch.from_numpy(np.ascontiguousarray(self.sharding.shard_and_idx_to_entity)).to(
+                    device=dev, dtype=torch.int32),
+            )
+        return self._ws, self._placement
+
+    def forward(
+        self,
+        relation: torch.Tensor,
+        head: Optional[torch.Tensor] = None,
+        tail: Optional[torch.Tensor] = None,
+        negative: Optional[torch.Tensor] = None,
+        triple_mask: Optional[torch.Tensor] = None,
+        negative_mask: Optional[torch.Tensor] = None,
+    ) -> Dict[str, Any]:
+        """Shapes as the reference (bess.py:691-740) with a leading `bps * n_shard`
+        axis: relation / head / tail [L, S]; negative / negative_mask
+        [L, n_shard, B, Nn] (candidates local to the shard of row L) or None to
+        score against every entity; triple_mask [L, S]."""
+        ws, pl = self._setup()
+        dev = ws.device
+        counts_dev, s2e_dev = self._maps
+        ent = self.score_fn.entity_embedding.data
+        rel_table = self.score_fn.relation_embedding.data
+        n = self.sharding.n_shard
+        Es = ent.shape[1]
+        W = ent.shape[-1]
+        cfg = self.score_fn.kernel_cfg()
+        tdt = ent.dtype
+        dt = L.dtype_code(tdt)
+        scheme = self.negative_sampler.corruption_scheme
+        mode = L.MODE_TAILS if scheme == "t" else L.MODE_HEADS
+        fixed_h, truth_h = (head, tail) if scheme == "t" else (tail, head)
+        if fixed_h is None:
+            raise ValueError("queries need the known entity: head for 't', tail for 'h'")
+        L_rows, S = relation.shape[0], relation.shape[-1]
+        if L_rows % n != 0:
+            raise ValueError(f"leading axis {L_rows} is not a multiple of n_shard={n}")
+        bps = L_rows // n
+        kb = self.k + 1
+        nS = n * S
+        R = pl.n_local
+        flat = self.negative_sampler.flat_negative_format
+
+        def to_dev(t, dtype):
+            if t is None:
+                return None
+            if pl.distributed:
+                t = t[pl.rank::n]
+            return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+
+        rel = to_dev(relation.reshape(L_rows, S), torch.int32)
+        fixed = to_dev(fixed_h.reshape(L_rows, S), torch.int32)
+        truth = to_dev(None if truth_h is None else truth_h.reshape(L_rows, S), torch.int32)
+        tmask = to_dev(None if triple_mask is None else triple_mask.reshape(L_rows, S), torch.bool)
+        cand_idx = cand_mask = None
+        if negative is not None:
+            assert negative_mask is not None
+            Nn = negative.shape[-1]
+            cand_idx = to_dev(negative.reshape(L_rows, -1, Nn), torch.int32)
+            cand_mask = to_dev(negative_mask.reshape(L_rows, -1, Nn), torch.uint8)
+            n_cand_total = Nn
+        else:
+            n_cand_total = Es
+
+        win = min(self.device_window, _pad8(n_cand_total))
+        nvec = K.call("bess_query_nvec", L.C.byref(cfg))
+        use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX) and (
+            negative is None or flat)
+        need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
+        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        Q = ws.get("tk_Q", (nS, W), tdt)
+        rel_all = ws.get("tk_rel", (nS,), torch.int32)
+        qv = ws.get("tk_qv", (nS, nvec, W), torch.float32)
+        scores = ws.get("tk_scores", (nS, win), torch.float32)
+        aux = ws.get("tk_aux", (nS, win), torch.float32) if need_aux else None
+        scale = ws.get("tk_scale", (win,), torch.float32) if need_scale else None
+        best_s = ws.get("tk_best_s", (R, nS, kb), torch.float32)
+        best_i = ws.get("tk_best_i", (R, nS, kb), torch.int32)
+        recv_s = ws.get("tk_recv_s", (R, n, S, kb), torch.float32)
+        recv_i = ws.get("tk_recv_i", (R, n, S, kb), torch.int32)
+        gemm_ws = None
+        if use_tc:
+            gemm_ws = ws.get("gemm_ws", (max(K.dot_gemm_workspace(nS, win, W) // 4, 1),),
+                             torch.float32)
+        n_out = bps * R
+        ids_out = torch.empty(n_out * S, self.k, dtype=torch.int32, device=dev)
+        sc_out = torch.empty(n_out * S, self.k, dtype=torch.float32, device=dev)
+        acc: Dict[str, List] = {}
+
+        for s in range(bps):
+            rows = [s] if pl.distributed else [s * n + r for r in pl.shards]
+            # ---- queries of every shard, replicated (bess.py:763-769)
+            if pl.distributed:
+                mine = ws.get("tk_Qmine", (S, W), tdt)
+                K.gather_rows(ent[pl.rank], fixed[rows[0]], mine)
+                torch.distributed.all_gather_into_tensor(Q.view(-1), mine.view(-1))
+                torch.distributed.all_gather_into_tensor(rel_all, rel[rows[0]].contiguous())
+            else:
+                for li, (row, shard) in enumerate(zip(rows, pl.shards)):
+                    K.gather_rows(ent[shard], fixed[row], Q[li * S:(li + 1) * S])
+                    rel_all[li * S:(li + 1) * S].copy_(rel[row])
+            K.prologue_fwd(cfg, dt, mode, L.rows(Q), rel_table, rel_all, L.IDENT, nS, qv)
+            q_op = None
+            if use_tc:
+                q_op = _TcOperand(ws, "tkq", nS, W, tdt, False)
+                q_op.fill(L.F32, L.rows(qv.view(nS, W)), dt, None, dev)
+            K.fill_f32(best_s, BAD_NEGATIVE_SCORE)
+            K.fill_i32(best_i, Es)
+            # ---- score where the candidates live, keep a running top-(k+1)
+            for li, (row, shard) in enumerate(zip(rows, pl.shards)):
+                table = ent[shard]
+                for c0 in range(0, n_cand_total, win):
+                    nc = min(win, n_cand_total - c0)
+                    if negative is None:
+                        cand = L.rows(table, offset_elems=c0 * table.stride(0))
+                        ids, ld_ids, id0 = None, 0, c0
+                        per_query = False
+                    elif flat:
+                        sel = cand_idx[row, 0, c0:c0 + nc].contiguous()
+                        cand = L.rows(table, idx=sel)
+                        ids, ld_ids, id0 = sel, 0, 0
+                        per_query = False
+                    else:
+                        sel = cand_idx[row, :, c0:c0 + nc].contiguous()  # [n*S, nc]
+                        cand = L.rows(table, idx=sel.view(-1))
+                        ids, ld_ids, id0 = sel, nc, 0
+                        per_query = True
+                    if per_query:
+                        K.pertriple_fwd(cfg, dt, mode, qv, nS, cand, nc, nc, scores, L.IDENT, win,
+                                        0, aux)
+                    elif use_tc:
+                        c_op = _TcOperand(ws, "tkc", nc, W, tdt, False)
+                        c_op.fill(dt, cand, dt, None, dev)
+                        K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld, nS, nc,
+                                   W, scores, L.IDENT, win, 0, False, gemm_ws)
+                    else:
+                        sc_ = None
+                        if need_scale:
+                            sc_ = scale[:nc]
+                            K.cand_inv_norm(dt, cand, nc, W, sc_)
+                        K.shared_fwd(cfg, dt, mode, qv, nS, cand, sc_, nc, scores, L.IDENT, win, 0,
+                                     aux)
+                    if cand_mask is not None:
+                        m = (cand_mask[row, 0:1, c0:c0 + nc] if flat
+                             else cand_mask[row, :, c0:c0 + nc]).contiguous()  # [1 or n*S, nc]
+                        K.mask_add(scores, nS, nc, win, m, nc, m.shape[0], False,
+                                   BAD_NEGATIVE_SCORE)
+                    K.topk_merge(scores, win, nS, nc, ids, ld_ids, id0, best_s[li], best_i[li], kb)
+            # ---- best lists back to the shard that owns the queries (bess.py:856-863)
+            if pl.distributed:
+                torch.distributed.all_to_all_single(recv_s.view(-1), best_s.view(-1))
+                torch.distributed.all_to_all_single(recv_i.view(-1), best_i.view(-1))
+            else:
+                recv_s.copy_(best_s.view(R, n, S, kb).transpose(0, 1))
+                recv_i.copy_(best_i.view(R, n, S, kb).transpose(0, 1))
+            for li in range(R):
+                o = s * R + li
+                K.topk_finalize(recv_s[li], recv_i[li], n, S, kb, counts_dev, s2e_dev, Es, self.k,
+                                BAD_NEGATIVE_SCORE, sc_out[o * S:(o + 1) * S],
+                                ids_out[o * S:(o + 1) * S])
+                if self.evaluation is not None:
+                    assert truth is not None, "Evaluation requires providing ground truth entities"
+                    rank = self.evaluation.ranks_from_indices(truth[rows[li]],
+                                                              ids_out[o * S:(o + 1) * S])
+                    if self.evaluation.return_ranks:
+                        acc.setdefault("ranks", []).append(rank)
+                    acc.setdefault("metrics", []).append(
+                        self.evaluation.stacked_metrics_from_ranks(
+                            rank, None if tmask is None else tmask[rows[li]]))
+
+        out: Dict[str, Any] = dict(topk_global_id=ids_out)
+        if self.return_scores:
+            out["topk_scores"] = sc_out if tdt == torch.float32 else sc_out.to(tdt)
+        if "ranks" in acc:
+            out["ranks"] = torch.cat(acc["ranks"])
+        if "metrics" in acc:
+            out["metrics"] = torch.cat(acc["metrics"], dim=0)
+        return out

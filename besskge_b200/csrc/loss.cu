@@ -235,9 +235,62 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* win_score,
   }
 }
 
+// Final merge of the per-shard best lists (bess.py:866-891): discard padding
+// rows of each scoring shard (score += bad where idx >= shard_counts[j]), map
+// local ids to global ids and select the k best of the n * kb entries.  Order:
+// score descending, ties by position in the [shard j, entry e] concatenation —
+// the stable order of the reference's flatten + topk.  One thread per query.
+__global__ void topk_finalize_kernel(const float* __restrict__ score, const int32_t* __restrict__ idx,
+                                     int n, int S, int kb, const int32_t* __restrict__ shard_counts,
+                                     const int32_t* __restrict__ shard_idx_to_entity, int Es, int k,
+                                     float bad, float* __restrict__ out_score,
+                                     int32_t* __restrict__ out_id) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= S) return;
+  const int total = n * kb;
+  float last_sc = CUDART_INF_F;
+  int last_pos = -1;
+  for (int o = 0; o < k; ++o) {
+    float best = -CUDART_INF_F;
+    int best_pos = -1;
+    for (int pos = 0; pos < total; ++pos) {
+      const int j = pos / kb, e = pos - j * kb;
+      const int64_t at = ((int64_t)j * S + q) * kb + e;
+      const int32_t id = idx[at];
+      const float sc = score[at] + (id >= shard_counts[j] ? bad : 0.f);
+      const bool eligible = sc < last_sc || (sc == last_sc && pos > last_pos);
+      if (eligible && sc > best) { best = sc; best_pos = pos; }
+    }
+    if (best_pos < 0) {  // fewer than k candidates in total
+      out_score[(int64_t)q * k + o] = -CUDART_INF_F;
+      out_id[(int64_t)q * k + o] = -1;
+      continue;
+    }
+    const int j = best_pos / kb, e = best_pos - j * kb;
+    const int32_t id = idx[((int64_t)j * S + q) * kb + e];
+    out_score[(int64_t)q * k + o] = best;
+    out_id[(int64_t)q * k + o] = shard_idx_to_entity[(int64_t)j * Es + min(id, Es - 1)];
+    last_sc = best;
+    last_pos = best_pos;
+  }
+}
+
 }  // namespace bess
 
 using namespace bess;
+
+extern "C" int bess_topk_finalize(const float* score, const int32_t* idx, int n_shard, int n_query,
+                                  int kb, const int32_t* shard_counts,
+                                  const int32_t* shard_idx_to_entity, int max_entity_per_shard, int k,
+                                  float bad_score, float* out_score, int32_t* out_id, void* stream) {
+  if (n_query == 0) return BESS_OK;
+  BESS_CHECK_ARG(k >= 1 && k <= n_shard * kb, "k=%d exceeds the %d merged entries", k, n_shard * kb);
+  topk_finalize_kernel<<<ceil_div(n_query, 128), 128, 0, (cudaStream_t)stream>>>(
+      score, idx, n_shard, n_query, kb, shard_counts, shard_idx_to_entity, max_entity_per_shard, k,
+      bad_score, out_score, out_id);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
 
 extern "C" int bess_mask_add(float* score, int n_row, int n_col, int64_t ld, const uint8_t* mask,
                              int64_t ld_mask, int mask_rows, int flag, float value, void* stream) {

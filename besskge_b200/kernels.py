@@ -260,6 +260,14 @@ def topk_merge(win_score: torch.Tensor, ld: int, n_query: int, n_win: int,
          win_id0, best_score.data_ptr(), best_id.data_ptr(), k, _st(win_score))
 
 
+def topk_finalize(score: torch.Tensor, idx: torch.Tensor, n_shard: int, n_query: int, kb: int,
+                  shard_counts: torch.Tensor, shard_idx_to_entity: torch.Tensor, es: int, k: int,
+                  bad: float, out_score: torch.Tensor, out_id: torch.Tensor) -> None:
+    call("bess_topk_finalize", score.data_ptr(), idx.data_ptr(), n_shard, n_query, kb,
+         shard_counts.data_ptr(), shard_idx_to_entity.data_ptr(), es, k, float(bad),
+         out_score.data_ptr(), out_id.data_ptr(), _st(score))
+
+
 def fill_f32(t: torch.Tensor, v: float) -> None:
     call("bess_fill_f32", t.data_ptr(), t.numel(), float(v), _st(t))
 

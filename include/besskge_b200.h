@@ -290,6 +290,17 @@ int bess_topk_merge(const float* win_score, int64_t ld, int n_query, int n_win,
                     const int32_t* win_ids, int64_t ld_ids, int win_id0, float* best_score,
                     int32_t* best_id, int k, void* stream);
 
+/* Final step of TopKQueryBessKGE (bess.py:866-891) on the shard that owns the
+ * queries: score / idx [n_shard, n_query, kb] are the best lists received from
+ * every scoring shard.  Adds bad_score to entries whose local id is a padding
+ * row of its shard (idx >= shard_counts[j]), maps local -> global ids through
+ * shard_idx_to_entity [n_shard, max_entity_per_shard] and writes the k best
+ * (score descending, ties by position) to out_score / out_id [n_query, k]. */
+int bess_topk_finalize(const float* score, const int32_t* idx, int n_shard, int n_query, int kb,
+                       const int32_t* shard_counts, const int32_t* shard_idx_to_entity,
+                       int max_entity_per_shard, int k, float bad_score, float* out_score,
+                       int32_t* out_id, void* stream);
+
 /* utility */
 int bess_fill_f32(float* p, int64_t n, float v, void* stream);
 int bess_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);

@@ -132,3 +132,110 @@ def test_training_vs_oracle_extra(fam, p, scheme, flat, shared, loss_kind, augme
     torch.cuda.synchronize()
     assert_close(sf.entity_embedding.detach().cpu(), want["ent"], rtol=1e-5, atol=2e-6)
     assert_close(sf.relation_embedding.detach().cpu(), want["rel"], rtol=1e-5, atol=2e-6)
+
+
+def _topk_compare(ids, scores, want_ids, want_scores, mask):
+    """ids must equal the reference's wherever the reference's neighbouring scores are
+    separated by more than the score tolerance; inside a near-tie group the SET of ids
+    must agree."""
+    assert_close(scores[mask], want_scores[mask], rtol=1e-5, atol=1e-5)
+    ids, want_ids, want_scores = ids[mask], want_ids[mask], want_scores[mask]
+    tol = 1e-5 + 1e-5 * want_scores.abs()
+    gap_ok = (want_scores[:, :-1] - want_scores[:, 1:]) > tol[:, 1:]
+    clean = torch.ones_like(want_ids, dtype=torch.bool)
+    clean[:, :-1] &= gap_ok
+    clean[:, 1:] &= gap_ok
+    clean[:, -1] = False  # the k-th entry may trade places with the unseen (k+1)-th
+    assert int(clean.sum()) > 0.8 * clean[:, :-1].numel()
+    assert bool((ids[clean] == want_ids[clean]).all())
+
+
+@pytest.mark.parametrize("name", golden_names("topk_"))
+def test_topk_query_vs_reference_golden(name):
+    B, H = _imports()
+    from besskge_b200.bess import TopKQueryBessKGE
+    from besskge_b200.metric import Evaluation
+    from besskge_b200.negative_sampler import PlaceholderNegativeSampler
+    from besskge_b200.sharding import Sharding
+    cfg, g = load_golden(name)
+    sh = Sharding.create(cfg["n_entity"], cfg["n_shard"], seed=cfg["seed"])
+    sf = H.make_score_fn(cfg["family"], True, cfg["p"], sh, cfg["n_rel"], cfg["d"],
+                         H.T(g["ent"]), H.T(g["rel"]))
+    ns = PlaceholderNegativeSampler(corruption_scheme=cfg["scheme"], seed=cfg["seed"])
+    ev = Evaluation(["mrr", "hits@3"], worst_rank_infty=True, reduction="sum", return_ranks=True)
+    model = TopKQueryBessKGE(k=cfg["k"], candidate_sampler=ns, score_fn=sf, evaluation=ev,
+                             return_scores=True, window_size=cfg["window"])
+    model.device_window = 24  # several windows per shard (51 rows)
+    batch = {k[3:]: H.T(v).flatten(end_dim=1) for k, v in g.items() if k.startswith("in_")}
+    res = model(**batch, triple_mask=H.T(g["triple_mask"]).flatten(end_dim=1))
+    torch.cuda.synchronize()
+    mask = H.T(g["triple_mask"]).flatten()
+    ids, scores = res["topk_global_id"].cpu(), res["topk_scores"].cpu()
+    _topk_compare(ids, scores, H.T(g["topk_global_id"]), H.T(g["topk_scores"]), mask)
+    # ranks follow from the ids: exact where the ids are exact
+    same = (ids == H.T(g["topk_global_id"])).all(-1) & mask
+    assert_close(res["ranks"].cpu()[same], H.T(g["ranks"])[same])
+    assert res["metrics"].shape == tuple(g["metrics"].shape)
+    if bool(same[mask].all()):
+        assert_close(res["metrics"].cpu(), H.T(g["metrics"]), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("fam,p", [("DistMult", 0), ("TransE", 1), ("RotatE", 2), ("PairRE", 1)])
+@pytest.mark.parametrize("flat", [True, False])
+def test_topk_query_given_candidates_vs_dense(fam, p, flat):
+    """Candidate-list variants (bess.py:712-724): top-k over masked candidate sets equals a
+    dense fp64-free restatement with the product's own score functions (the un-sharded
+    `score_tails` / `score_heads` evaluated on the same candidates)."""
+    B, H = _imports()
+    from besskge_b200.bess import TopKQueryBessKGE
+    from besskge_b200.sharding import Sharding
+    n, S, Nn, d, n_rel, n_ent, k = 2, 6, 37, 16, 4, 90, 4
+    sh = Sharding.create(n_ent, n, seed=5)
+    gen = torch.Generator().manual_seed(3)
+    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
+    rw = 2 * d if fam in ("ComplEx", "PairRE") else d
+    ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen)
+    rel = torch.randn(n_rel, rw, generator=gen)
+    sf = H.make_score_fn(fam, flat, p, sh, n_rel, d, ent, rel)
+    ns = H.fake_sampler("t", flat, triple_based=True)
+    ns.mask_on_gather = True
+    model = TopKQueryBessKGE(k=k, candidate_sampler=ns, score_fn=sf, return_scores=True)
+    model.device_window = 16
+    cmin = int(sh.shard_counts.min())
+    Bn = 1 if flat else S
+    head = torch.randint(cmin, (n, S), generator=gen, dtype=torch.int32)
+    relation = torch.randint(n_rel, (n, S), generator=gen, dtype=torch.int32)
+    # row j of `negative`: candidates stored on shard j, for the queries of every shard
+    negative = torch.stack([torch.stack([torch.randperm(cmin, generator=gen)[:Nn]
+                                         for _ in range(n * Bn)]).view(n, Bn, Nn)
+                            for _ in range(n)]).to(torch.int32)
+    nmask = torch.rand(n, n, Bn, Nn, generator=gen) > 0.2
+    res = model(relation=relation, head=head, negative=negative, negative_mask=nmask)
+    torch.cuda.synchronize()
+    ids, scores = res["topk_global_id"].cpu(), res["topk_scores"].cpu()
+    s2e = torch.from_numpy(sh.shard_and_idx_to_entity.astype("int64"))
+    for r in range(n):
+        q = ent[r][head[r].long()].cuda()
+        all_sc, all_id = [], []
+        for j in range(n):
+            if flat:
+                cidx = negative[j, 0, 0].long()
+                sc = sf.score_tails(q, relation[r].cuda(), ent[j][cidx].cuda().unsqueeze(0)).cpu()
+                m = nmask[j, 0, 0].expand(S, Nn)
+                gid = s2e[j][cidx].expand(S, Nn)
+            else:
+                cidx = negative[j, r].long()  # [S, Nn]
+                sc = sf.score_tails(q, relation[r].cuda(), ent[j][cidx].cuda()).cpu()
+                m = nmask[j, r]
+                gid = s2e[j][cidx]
+            all_sc.append(torch.where(m, sc, sc + K_BAD))
+            all_id.append(gid)
+        sc, gid = torch.cat(all_sc, 1), torch.cat(all_id, 1)
+        top = torch.topk(sc, k, dim=1)
+        assert_close(scores[r * S:(r + 1) * S], top.values, rtol=1e-5, atol=1e-5)
+        want_ids = torch.gather(gid, 1, top.indices).to(torch.int32)
+        _topk_compare(ids[r * S:(r + 1) * S], scores[r * S:(r + 1) * S], want_ids, top.values,
+                      torch.ones(S, dtype=torch.bool))
+
+
+K_BAD = -50000.0
