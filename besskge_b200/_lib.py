@@ -78,7 +78,7 @@ SIGNATURES = {
     "bess_score_shared_bwd_cand": [_CFG, _I, _I, _P, _I, Rows, _P, _I, _P, _P, RowMap, _L, _I, _P,
                                    Rows, _I, _P, _P],
     "bess_dot_gemm_workspace": [_I, _I, _I],
-    "bess_dot_gemm": [_I, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P],
+    "bess_dot_gemm": [_I, _P, _P, _L, _I, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P],
     "bess_split_operand": [_I, Rows, _I, _I, _P, _I, _P, _P, _L, _P, _P, _L, _P],
     "bess_score_pertriple_fwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, RowMap, _L, _I, _P, _P],
     "bess_score_pertriple_bwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, _P, RowMap, _L, _I, _P, _P,
@@ -86,6 +86,8 @@ SIGNATURES = {
     "bess_mask_add": [_P, _I, _I, _L, _P, _L, _I, _I, _F, _P],
     "bess_mask_diag": [_P, _I, _L, _I, _I, _I, _F, _P],
     "bess_loss_fwd_bwd": [_I, _F, _I, _F, _F, _L, _P, _P, _I, _I, _L, _P, _I, _P, _P, _P, _P],
+    "bess_loss_fwd_bwd_operand": [_I, _F, _I, _F, _F, _L, _P, _P, _I, _I, _L, _P, _I, _P, _P, _I, _P, _P,
+                                  _L, _P],
     "bess_sum_f32": [_P, _I, _P, _P],
     "bess_rank_from_scores": [_P, _P, _I, _I, _L, _I, _I, _P, _P],
     "bess_sort_workspace": [_I],

@@ -519,6 +519,18 @@ class EmbeddingMovingBessKGE(BessKGE):
                         nbytes = max(nbytes, K.dot_gemm_workspace(ps.n_query, W, ps.n_cand),
                                      K.dot_gemm_workspace(ps.n_cand, W, ps.n_query))
             gemm_ws = ws.get("gemm_ws", (max(nbytes // 4, 1),), torch.float32)
+        # The loss kernel can emit dL/dscore directly as GEMM operand arrays (no fp32 [S, N]
+        # gradient, no split / transpose pass) when every pass is a tensor-core pass over
+        # all S rows in micro-batch order and its column block is 16-byte aligned.
+        ldN = _pad8(N)
+        direct_ds = bool(
+            use_tc and train and passes
+            and all(ps.shared and ps.qmap.group <= 0 and ps.qmap.offset == 0 and ps.n_query == S
+                    and ps.col0 % 8 == 0 for ps in passes))
+        ds_hi = ds_lo = None
+        if direct_ds:
+            ds_hi = ws.get("tc_dsd_hi", (S, ldN), tdt)
+            ds_lo = ws.get("tc_dsd_lo", (S, ldN), tdt) if tdt == torch.float32 else None
 
         flat = self.negative_sampler.flat_negative_format
         scheme = self.negative_sampler.corruption_scheme
@@ -584,9 +596,15 @@ class EmbeddingMovingBessKGE(BessKGE):
                     if ce_copy:
                         neg_l.copy_(neg)
                         neg_for_loss = neg_l
-                    K.loss_fwd_bwd(lp["kind"], lp["margin"], lp["adversarial"], lp["adv_scale"],
-                                   lp["loss_scale"], lp["n_entity"], pos, neg_for_loss, S, N, N, w,
-                                   row_loss, d_pos[li], d_neg[li])
+                    if direct_ds:
+                        K.loss_fwd_bwd_operand(lp["kind"], lp["margin"], lp["adversarial"],
+                                               lp["adv_scale"], lp["loss_scale"], lp["n_entity"],
+                                               pos, neg_for_loss, S, N, N, w, row_loss, d_pos[li],
+                                               dt, ds_hi, ds_lo, ldN)
+                    else:
+                        K.loss_fwd_bwd(lp["kind"], lp["margin"], lp["adversarial"],
+                                       lp["adv_scale"], lp["loss_scale"], lp["n_entity"], pos,
+                                       neg_for_loss, S, N, N, w, row_loss, d_pos[li], d_neg[li])
                     K.sum_f32(row_loss, S, loss_out[o:o + 1])
                     if ce_copy and want_scores:
                         neg_saved = ws.get("neg_unshift", (R, S, N), torch.float32)
@@ -618,15 +636,26 @@ class EmbeddingMovingBessKGE(BessKGE):
                             # dQ = dS C and dC = dS^T Q on the tensor cores; the operand
                             # arrays of Q and C (and their transposes) survive from forward
                             q_op, c_op = tc_q[pi], tc_c[pi]
-                            ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True)
-                            ds.fill(L.F32, L.rows(d_neg[li], rmap=ps.qmap, pitch=N,
-                                                  offset_elems=ps.col0), dt, None, dev)
-                            K.dot_gemm(dt, ds.hi, ds.lo, ds.ld, c_op.hit, c_op.lot, c_op.ldt,
-                                       ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
-                                       gemm_ws)
-                            K.dot_gemm(dt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot, q_op.ldt,
-                                       ps.n_cand, W, ps.n_query, d_qv, d_cand.map, d_cand.pitch, 0,
-                                       ps.aug, gemm_ws, out_ptr=d_cand.base)
+                            if direct_ds:
+                                # dS operand arrays came straight from the loss kernel; dC reads
+                                # them MN-major (dS^T without a transposed copy)
+                                K.dot_gemm(dt, ds_hi, ds_lo, ldN, c_op.hit, c_op.lot, c_op.ldt,
+                                           ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
+                                           gemm_ws, a_offset_elems=ps.col0)
+                                K.dot_gemm(dt, ds_hi, ds_lo, ldN, q_op.hit, q_op.lot, q_op.ldt,
+                                           ps.n_cand, W, ps.n_query, d_qv, d_cand.map, d_cand.pitch,
+                                           0, ps.aug, gemm_ws, out_ptr=d_cand.base,
+                                           a_mn_major=True, a_offset_elems=ps.col0)
+                            else:
+                                ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True)
+                                ds.fill(L.F32, L.rows(d_neg[li], rmap=ps.qmap, pitch=N,
+                                                      offset_elems=ps.col0), dt, None, dev)
+                                K.dot_gemm(dt, ds.hi, ds.lo, ds.ld, c_op.hit, c_op.lot, c_op.ldt,
+                                           ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
+                                           gemm_ws)
+                                K.dot_gemm(dt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot,
+                                           q_op.ldt, ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
+                                           d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base)
                             K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                            ps.n_query, d_qv, d_fixed, dRq[li], True, True)
                             continue

@@ -52,6 +52,11 @@ struct ModeTraits {
   static constexpr uint64_t kLayoutType = MODE == GEMM_TF32X3 ? 4 : 2;
   // instruction-descriptor operand format: 0 = F16, 1 = BF16, 2 = TF32
   static constexpr uint32_t kFmt = MODE == GEMM_TF32X3 ? 2u : (MODE == GEMM_BF16 ? 1u : 0u);
+  // MN-major A (A stored [K, M], M contiguous): SWIZZLE_128B atoms of 8 K-rows x 128 B of M
+  static constexpr int kMnAtom = 128 / kElemBytes;        // M elements per atom
+  static constexpr int kMnAtoms = kBlockM / kMnAtom;      // atoms along M per tile
+  static constexpr int kMnSlab = kBlockK * 128;           // bytes of one atom column (all K rows)
+  static constexpr int kMnKStep = (32 / kElemBytes) * 128;  // bytes of K consumed per MMA
 };
 
 constexpr int kBarrierBytes = 256;
@@ -177,6 +182,26 @@ BESS_D uint64_t smem_desc(uint32_t addr) {
   return d;
 }
 
+// MN-major descriptor: leading byte offset = distance between consecutive
+// 128-byte atoms along M, stride byte offset = distance between consecutive
+// K-groups of the swizzle atom.  16-bit operands: SWIZZLE_128B, 8 K-rows per
+// atom.  32-bit (tf32) operands: the only MN-major layout the tensor core
+// accepts is SWIZZLE_128B_BASE32B (32-byte swizzle granules, 4 K-rows per atom;
+// TMA counterpart CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+template <int MODE>
+BESS_D uint64_t smem_desc_mn(uint32_t addr) {
+  using T = ModeTraits<MODE>;
+  constexpr uint64_t kSbo = MODE == GEMM_TF32X3 ? 512 : 1024;
+  constexpr uint64_t kType = MODE == GEMM_TF32X3 ? 1 : 2;
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(T::kMnSlab >> 4) << 16;
+  d |= (kSbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= kType << 61;
+  return d;
+}
+
 struct GemmParams {
   int M, N, K;
   int k_per_split;  // multiple of kBlockK; split count = ceil(K / k_per_split)
@@ -190,7 +215,7 @@ struct GemmParams {
   int64_t ld_partial;
 };
 
-template <int MODE>
+template <int MODE, bool A_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -252,12 +277,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t sa = smem_base + stage * T::kStageBytes;
           const uint32_t sb = sa + T::kOperandTiles * T::kATile;
           mbar_expect_tx(full_bar(stage), T::kStageBytes);
-          tma_load_2d(sa, &map_a_hi, full_bar(stage), k, m0);
-          tma_load_2d(sb, &map_b_hi, full_bar(stage), k, n0);
-          if (MODE == GEMM_TF32X3) {
-            tma_load_2d(sa + T::kATile, &map_a_lo, full_bar(stage), k, m0);
-            tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < T::kMnAtoms; ++i) {
+              tma_load_2d(sa + i * T::kMnSlab, &map_a_hi, full_bar(stage), m0 + i * T::kMnAtom, k);
+              if (MODE == GEMM_TF32X3)
+                tma_load_2d(sa + T::kATile + i * T::kMnSlab, &map_a_lo, full_bar(stage),
+                            m0 + i * T::kMnAtom, k);
+            }
+          } else {
+            tma_load_2d(sa, &map_a_hi, full_bar(stage), k, m0);
+            if (MODE == GEMM_TF32X3) tma_load_2d(sa + T::kATile, &map_a_lo, full_bar(stage), k, m0);
           }
+          tma_load_2d(sb, &map_b_hi, full_bar(stage), k, n0);
+          if (MODE == GEMM_TF32X3) tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -266,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ============================= MMA issuer =============================
     if (lane == 0) {
       // instruction descriptor: D = F32, A/B format, K-major both, N >> 3, M >> 4
-      const uint32_t idesc = (1u << 4) | (T::kFmt << 7) | (T::kFmt << 10) |
+      const uint32_t idesc = (1u << 4) | (T::kFmt << 7) | (T::kFmt << 10) | ((A_MN ? 1u : 0u) << 15) |
                              ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -288,10 +321,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t sb = sa + T::kOperandTiles * T::kATile;
 #pragma unroll
           for (int ks = 0; ks < T::kKSteps; ++ks) {
-            const uint64_t a_hi = smem_desc<MODE>(sa + ks * 32);
+            const uint64_t a_hi = A_MN ? smem_desc_mn<MODE>(sa + ks * T::kMnKStep) : smem_desc<MODE>(sa + ks * 32);
             const uint64_t b_hi = smem_desc<MODE>(sb + ks * 32);
             if (MODE == GEMM_TF32X3) {
-              const uint64_t a_lo = smem_desc<MODE>(sa + T::kATile + ks * 32);
+              const uint64_t a_lo = A_MN ? smem_desc_mn<MODE>(sa + T::kATile + ks * T::kMnKStep)
+                                         : smem_desc<MODE>(sa + T::kATile + ks * 32);
               const uint64_t b_lo = smem_desc<MODE>(sb + T::kBTile + ks * 32);
               umma<MODE>(tmem_d, a_lo, b_hi, idesc, first ? 0u : 1u);
               umma<MODE>(tmem_d, a_hi, b_lo, idesc, 1u);
@@ -462,6 +496,11 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D K-major operand [rows, K] with leading dimension ld (elements).
+// MN-major A: stored [K, M] (M contiguous, leading dimension ld), boxes of one 128-byte atom
+// of M by kBlockK rows of K, SWIZZLE_128B.
+template <int MODE>
+static int make_map_mn(CUtensorMap* map, const void* base, int M, int K, int64_t ld);
+
 template <int MODE>
 static int make_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, int box_rows) {
   using T = ModeTraits<MODE>;
@@ -489,6 +528,33 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int K, int64_t
   return BESS_OK;
 }
 
+template <int MODE>
+static int make_map_mn(CUtensorMap* map, const void* base, int M, int K, int64_t ld) {
+  using T = ModeTraits<MODE>;
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    bess_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return BESS_ERR_CUDA;
+  }
+  const CUtensorMapDataType dt = MODE == GEMM_TF32X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : MODE == GEMM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * T::kElemBytes};
+  cuuint32_t box[2] = {(cuuint32_t)T::kMnAtom, (cuuint32_t)T::kBlockK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  MODE == GEMM_TF32X3 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    bess_set_error("cuTensorMapEncodeTiled (MN-major A) failed (%d): base %p M %d K %d ld %lld", (int)r,
+                   base, M, K, (long long)ld);
+    return BESS_ERR_CUDA;
+  }
+  return BESS_OK;
+}
+
 static int choose_split(int M, int N, int K, int block_k, int* k_per_split) {
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
   const int kb = ceil_div(K, block_k);
@@ -500,17 +566,19 @@ static int choose_split(int M, int N, int K, int block_k, int* k_per_split) {
   return split;
 }
 
-template <int MODE>
+template <int MODE, bool A_MN>
 static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
                        int64_t ldb, int M, int N, int K, float* out, bess_rowmap_t out_map, int64_t ld_out,
                        int col0, int accumulate, float* workspace, int64_t workspace_bytes,
                        cudaStream_t stream) {
   using T = ModeTraits<MODE>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (int e = make_map<MODE>(&ma_hi, a_hi, M, K, lda, kBlockM)) return e;
+  if (int e = A_MN ? make_map_mn<MODE>(&ma_hi, a_hi, M, K, lda) : make_map<MODE>(&ma_hi, a_hi, M, K, lda, kBlockM))
+    return e;
   if (int e = make_map<MODE>(&mb_hi, b_hi, N, K, ldb, kBlockN)) return e;
   if (MODE == GEMM_TF32X3) {
-    if (int e = make_map<MODE>(&ma_lo, a_lo, M, K, lda, kBlockM)) return e;
+    if (int e = A_MN ? make_map_mn<MODE>(&ma_lo, a_lo, M, K, lda) : make_map<MODE>(&ma_lo, a_lo, M, K, lda, kBlockM))
+      return e;
     if (int e = make_map<MODE>(&mb_lo, b_lo, N, K, ldb, kBlockN)) return e;
   } else {
     ma_lo = ma_hi;
@@ -529,7 +597,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   p.partial = workspace;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes<MODE>());
     if (e != cudaSuccess) {
       bess_set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
@@ -539,7 +607,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   }
   const int n_tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN) * p.n_split;
   const int grid = min(n_tiles, kNumSM);
-  gemm_tc_kernel<MODE><<<grid, kThreads, smem_bytes<MODE>(), stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  gemm_tc_kernel<MODE, A_MN><<<grid, kThreads, smem_bytes<MODE>(), stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   BESS_CHECK_LAUNCH();
   if (p.n_split > 1) {
     const int64_t total = (int64_t)M * N;
@@ -567,9 +635,9 @@ extern "C" int64_t bess_dot_gemm_workspace(int M, int N, int K) {
   return s > 1 ? (int64_t)s * M * ((N + 3) & ~3) * 4 : 0;
 }
 
-extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
-                             const void* b_lo, int64_t ldb, int M, int N, int K, float* out,
-                             bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate,
+extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, int a_mn_major,
+                             const void* b_hi, const void* b_lo, int64_t ldb, int M, int N, int K,
+                             float* out, bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate,
                              void* workspace, int64_t workspace_bytes, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return BESS_OK;
   const int es = dtype == BESS_F32 ? 4 : 2;
@@ -580,20 +648,22 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
   BESS_CHECK_ARG(((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) % 16 == 0,
                  "bess_dot_gemm: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+#define GEMM_GO(MODE)                                                                                   \
+  return a_mn_major ? launch_gemm<MODE, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, \
+                                              ld_out, col0, accumulate, (float*)workspace,             \
+                                              workspace_bytes, st)                                     \
+                    : launch_gemm<MODE, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, \
+                                               ld_out, col0, accumulate, (float*)workspace,            \
+                                               workspace_bytes, st)
   switch (dtype) {
-    case BESS_F32:
-      return launch_gemm<GEMM_TF32X3>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0,
-                                      accumulate, (float*)workspace, workspace_bytes, st);
-    case BESS_F16:
-      return launch_gemm<GEMM_F16>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0,
-                                   accumulate, (float*)workspace, workspace_bytes, st);
-    case BESS_BF16:
-      return launch_gemm<GEMM_BF16>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0,
-                                    accumulate, (float*)workspace, workspace_bytes, st);
+    case BESS_F32: GEMM_GO(GEMM_TF32X3);
+    case BESS_F16: GEMM_GO(GEMM_F16);
+    case BESS_BF16: GEMM_GO(GEMM_BF16);
     default:
       bess_set_error("bess_dot_gemm: unknown dtype %d", dtype);
       return BESS_ERR_INVALID_ARG;
   }
+#undef GEMM_GO
 }
 
 extern "C" int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,

@@ -39,39 +39,155 @@ __global__ void mask_diag_kernel(float* score, int n_row, int64_t ld, int step, 
 }
 
 // ---------------------------------------------------------------------------
-// Loss forward + gradient w.r.t. scores.
+// Loss forward + gradient w.r.t. scores.  One CTA per query row.  The row is
+// read ONCE with 128-bit loads into registers (up to L_CACHE * L_THREADS
+// scores; longer rows re-read the tail from L2) and the gradient is written
+// once, either as plain fp32 or directly in the operand form the tcgen05
+// backward contractions consume (GRAD_TF32: hi = rna_tf32(g), lo =
+// rna_tf32(g - hi); GRAD_BF16 / GRAD_F16: rounded halves), which removes a
+// separate split pass over the [S, N] gradient.
 // ---------------------------------------------------------------------------
-template <int KIND>
+constexpr int L_CACHE = 16;  // scores per thread kept in registers
+enum GradOut { GRAD_F32 = 0, GRAD_TF32 = 1, GRAD_BF16 = 2, GRAD_F16 = 3 };
+
+BESS_D float rna_tf32_(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int OUT>
+BESS_D void store_grad4(void* g_hi, void* g_lo, int64_t at, const float (&g)[4], int n_valid, bool vec) {
+  if (OUT == GRAD_F32 || OUT == GRAD_TF32) {
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = OUT == GRAD_TF32 ? rna_tf32_(g[j]) : g[j];
+      l[j] = OUT == GRAD_TF32 ? rna_tf32_(g[j] - h[j]) : 0.f;
+    }
+    float* ph = reinterpret_cast<float*>(g_hi) + at;
+    float* pl = reinterpret_cast<float*>(g_lo) + at;
+    if (vec && n_valid == 4) {
+      *reinterpret_cast<float4*>(ph) = make_float4(h[0], h[1], h[2], h[3]);
+      if (OUT == GRAD_TF32) *reinterpret_cast<float4*>(pl) = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < n_valid) {
+          ph[j] = h[j];
+          if (OUT == GRAD_TF32) pl[j] = l[j];
+        }
+    }
+  } else if (OUT == GRAD_BF16) {
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(g_hi) + at;
+    if (vec && n_valid == 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(g[0], g[1]), b = __floats2bfloat162_rn(g[2], g[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(ph) = u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < n_valid) ph[j] = __float2bfloat16_rn(g[j]);
+    }
+  } else {
+    __half* ph = reinterpret_cast<__half*>(g_hi) + at;
+    if (vec && n_valid == 4) {
+      __half2 a = __floats2half2_rn(g[0], g[1]), b = __floats2half2_rn(g[2], g[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(ph) = u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < n_valid) ph[j] = __float2half_rn(g[j]);
+    }
+  }
+}
+
+template <int KIND, int OUT>
 __global__ void __launch_bounds__(L_THREADS) loss_kernel(float margin, int adversarial,
                                                           float adv_scale, float loss_scale,
                                                           float ce_shift, const float* pos,
                                                           float* neg, int n, int n_neg, int64_t ld,
                                                           const float* weight, int weight_n,
                                                           float* row_loss, float* d_pos,
-                                                          float* d_neg) {
+                                                          void* g_hi, void* g_lo, int64_t ld_g) {
   __shared__ float red[L_THREADS / 32];
   const int r = blockIdx.x;
-  const float* nrow = neg + (int64_t)r * ld;
-  float* grow = d_neg + (int64_t)r * ld;
+  float* nrow = neg + (int64_t)r * ld;
+  const int64_t grow = (int64_t)r * ld_g;
   const float w = weight_n == 1 ? weight[0] : weight[r];
   const float p = pos[r];
+  const bool vec_in = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(neg) & 15) == 0;
+  constexpr int kGradBytes = (OUT == GRAD_BF16 || OUT == GRAD_F16) ? 2 : 4;
+  const bool vec_out = (ld_g & 3) == 0 && (reinterpret_cast<uintptr_t>(g_hi) & 15) == 0 &&
+                       (OUT != GRAD_TF32 || (reinterpret_cast<uintptr_t>(g_lo) & 15) == 0);
+  (void)kGradBytes;
+
+  // ---- the row, in registers: slot (i, j) <-> column (i * L_THREADS + tid) * 4 + j
+  float v[L_CACHE];
+#pragma unroll
+  for (int i = 0; i < L_CACHE / 4; ++i) {
+    const int c = (i * L_THREADS + threadIdx.x) * 4;
+    if (vec_in && c + 4 <= n_neg) {
+      const float4 t = *reinterpret_cast<const float4*>(nrow + c);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 * i + j] = c + j < n_neg ? nrow[c + j] : 0.f;
+    }
+  }
+  constexpr int kCached = L_CACHE * L_THREADS;  // columns beyond this are re-read
 
   if (KIND == BESS_LOSS_SOFTMAX_CE) {
     // scores adjusted in place by log(E-1) - log(N) (loss.py:233-237), then
     // cross entropy of [pos, neg...] against class 0
     float mx = p;
-    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) {
-      const float v = nrow[c] + ce_shift;
-      neg[(int64_t)r * ld + c] = v;
-      mx = fmaxf(mx, v);
+#pragma unroll
+    for (int i = 0; i < L_CACHE / 4; ++i) {
+      const int c = (i * L_THREADS + threadIdx.x) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < n_neg) {
+          v[4 * i + j] += ce_shift;
+          nrow[c + j] = v[4 * i + j];
+          mx = fmaxf(mx, v[4 * i + j]);
+        }
+    }
+    for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) {
+      const float t = nrow[c] + ce_shift;
+      nrow[c] = t;
+      mx = fmaxf(mx, t);
     }
     mx = block_max<L_THREADS>(mx, red);
     float se = 0.f;
-    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) se += expf(neg[(int64_t)r * ld + c] - mx);
+#pragma unroll
+    for (int i = 0; i < L_CACHE / 4; ++i) {
+      const int c = (i * L_THREADS + threadIdx.x) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < n_neg) se += expf(v[4 * i + j] - mx);
+    }
+    for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) se += expf(nrow[c] - mx);
     se = block_sum<L_THREADS>(se, red) + expf(p - mx);
     const float lse = mx + logf(se);
-    for (int c = threadIdx.x; c < n_neg; c += L_THREADS)
-      grow[c] = loss_scale * w * expf(neg[(int64_t)r * ld + c] - lse);
+#pragma unroll
+    for (int i = 0; i < L_CACHE / 4; ++i) {
+      const int c = (i * L_THREADS + threadIdx.x) * 4;
+      if (c < n_neg) {
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = loss_scale * w * expf(v[4 * i + j] - lse);
+        store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out);
+      }
+    }
+    for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) {
+      float g[4] = {loss_scale * w * expf(nrow[c] - lse), 0.f, 0.f, 0.f};
+      store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false);
+    }
     if (threadIdx.x == 0) {
       row_loss[r] = loss_scale * w * (lse - p);
       d_pos[r] = loss_scale * w * (expf(p - lse) - 1.f);
@@ -83,29 +199,55 @@ __global__ void __launch_bounds__(L_THREADS) loss_kernel(float margin, int adver
   float mx = 0.f, inv_se = 1.f / (float)n_neg;
   if (adversarial) {
     mx = -CUDART_INF_F;
-    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) mx = fmaxf(mx, adv_scale * nrow[c]);
+#pragma unroll
+    for (int i = 0; i < L_CACHE / 4; ++i) {
+      const int c = (i * L_THREADS + threadIdx.x) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < n_neg) mx = fmaxf(mx, adv_scale * v[4 * i + j]);
+    }
+    for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) mx = fmaxf(mx, adv_scale * nrow[c]);
     mx = block_max<L_THREADS>(mx, red);
     float se = 0.f;
-    for (int c = threadIdx.x; c < n_neg; c += L_THREADS) se += expf(adv_scale * nrow[c] - mx);
+#pragma unroll
+    for (int i = 0; i < L_CACHE / 4; ++i) {
+      const int c = (i * L_THREADS + threadIdx.x) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < n_neg) se += expf(adv_scale * v[4 * i + j] - mx);
+    }
+    for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) se += expf(adv_scale * nrow[c] - mx);
     se = block_sum<L_THREADS>(se, red);
     inv_se = 1.f / se;
   }
   float part = 0.f, dp = 0.f;
-  for (int c = threadIdx.x; c < n_neg; c += L_THREADS) {
-    const float s = nrow[c];
+  auto one = [&](float s) -> float {  // gradient of column with score s; accumulates the loss
     const float wj = adversarial ? expf(adv_scale * s - mx) * inv_se : inv_se;
     if (KIND == BESS_LOSS_LOGSIGMOID) {
       part += wj * log_sigmoid(-s - margin);
       // d/ds [-0.5 w wj logsigmoid(-s-m)] = 0.5 w wj sigmoid(s+m)
-      grow[c] = loss_scale * 0.5f * w * wj * sigmoidf_(s + margin);
-    } else {  // margin ranking: relu(s - pos + m)
-      const float a = s - p + margin;
-      const float on = a > 0.f ? 1.f : 0.f;
-      part += wj * fmaxf(a, 0.f);
-      const float g = loss_scale * w * wj * on;
-      grow[c] = g;
-      dp -= g;
+      return loss_scale * 0.5f * w * wj * sigmoidf_(s + margin);
     }
+    // margin ranking: relu(s - pos + m)
+    const float a = s - p + margin;
+    part += wj * fmaxf(a, 0.f);
+    const float g = loss_scale * w * wj * (a > 0.f ? 1.f : 0.f);
+    dp -= g;
+    return g;
+  };
+#pragma unroll
+  for (int i = 0; i < L_CACHE / 4; ++i) {
+    const int c = (i * L_THREADS + threadIdx.x) * 4;
+    if (c < n_neg) {
+      float g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = c + j < n_neg ? one(v[4 * i + j]) : 0.f;
+      store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out);
+    }
+  }
+  for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) {
+    float g[4] = {one(nrow[c]), 0.f, 0.f, 0.f};
+    store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false);
   }
   part = block_sum<L_THREADS>(part, red);
   if (KIND == BESS_LOSS_MARGIN_RANKING) dp = block_sum<L_THREADS>(dp, red);
@@ -311,24 +453,27 @@ extern "C" int bess_mask_diag(float* score, int n_row, int64_t ld, int step, int
   return BESS_OK;
 }
 
-extern "C" int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float adv_scale,
-                                 float loss_scale, int64_t n_entity, const float* pos, float* neg,
-                                 int n, int n_neg, int64_t ld, const float* weight, int weight_n,
-                                 float* row_loss, float* d_pos, float* d_neg, void* stream) {
-  if (n == 0) return BESS_OK;
-  BESS_CHECK_ARG(n_neg > 0, "loss needs at least one negative");
-  BESS_CHECK_ARG(weight_n == 1 || weight_n == n, "triple_weight has %d entries, need 1 or %d", weight_n, n);
-  cudaStream_t st = (cudaStream_t)stream;
+template <int OUT>
+static int launch_loss(int kind, float margin, int adversarial, float adv_scale, float loss_scale,
+                       int64_t n_entity, const float* pos, float* neg, int n, int n_neg, int64_t ld,
+                       const float* weight, int weight_n, float* row_loss, float* d_pos, void* g_hi,
+                       void* g_lo, int64_t ld_g, cudaStream_t st) {
   switch (kind) {
     case BESS_LOSS_LOGSIGMOID:
-      loss_kernel<BESS_LOSS_LOGSIGMOID><<<n, L_THREADS, 0, st>>>(margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg);
+      loss_kernel<BESS_LOSS_LOGSIGMOID, OUT><<<n, L_THREADS, 0, st>>>(
+          margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n,
+          row_loss, d_pos, g_hi, g_lo, ld_g);
       break;
     case BESS_LOSS_MARGIN_RANKING:
-      loss_kernel<BESS_LOSS_MARGIN_RANKING><<<n, L_THREADS, 0, st>>>(margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg);
+      loss_kernel<BESS_LOSS_MARGIN_RANKING, OUT><<<n, L_THREADS, 0, st>>>(
+          margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n,
+          row_loss, d_pos, g_hi, g_lo, ld_g);
       break;
     case BESS_LOSS_SOFTMAX_CE: {
       const float shift = (float)(log((double)(n_entity - 1)) - log((double)n_neg));
-      loss_kernel<BESS_LOSS_SOFTMAX_CE><<<n, L_THREADS, 0, st>>>(0.f, 0, 0.f, loss_scale, shift, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg);
+      loss_kernel<BESS_LOSS_SOFTMAX_CE, OUT><<<n, L_THREADS, 0, st>>>(
+          0.f, 0, 0.f, loss_scale, shift, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos,
+          g_hi, g_lo, ld_g);
       break;
     }
     default:
@@ -337,6 +482,49 @@ extern "C" int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float 
   }
   BESS_CHECK_LAUNCH();
   return BESS_OK;
+}
+
+extern "C" int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float adv_scale,
+                                 float loss_scale, int64_t n_entity, const float* pos, float* neg,
+                                 int n, int n_neg, int64_t ld, const float* weight, int weight_n,
+                                 float* row_loss, float* d_pos, float* d_neg, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(n_neg > 0, "loss needs at least one negative");
+  BESS_CHECK_ARG(weight_n == 1 || weight_n == n, "triple_weight has %d entries, need 1 or %d", weight_n, n);
+  return launch_loss<GRAD_F32>(kind, margin, adversarial, adv_scale, loss_scale, n_entity, pos, neg, n,
+                               n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg, nullptr, ld,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int bess_loss_fwd_bwd_operand(int kind, float margin, int adversarial, float adv_scale,
+                                         float loss_scale, int64_t n_entity, const float* pos,
+                                         float* neg, int n, int n_neg, int64_t ld,
+                                         const float* weight, int weight_n, float* row_loss,
+                                         float* d_pos, int grad_dtype, void* d_neg_hi, void* d_neg_lo,
+                                         int64_t ld_grad, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(n_neg > 0, "loss needs at least one negative");
+  BESS_CHECK_ARG(weight_n == 1 || weight_n == n, "triple_weight has %d entries, need 1 or %d", weight_n, n);
+  BESS_CHECK_ARG(d_neg_hi != nullptr && (grad_dtype != BESS_F32 || d_neg_lo != nullptr),
+                 "bess_loss_fwd_bwd_operand: missing gradient output");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (grad_dtype) {
+    case BESS_F32:
+      return launch_loss<GRAD_TF32>(kind, margin, adversarial, adv_scale, loss_scale, n_entity, pos, neg,
+                                    n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg_hi, d_neg_lo,
+                                    ld_grad, st);
+    case BESS_BF16:
+      return launch_loss<GRAD_BF16>(kind, margin, adversarial, adv_scale, loss_scale, n_entity, pos, neg,
+                                    n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg_hi, nullptr,
+                                    ld_grad, st);
+    case BESS_F16:
+      return launch_loss<GRAD_F16>(kind, margin, adversarial, adv_scale, loss_scale, n_entity, pos, neg,
+                                   n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg_hi, nullptr,
+                                   ld_grad, st);
+    default:
+      bess_set_error("bess_loss_fwd_bwd_operand: unknown gradient dtype %d", grad_dtype);
+      return BESS_ERR_INVALID_ARG;
+  }
 }
 
 extern "C" int bess_sum_f32(const float* x, int n, float* out, void* stream) {

@@ -152,11 +152,15 @@ def split_operand(src_dt: int, src: Rows, n_rows: int, width: int,
 def dot_gemm(dt: int, a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], lda: int,
              b_hi: torch.Tensor, b_lo: Optional[torch.Tensor], ldb: int, m: int, n: int, k: int,
              out: torch.Tensor, out_map: RowMap, ld_out: int, col0: int, accumulate: bool,
-             workspace: Optional[torch.Tensor], out_ptr: Optional[int] = None) -> None:
-    """out[out_map(i) * ld_out + col0 + j] (+)= sum_k A[i, k] * B[j, k] on the tcgen05 path."""
+             workspace: Optional[torch.Tensor], out_ptr: Optional[int] = None,
+             a_mn_major: bool = False, a_offset_elems: int = 0) -> None:
+    """out[out_map(i) * ld_out + col0 + j] (+)= sum_k A[i, k] * B[j, k] on the tcgen05 path.
+    a_mn_major: A is stored transposed [K, M] (M contiguous, leading dimension lda)."""
     ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
-    call("bess_dot_gemm", dt, a_hi.data_ptr(), ptr(a_lo), lda, b_hi.data_ptr(), ptr(b_lo), ldb, m, n,
-         k, out.data_ptr() if out_ptr is None else out_ptr, out_map, ld_out, col0, int(accumulate),
+    off = a_offset_elems * a_hi.element_size()
+    call("bess_dot_gemm", dt, a_hi.data_ptr() + off, None if a_lo is None else a_lo.data_ptr() + off,
+         lda, int(a_mn_major), b_hi.data_ptr(), ptr(b_lo), ldb, m, n, k,
+         out.data_ptr() if out_ptr is None else out_ptr, out_map, ld_out, col0, int(accumulate),
          ptr(workspace), ws_bytes, _st(a_hi))
 
 
@@ -198,6 +202,18 @@ def loss_fwd_bwd(kind: int, margin: float, adversarial: bool, adv_scale: float, 
          float(loss_scale), int(n_entity), pos.data_ptr(), neg.data_ptr(), n, n_neg, ld,
          weight.data_ptr(), weight.numel(), row_loss.data_ptr(), d_pos.data_ptr(),
          d_neg.data_ptr(), _st(pos))
+
+
+def loss_fwd_bwd_operand(kind: int, margin: float, adversarial: bool, adv_scale: float,
+                         loss_scale: float, n_entity: int, pos: torch.Tensor, neg: torch.Tensor,
+                         n: int, n_neg: int, ld: int, weight: torch.Tensor, row_loss: torch.Tensor,
+                         d_pos: torch.Tensor, grad_dt: int, d_neg_hi: torch.Tensor,
+                         d_neg_lo: Optional[torch.Tensor], ld_grad: int) -> None:
+    """loss + dL/dscore with the [n, n_neg] gradient written as GEMM operand arrays."""
+    call("bess_loss_fwd_bwd_operand", kind, float(margin), int(adversarial), float(adv_scale),
+         float(loss_scale), int(n_entity), pos.data_ptr(), neg.data_ptr(), n, n_neg, ld,
+         weight.data_ptr(), weight.numel(), row_loss.data_ptr(), d_pos.data_ptr(), grad_dt,
+         d_neg_hi.data_ptr(), ptr(d_neg_lo), ld_grad, _st(pos))
 
 
 def sum_f32(x: torch.Tensor, n: int, out: torch.Tensor) -> None:

@@ -181,12 +181,15 @@ int bess_score_shared_bwd_cand(const bess_score_cfg_t* cfg, int dtype, int mode,
  *   dtype BESS_F32        : fp32 arrays hi / lo (3xTF32: hi*hi + hi*lo + lo*hi,
  *                           fp32-grade products, fp32 accumulate in TMEM)
  *   dtype BESS_F16 / BF16 : half arrays in *_hi (one MMA per k-step), *_lo unused
+ * a_mn_major != 0: A is given transposed, as [K, M] with M contiguous (leading
+ * dimension lda) and consumed through MN-major UMMA descriptors — how the
+ * dC = dS^T Q contraction reads the [S, N] score gradient without a transposed copy.
  * Small output grids are split over K; `workspace` (>= bess_dot_gemm_workspace
  * bytes, may be NULL when that is 0) holds the partial sums, reduced in a fixed
  * order (deterministic). */
 int64_t bess_dot_gemm_workspace(int M, int N, int K);
-int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi,
-                  const void* b_lo, int64_t ldb, int M, int N, int K, float* out,
+int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, int a_mn_major,
+                  const void* b_hi, const void* b_lo, int64_t ldb, int M, int N, int K, float* out,
                   bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate, void* workspace,
                   int64_t workspace_bytes, void* stream);
 /* Operand pre-pass for bess_dot_gemm: rows of `src` (dtype src_dtype, addressed
@@ -233,6 +236,15 @@ int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float adv_scale, 
                       int64_t n_entity, const float* pos, float* neg, int n, int n_neg,
                       int64_t ld, const float* weight, int weight_n, float* row_loss,
                       float* d_pos, float* d_neg, void* stream);
+/* Same loss, but dL/dneg is written directly in the operand form bess_dot_gemm
+ * consumes for the backward contractions: grad_dtype BESS_F32 -> d_neg_hi =
+ * rna_tf32(g), d_neg_lo = rna_tf32(g - hi) (fp32 arrays); BESS_BF16 / BESS_F16 ->
+ * d_neg_hi = g rounded to that type, d_neg_lo unused.  ld_grad in elements. */
+int bess_loss_fwd_bwd_operand(int kind, float margin, int adversarial, float adv_scale,
+                              float loss_scale, int64_t n_entity, const float* pos, float* neg, int n,
+                              int n_neg, int64_t ld, const float* weight, int weight_n,
+                              float* row_loss, float* d_pos, int grad_dtype, void* d_neg_hi,
+                              void* d_neg_lo, int64_t ld_grad, void* stream);
 /* deterministic sum of n floats (fixed order) -> out[0] */
 int bess_sum_f32(const float* x, int n, float* out, void* stream);
 

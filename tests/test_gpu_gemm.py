@@ -111,8 +111,14 @@ def test_dot_gemm_matches_fp64(name, M, N, Kd):
     ws = torch.empty(max(ws_bytes // 4, 1), device="cuda")
     K.dot_gemm(L.dtype_code(dtype), a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, Kd, out, L.IDENT, ld_out,
                1, False, ws)
+    # the same product with A handed over transposed ([K, M], MN-major UMMA descriptors)
+    at_hi, at_lo, ldat, *_ = _operands(K, L, a.t().contiguous(), dtype)
+    out_mn = torch.full((M, ld_out), 7.0, device="cuda")
+    K.dot_gemm(L.dtype_code(dtype), at_hi, at_lo, ldat, b_hi, b_lo, ldb, M, N, Kd, out_mn, L.IDENT,
+               ld_out, 1, False, ws, a_mn_major=True)
     torch.cuda.synchronize()
     assert torch.all(out[:, 0] == 7.0) and torch.all(out[:, N + 1:] == 7.0)  # untouched columns
+    assert torch.equal(out, out_mn)  # same operand values, same accumulation order
     got = out[:, 1:N + 1].double()
     if dtype == torch.float32:
         ref = a.double() @ b.double().t()

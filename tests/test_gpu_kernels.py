@@ -190,3 +190,73 @@ def test_metrics_vs_reference_golden():
     res = ev.dict_metrics_from_ranks(ev.ranks_from_scores(pos, neg))
     assert_close(res["hits@5"].cpu(), torch.tensor([0.0, 1.0, 1.0, 0.0]))
     assert_close(res["mrr"].cpu(), torch.tensor([0.0, 1 / 4, 1 / 2, 0.0]))
+
+
+@pytest.mark.parametrize("kind", ["logsigmoid", "margin_ranking", "softmax_ce"])
+@pytest.mark.parametrize("gdt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n_neg", [37, 2048, 5000])
+def test_loss_operand_gradient_matches_plain(kind, gdt, n_neg):
+    """bess_loss_fwd_bwd_operand = bess_loss_fwd_bwd with the gradient written as GEMM
+    operand arrays (tf32 hi/lo or rounded halves)."""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(n_neg)
+    n = 33
+    pos = torch.randn(n, generator=g).cuda() * 3
+    neg = (torch.randn(n, n_neg, generator=g) * 3).cuda()
+    w = (torch.rand(n, generator=g) + 0.5).cuda()
+    kd = {"logsigmoid": L.LOSS_LOGSIGMOID, "margin_ranking": L.LOSS_MARGIN_RANKING,
+          "softmax_ce": L.LOSS_SOFTMAX_CE}[kind]
+    outs = []
+    for operand in (False, True):
+        neg_c = neg.clone()
+        row_loss = torch.empty(n, device="cuda")
+        d_pos = torch.empty(n, device="cuda")
+        if operand:
+            ld = (n_neg + 7) // 8 * 8
+            hi = torch.zeros(n, ld, dtype=gdt, device="cuda")
+            lo = torch.zeros(n, ld, dtype=gdt, device="cuda") if gdt == torch.float32 else None
+            K.loss_fwd_bwd_operand(kd, 3.0, True, 0.7, 1.5, 1000, pos, neg_c, n, n_neg, n_neg, w,
+                                   row_loss, d_pos, L.dtype_code(gdt), hi, lo, ld)
+            grad = hi[:, :n_neg].float() + (lo[:, :n_neg] if lo is not None else 0)
+            if lo is not None:
+                assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        else:
+            grad = torch.empty(n, n_neg, device="cuda")
+            K.loss_fwd_bwd(kd, 3.0, True, 0.7, 1.5, 1000, pos, neg_c, n, n_neg, n_neg, w, row_loss,
+                           d_pos, grad)
+        torch.cuda.synchronize()
+        outs.append((row_loss, d_pos, grad, neg_c))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][3], outs[1][3])
+    tol = {torch.float32: 2.0 ** -21, torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -10}[gdt]
+    ref, got = outs[0][2], outs[1][2]
+    big = ref.abs() > 1e-30 if gdt != torch.float16 else ref.abs() > 1e-4
+    assert float(((got - ref).abs()[big] / ref.abs()[big]).max()) <= tol
+
+
+@pytest.mark.parametrize("kind", ["logsigmoid", "margin_ranking", "softmax_ce"])
+@pytest.mark.parametrize("n_neg", [1, 37, 2048, 5000])
+def test_loss_kernel_vs_oracle_long_rows(kind, n_neg):
+    """Register-cached loss kernel (rows longer than the 4096-score cache re-read the tail)."""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(7 + n_neg)
+    n = 19
+    pos = torch.randn(n, generator=g) * 2
+    neg = torch.randn(n, n_neg, generator=g) * 2
+    w = torch.rand(n, generator=g) + 0.5
+    cfg = dict(kind=kind, margin=2.0, adversarial=True, adv_scale=1.3, loss_scale=1.0, n_entity=777)
+    negr = neg.clone().requires_grad_(True)
+    posr = pos.clone().requires_grad_(True)
+    want = O.loss_value(cfg, posr, negr, w)
+    want.backward()
+    kd = {"logsigmoid": L.LOSS_LOGSIGMOID, "margin_ranking": L.LOSS_MARGIN_RANKING,
+          "softmax_ce": L.LOSS_SOFTMAX_CE}[kind]
+    row_loss = torch.empty(n, device="cuda")
+    d_pos = torch.empty(n, device="cuda")
+    grad = torch.empty(n, n_neg, device="cuda")
+    K.loss_fwd_bwd(kd, 2.0, True, 1.3, 1.0, 777, pos.cuda(), neg.cuda(), n, n_neg, n_neg, w.cuda(),
+                   row_loss, d_pos, grad)
+    torch.cuda.synchronize()
+    assert_close(row_loss.sum().cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+    assert_close(grad.cpu(), negr.grad, rtol=2e-5, atol=1e-7)
+    assert_close(d_pos.cpu(), posr.grad, rtol=2e-5, atol=1e-7)
