@@ -418,6 +418,22 @@ class EmbeddingMovingBessKGE(BessKGE):
                            for t in (st.gidx, st.rel, st.tw, st.nmask, st.tmask) if t is not None)
         return st
 
+    def _restage(self, staged: "_Staged") -> "_Staged":
+        """Device-to-device copy of staged inputs into the persistent input
+        buffers (fixed addresses: what a captured CUDA graph reads)."""
+        ws, _ = self._setup()
+        st = _Staged()
+        st.dims, st.h2d_bytes = staged.dims, staged.h2d_bytes
+        for name in ("gidx", "rel", "tw", "nmask", "tmask"):
+            t = getattr(staged, name)
+            if t is not None:
+                buf = ws.get("in_" + name, tuple(t.shape), t.dtype)
+                if buf.data_ptr() != t.data_ptr():
+                    buf.copy_(t, non_blocking=True)
+                t = buf
+            setattr(st, name, t)
+        return st
+
     def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
              optimizer, staged: Optional["_Staged"] = None) -> Dict[str, Any]:
         ws, pl = self._setup()
@@ -955,20 +971,37 @@ class ScoreMovingBessKGE(BessKGE):
 # ---------------------------------------------------------------------------
 class TrainingModel:
     """Callable returned by `training_model`: one call = `batches_per_step`
-    fused forward + backward + optimizer steps; returns the forward dict."""
+    fused forward + backward + optimizer steps; returns the forward dict.
+
+    With `cuda_graph=True` (default for SGD / SGD-momentum) the whole device
+    sequence of a call — gather, exchange, scoring, loss, backward, sort,
+    scatter + update — is captured once per input signature into a CUDA graph
+    and replayed: the B200 counterpart of PopTorch's `deviceIterations` loop
+    (one host launch per call instead of ~40 kernel launches).  The first call
+    with a new signature runs eagerly (it sizes the persistent workspaces), the
+    second is captured.  The returned tensors are then STATIC buffers that the
+    next call overwrites."""
 
     def __init__(self, model: BessKGE, optimizer: Union[SGD, AdamW],
-                 relation_grad_reduction: str = "mean") -> None:
+                 relation_grad_reduction: str = "mean", cuda_graph: Optional[bool] = None) -> None:
         if relation_grad_reduction not in ("mean", "sum"):
             raise ValueError("relation_grad_reduction must be 'mean' or 'sum'")
         self.model = model
         self.optimizer = optimizer
         self.optimizer.relation_grad_reduction = relation_grad_reduction
+        # AdamW's bias correction takes the step count by value: not replayable
+        graph_ok = optimizer.kind != L.OPT_ADAMW and isinstance(model, EmbeddingMovingBessKGE)
+        self.cuda_graph = graph_ok if cuda_graph is None else (bool(cuda_graph) and graph_ok)
+        self._graphs: Dict[Any, Any] = {}
 
     def __call__(self, head, relation, tail, negative, triple_mask=None, triple_weight=None,
                  negative_mask=None) -> Dict[str, Any]:
-        return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
-                               negative_mask, optimizer=self.optimizer)
+        if not self.cuda_graph:
+            return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
+                                   negative_mask, optimizer=self.optimizer)
+        staged = self.model.stage(head, relation, tail, negative, triple_mask, triple_weight,
+                                  negative_mask)  # H2D into the persistent input buffers
+        return self._run_graphed(staged)
 
     def stage(self, **batch) -> _Staged:
         """Copy a batch to the device once; see `run_staged`."""
@@ -976,17 +1009,39 @@ class TrainingModel:
 
     def run_staged(self, staged: _Staged) -> Dict[str, Any]:
         """Training step(s) on inputs that are already resident in HBM."""
-        return self.model._run(None, None, None, None, None, None, None,
-                               optimizer=self.optimizer, staged=staged)
+        if not self.cuda_graph:
+            return self.model._run(None, None, None, None, None, None, None,
+                                   optimizer=self.optimizer, staged=staged)
+        return self._run_graphed(self.model._restage(staged))
+
+    def _run_graphed(self, staged: _Staged) -> Dict[str, Any]:
+        key = (staged.dims, staged.tw is not None, staged.nmask is not None,
+               staged.tmask is not None, self.model.score_fn.entity_embedding.dtype)
+        entry = self._graphs.get(key)
+        if entry is None or entry == "warm":
+            if entry is None:
+                self._graphs[key] = "warm"
+                return self.model._run(None, None, None, None, None, None, None,
+                                       optimizer=self.optimizer, staged=staged)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                out = self.model._run(None, None, None, None, None, None, None,
+                                      optimizer=self.optimizer, staged=staged)
+            entry = self._graphs[key] = (graph, out)
+        graph, out = entry
+        graph.replay()
+        return out
 
 
 def training_model(model: BessKGE, optimizer: Union[SGD, AdamW],
-                   relation_grad_reduction: str = "mean") -> TrainingModel:
+                   relation_grad_reduction: str = "mean",
+                   cuda_graph: Optional[bool] = None) -> TrainingModel:
     """Counterpart of `poptorch.trainingModel(model, options, optimizer)`
     (reference notebooks, e.g. 1_biokg cell 28).  `relation_grad_reduction`:
     how the replicated relation table's gradient is combined over replicas
     ("mean" = PopTorch default, "sum")."""
-    return TrainingModel(model, optimizer, relation_grad_reduction)
+    return TrainingModel(model, optimizer, relation_grad_reduction, cuda_graph)
 
 
 class TopKQueryBessKGE(torch.nn.Module):

@@ -107,16 +107,53 @@ BESS_D void store_grad4(void* g_hi, void* g_lo, int64_t at, const float (&g)[4],
   }
 }
 
-template <int KIND, int OUT>
-__global__ void __launch_bounds__(L_THREADS) loss_kernel(float margin, int adversarial,
-                                                          float adv_scale, float loss_scale,
-                                                          float ce_shift, const float* pos,
-                                                          float* neg, int n, int n_neg, int64_t ld,
-                                                          const float* weight, int weight_n,
-                                                          float* row_loss, float* d_pos,
-                                                          void* g_hi, void* g_lo, int64_t ld_g) {
-  __shared__ float red[L_THREADS / 32];
-  const int r = blockIdx.x;
+struct LossArgs {
+  float margin;
+  int adversarial;
+  float adv_scale, loss_scale, ce_shift;
+  const float* pos;
+  float* neg;
+  int n, n_neg;
+  int64_t ld;
+  const float* weight;
+  int weight_n;
+  float* row_loss;
+  float* d_pos;
+  void* g_hi;
+  void* g_lo;
+  int64_t ld_g;
+};
+
+// registers <- one row of scores: slot (i, j) <-> column (i * TPB + tid) * 4 + j
+template <int TPB>
+BESS_D void loss_load_row(const float* nrow, int n_neg, bool vec_in, float (&v)[L_CACHE]) {
+#pragma unroll
+  for (int i = 0; i < L_CACHE / 4; ++i) {
+    const int c = (i * TPB + threadIdx.x) * 4;
+    if (vec_in && c + 4 <= n_neg) {
+      const float4 t = *reinterpret_cast<const float4*>(nrow + c);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 * i + j] = c + j < n_neg ? nrow[c + j] : 0.f;
+    }
+  }
+}
+
+template <int KIND, int OUT, int TPB>
+BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) {
+  constexpr int L_THREADS = TPB;
+  const float margin = a.margin, adv_scale = a.adv_scale, loss_scale = a.loss_scale,
+              ce_shift = a.ce_shift;
+  const int adversarial = a.adversarial, n_neg = a.n_neg, weight_n = a.weight_n;
+  const float* pos = a.pos;
+  const float* weight = a.weight;
+  float* neg = a.neg;
+  float* row_loss = a.row_loss;
+  float* d_pos = a.d_pos;
+  void* g_hi = a.g_hi;
+  void* g_lo = a.g_lo;
+  const int64_t ld = a.ld, ld_g = a.ld_g;
   float* nrow = neg + (int64_t)r * ld;
   const int64_t grow = (int64_t)r * ld_g;
   const float w = weight_n == 1 ? weight[0] : weight[r];
@@ -127,19 +164,7 @@ __global__ void __launch_bounds__(L_THREADS) loss_kernel(float margin, int adver
                        (OUT != GRAD_TF32 || (reinterpret_cast<uintptr_t>(g_lo) & 15) == 0);
   (void)kGradBytes;
 
-  // ---- the row, in registers: slot (i, j) <-> column (i * L_THREADS + tid) * 4 + j
-  float v[L_CACHE];
-#pragma unroll
-  for (int i = 0; i < L_CACHE / 4; ++i) {
-    const int c = (i * L_THREADS + threadIdx.x) * 4;
-    if (vec_in && c + 4 <= n_neg) {
-      const float4 t = *reinterpret_cast<const float4*>(nrow + c);
-      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[4 * i + j] = c + j < n_neg ? nrow[c + j] : 0.f;
-    }
-  }
+  (void)vec_in;
   constexpr int kCached = L_CACHE * L_THREADS;  // columns beyond this are re-read
 
   if (KIND == BESS_LOSS_SOFTMAX_CE) {
@@ -259,6 +284,25 @@ __global__ void __launch_bounds__(L_THREADS) loss_kernel(float margin, int adver
       row_loss[r] = loss_scale * w * part;
       d_pos[r] = dp;
     }
+  }
+}
+
+// Persistent CTAs over rows; the next row's loads are issued before the
+// current row is processed so every CTA always has one row in flight.
+template <int KIND, int OUT, int TPB>
+__global__ void __launch_bounds__(TPB) loss_kernel(const LossArgs a) {
+  __shared__ float red[TPB / 32 + 1];
+  const bool vec_in = (a.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.neg) & 15) == 0;
+  int r = blockIdx.x;
+  if (r >= a.n) return;
+  float v[L_CACHE], nxt[L_CACHE];
+  loss_load_row<TPB>(a.neg + (int64_t)r * a.ld, a.n_neg, vec_in, nxt);
+  for (; r < a.n; r += gridDim.x) {
+#pragma unroll
+    for (int i = 0; i < L_CACHE; ++i) v[i] = nxt[i];
+    const int rn = r + gridDim.x;
+    if (rn < a.n) loss_load_row<TPB>(a.neg + (int64_t)rn * a.ld, a.n_neg, vec_in, nxt);
+    loss_row<KIND, OUT, TPB>(a, r, v, red);
   }
 }
 
@@ -453,29 +497,39 @@ extern "C" int bess_mask_diag(float* score, int n_row, int64_t ld, int step, int
   return BESS_OK;
 }
 
+template <int KIND, int OUT, int TPB>
+static void launch_loss_tpb(const LossArgs& a, cudaStream_t st) {
+  // enough CTAs to keep ~48 KB of row loads in flight per SM, but persistent
+  const int per_sm = TPB == 64 ? 16 : (TPB == 128 ? 8 : 4);
+  const int grid = a.n < kNumSM * per_sm ? a.n : kNumSM * per_sm;
+  loss_kernel<KIND, OUT, TPB><<<grid, TPB, 0, st>>>(a);
+}
+
+template <int KIND, int OUT>
+static void launch_loss_kind(const LossArgs& a, cudaStream_t st) {
+  if (a.n_neg <= 64 * L_CACHE) launch_loss_tpb<KIND, OUT, 64>(a, st);
+  else if (a.n_neg <= 128 * L_CACHE) launch_loss_tpb<KIND, OUT, 128>(a, st);
+  else launch_loss_tpb<KIND, OUT, 256>(a, st);
+}
+
 template <int OUT>
 static int launch_loss(int kind, float margin, int adversarial, float adv_scale, float loss_scale,
                        int64_t n_entity, const float* pos, float* neg, int n, int n_neg, int64_t ld,
                        const float* weight, int weight_n, float* row_loss, float* d_pos, void* g_hi,
                        void* g_lo, int64_t ld_g, cudaStream_t st) {
+  LossArgs a;
+  a.margin = margin; a.adversarial = adversarial; a.adv_scale = adv_scale; a.loss_scale = loss_scale;
+  a.ce_shift = 0.f; a.pos = pos; a.neg = neg; a.n = n; a.n_neg = n_neg; a.ld = ld; a.weight = weight;
+  a.weight_n = weight_n; a.row_loss = row_loss; a.d_pos = d_pos; a.g_hi = g_hi; a.g_lo = g_lo;
+  a.ld_g = ld_g;
   switch (kind) {
-    case BESS_LOSS_LOGSIGMOID:
-      loss_kernel<BESS_LOSS_LOGSIGMOID, OUT><<<n, L_THREADS, 0, st>>>(
-          margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n,
-          row_loss, d_pos, g_hi, g_lo, ld_g);
+    case BESS_LOSS_LOGSIGMOID: launch_loss_kind<BESS_LOSS_LOGSIGMOID, OUT>(a, st); break;
+    case BESS_LOSS_MARGIN_RANKING: launch_loss_kind<BESS_LOSS_MARGIN_RANKING, OUT>(a, st); break;
+    case BESS_LOSS_SOFTMAX_CE:
+      a.adversarial = 0;
+      a.ce_shift = (float)(log((double)(n_entity - 1)) - log((double)n_neg));
+      launch_loss_kind<BESS_LOSS_SOFTMAX_CE, OUT>(a, st);
       break;
-    case BESS_LOSS_MARGIN_RANKING:
-      loss_kernel<BESS_LOSS_MARGIN_RANKING, OUT><<<n, L_THREADS, 0, st>>>(
-          margin, adversarial, adv_scale, loss_scale, 0.f, pos, neg, n, n_neg, ld, weight, weight_n,
-          row_loss, d_pos, g_hi, g_lo, ld_g);
-      break;
-    case BESS_LOSS_SOFTMAX_CE: {
-      const float shift = (float)(log((double)(n_entity - 1)) - log((double)n_neg));
-      loss_kernel<BESS_LOSS_SOFTMAX_CE, OUT><<<n, L_THREADS, 0, st>>>(
-          0.f, 0, 0.f, loss_scale, shift, pos, neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos,
-          g_hi, g_lo, ld_g);
-      break;
-    }
     default:
       bess_set_error("unknown loss kind %d", kind);
       return BESS_ERR_INVALID_ARG;
