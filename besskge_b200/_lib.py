@@ -98,6 +98,10 @@ SIGNATURES = {
     "bess_relation_grad_reduce": [_P, _I, _P, _P, _I, _I, _P, _P],
     "bess_topk_merge": [_P, _L, _I, _I, _P, _L, _I, _P, _P, _I, _P],
     "bess_topk_finalize": [_P, _P, _I, _I, _I, _P, _P, _I, _I, _F, _P, _P, _P],
+    "bess_peer_signal": [_P, C.POINTER(_P), _I, _I, _P],
+    "bess_peer_wait": [_P, _P, _I, _P],
+    "bess_peer_push": [_P, _L, C.POINTER(_P), _I, _L, _P],
+    "bess_peer_reduce": [_P, _I, _L, _F, _P, _P],
     "bess_fill_f32": [_P, _L, _F, _P],
     "bess_fill_i32": [_P, _L, C.c_int32, _P],
     "bess_cast_from_f32": [_P, _P, _I, _L, _P],

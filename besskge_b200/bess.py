@@ -87,6 +87,78 @@ class _Placement:
         torch.distributed.all_to_all_single(recv.view(-1), send.view(-1))
 
 
+# Distributed mode exchanges blocks with this process's own kernels over peer
+# (symmetric) memory; the NCCL path is kept selectable for A/B tests.
+USE_PEER_EXCHANGE = True
+
+_ALIGN = 256
+
+
+def _up(x: int, a: int = _ALIGN) -> int:
+    return (x + a - 1) // a * a
+
+
+class _PeerExchange:
+    """This rank's symmetric-memory receive buffers and flag rows.
+
+    Layout (identical on every rank, so peer j's address of a region is
+    `ptrs[j] + offset`): 3 flag rows (forward rows / gradient rows / relation
+    partials) | TN receive buffer [n, per, W] (table dtype) | gradient receive
+    buffer [n, per, W] fp32 | relation partial slots [n, count] fp32.
+    Allocation and (re)sizing are collective: every rank calls `ensure` with
+    the same sizes at the same point of the step."""
+
+    FLAG_BYTES = 3 * 64 * 4
+
+    def __init__(self, device: torch.device, n: int, rank: int) -> None:
+        self.device, self.n, self.rank = device, n, rank
+        self.sizes = (0, 0, 0)
+        self.buf: Optional[torch.Tensor] = None
+        self._keep: List[Any] = []
+        self.counters = torch.zeros(3, dtype=torch.int32, device=device)
+
+    def ensure(self, tn_bytes: int, grad_bytes: int, rel_bytes: int) -> None:
+        want = (_up(tn_bytes), _up(grad_bytes), _up(rel_bytes))
+        if self.buf is not None and all(w <= h for w, h in zip(want, self.sizes)):
+            return
+        import torch.distributed._symmetric_memory as symm
+
+        sizes = tuple(max(w, h) for w, h in zip(want, self.sizes))
+        total = _up(self.FLAG_BYTES) + sum(sizes)
+        torch.cuda.synchronize(self.device)
+        torch.distributed.barrier()
+        group = torch.distributed.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # newer torch enables it implicitly
+            pass
+        buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+        hdl = symm.rendezvous(buf, group)
+        buf.zero_()
+        self.counters.zero_()
+        torch.cuda.synchronize(self.device)
+        torch.distributed.barrier()  # nobody signals before every flag row is zero
+        self._keep.append((self.buf, getattr(self, "hdl", None)))  # peers may still map it
+        self.buf, self.hdl, self.sizes = buf, hdl, sizes
+        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.off_tn = _up(self.FLAG_BYTES)
+        self.off_grad = self.off_tn + sizes[0]
+        self.off_rel = self.off_grad + sizes[1]
+
+    def view(self, offset: int, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        return self.buf[offset:offset + nbytes].view(dtype).view(*shape)
+
+    def flags(self, channel: int) -> torch.Tensor:
+        return self.view(channel * 64 * 4, (self.n,), torch.int32)
+
+    def handshake(self, channel: int) -> None:
+        """signal every rank, then wait for every rank, on one channel."""
+        K.peer_signal(self.counters[channel:channel + 1],
+                      [p + channel * 64 * 4 for p in self.ptrs], self.rank)
+        K.peer_wait(self.counters[channel:channel + 1], self.flags(channel), self.n)
+
+
 class _Staged:
     """Device-resident inputs of one call (see EmbeddingMovingBessKGE.stage)."""
 
@@ -200,6 +272,7 @@ class BessKGE(torch.nn.Module, ABC):
         self.entity_embedding_size: int = self.score_fn.entity_embedding.shape[-1]
         self._ws: Optional[K.Workspace] = None
         self._placement: Optional[_Placement] = None
+        self._px: Optional[_PeerExchange] = None
         self._opt_state: Dict[str, Any] = {}
 
     # ------------------------------------------------------------------ misc
@@ -471,8 +544,17 @@ class EmbeddingMovingBessKGE(BessKGE):
         G = gidx.shape[1]
         # ---- persistent buffers
         H = ws.get("H", (R, n_loc_rows, W), tdt)
-        TN = ws.get("TN", (R, n, per, W), tdt)
-        SEND = ws.get("SEND", (n, per, W), tdt) if pl.distributed else None
+        px: Optional[_PeerExchange] = None
+        if pl.distributed and USE_PEER_EXCHANGE:
+            if self._px is None:
+                self._px = _PeerExchange(dev, n, pl.rank)
+            px = self._px
+            rel_cnt = _up(rel_table.numel() * 4, 16) // 4
+            px.ensure(n * per * W * ent.element_size(), n * per * W * 4, n * rel_cnt * 4)
+            TN = px.view(px.off_tn, (1, n, per, W), tdt)
+        else:
+            TN = ws.get("TN", (R, n, per, W), tdt)
+        SEND = ws.get("SEND", (n, per, W), tdt) if pl.distributed and px is None else None
         pos_ws = ws.get("pos", (R, S), torch.float32)
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         qv = ws.get("qv", (S, nvec, W), torch.float32)
@@ -501,7 +583,11 @@ class EmbeddingMovingBessKGE(BessKGE):
         if train:
             dH = ws.get("dH", (R, n_loc_rows, W), torch.float32)
             dTN = ws.get("dTN", (R, n, per, W), torch.float32)
-            dBACK = ws.get("dBACK", (n, per, W), torch.float32) if pl.distributed else None
+            dBACK = None
+            if px is not None:
+                dBACK = px.view(px.off_grad, (n, per, W), torch.float32)
+            elif pl.distributed:
+                dBACK = ws.get("dBACK", (n, per, W), torch.float32)
             dRq = ws.get("dRq", (R, S, Wr), torch.float32)
             d_qv = ws.get("d_qv", (S, nvec, W), torch.float32)
             max_cand = max(ps.n_cand for ps in passes if ps.shared) if any(
@@ -516,7 +602,8 @@ class EmbeddingMovingBessKGE(BessKGE):
             sort_ws = ws.get("sort_ws", (K.sort_workspace(max(G, R * S)) // 4 + 64,), torch.int32)
             rk = ws.get("rel_keys", (R * S,), torch.int32)
             rp = ws.get("rel_perm", (R * S,), torch.int32)
-            d_rel_table = ws.get("d_rel_table", tuple(rel_table.shape), torch.float32)
+            d_rel_table = ws.get("d_rel_table", (_up(rel_table.numel() * 4, 16) // 4,),
+                                 torch.float32)[:rel_table.numel()].view(rel_table.shape)
             key_bits = max(1, int(ent.shape[1] - 1).bit_length())
             rel_bits = max(1, int(rel_table.shape[0] - 1).bit_length())
         scale_buf = ws.get("cand_scale", (max(ps.n_cand for ps in passes),), torch.float32) \
@@ -555,14 +642,19 @@ class EmbeddingMovingBessKGE(BessKGE):
             # ================= gather (+ exchange) =================
             for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                 table = ent[shard]
-                if pl.distributed:
+                if px is not None:  # rows go straight into every peer's receive buffer
+                    dst = [p + px.off_tn for p in px.ptrs]
+                    slot = pl.rank
+                elif pl.distributed:
                     dst = [SEND[j].data_ptr() for j in range(n)]
                     slot = 0
                 else:
                     dst = [TN[j].data_ptr() for j in range(n)]
                     slot = li
                 K.gather_route(table, gidx[row], n_loc_rows, per, H[li], dst, slot)
-            if pl.distributed:
+            if px is not None:
+                px.handshake(0)
+            elif pl.distributed:
                 pl.all_to_all(TN[0], SEND)
 
             for li, row in enumerate(step_rows):
@@ -700,8 +792,14 @@ class EmbeddingMovingBessKGE(BessKGE):
                         K.boxe_rel_finalize(cfg, dt, rel_table, rel[row], S, dRq[li])
 
             # ================= reverse exchange + update =================
+            if px is not None and not train:
+                px.handshake(1)  # every rank is done reading its receive buffer
             if train:
-                if pl.distributed:
+                if px is not None:
+                    blk = per * W * 4
+                    K.peer_push(dTN[0], blk, [p + px.off_grad + pl.rank * blk for p in px.ptrs], blk)
+                    px.handshake(1)
+                elif pl.distributed:
                     pl.all_to_all(dBACK, dTN[0])
                 self._opt_state.setdefault("step", 0)
                 self._opt_state["step"] += 1
@@ -722,10 +820,22 @@ class EmbeddingMovingBessKGE(BessKGE):
                 K.sort_keys(rows_this_step.view(-1), R * S, rel_bits, rk, rp, sort_ws)
                 K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
                                        rel_table.shape[0], d_rel_table)
-                if pl.distributed:
-                    torch.distributed.all_reduce(d_rel_table)
-                if getattr(optimizer, "relation_grad_reduction", "mean") == "mean" and n > 1:
-                    d_rel_table.mul_(1.0 / n)
+                mean = getattr(optimizer, "relation_grad_reduction", "mean") == "mean"
+                if px is not None:
+                    # all-reduce of the replicated relation gradient: every rank pushes its
+                    # partial into slot [rank] of every rank, then sums the n slots in rank
+                    # order (bit-identical tables on all ranks)
+                    cnt = _up(rel_table.numel() * 4, 16) // 4
+                    K.peer_push(d_rel_table, 0, [p + px.off_rel + pl.rank * cnt * 4 for p in px.ptrs],
+                                cnt * 4)
+                    px.handshake(2)
+                    K.peer_reduce(px.view(px.off_rel, (n, cnt), torch.float32), n, cnt,
+                                  1.0 / n if mean else 1.0, d_rel_table)
+                else:
+                    if pl.distributed:
+                        torch.distributed.all_reduce(d_rel_table)
+                    if mean and n > 1:
+                        d_rel_table.mul_(1.0 / n)
                 self._update_relation(optimizer, rel_table, d_rel_table, step_no, ws)
 
         out: Dict[str, Any] = {}
@@ -994,9 +1104,14 @@ class TrainingModel:
         self.cuda_graph = graph_ok if cuda_graph is None else (bool(cuda_graph) and graph_ok)
         self._graphs: Dict[Any, Any] = {}
 
+    def _use_graph(self) -> bool:
+        # NCCL collectives inside a captured step hung on 2 x B200 (NCCL 2.28.9, torch 2.11);
+        # with the peer-memory exchange the step contains only this library's kernels
+        return self.cuda_graph and (not self.model._setup()[1].distributed or USE_PEER_EXCHANGE)
+
     def __call__(self, head, relation, tail, negative, triple_mask=None, triple_weight=None,
                  negative_mask=None) -> Dict[str, Any]:
-        if not self.cuda_graph:
+        if not self._use_graph():
             return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
                                    negative_mask, optimizer=self.optimizer)
         staged = self.model.stage(head, relation, tail, negative, triple_mask, triple_weight,
@@ -1009,7 +1124,7 @@ class TrainingModel:
 
     def run_staged(self, staged: _Staged) -> Dict[str, Any]:
         """Training step(s) on inputs that are already resident in HBM."""
-        if not self.cuda_graph:
+        if not self._use_graph():
             return self.model._run(None, None, None, None, None, None, None,
                                    optimizer=self.optimizer, staged=staged)
         return self._run_graphed(self.model._restage(staged))

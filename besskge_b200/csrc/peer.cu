@@ -1,0 +1,145 @@
+// Peer-memory exchange primitives for one-process-per-GPU BESS (one entity
+// shard per GPU over NVLink 5 / NVSwitch).
+//
+// The reference exchanges the n x n triple blocks with a balanced AllToAll
+// (bess.py:348-350; autograd gives the reverse AllToAll of the gradients, and
+// PopTorch all-reduces the replicated relation gradient).  Here the gather
+// kernel (rows.cu: bess_gather_route) already stores every tail / negative row
+// straight into the destination GPU's receive buffer through a peer-mapped
+// pointer, so the forward "collective" is just that kernel plus a flag
+// handshake; the gradient blocks and the relation partials are pushed with
+// vectorised remote stores.  No NCCL call is left inside the step, which makes
+// the whole step capturable in a CUDA graph.
+//
+// Handshake: every rank owns, per channel, a row of n int32 flags (symmetric
+// memory) and a local int32 sequence counter.  signal: seq = ++counter, then
+// flag[my_rank] on every peer := seq with release semantics at system scope.
+// wait: spin (acquire, system scope) until all n local flags >= counter.
+// Waits are bounded: a missing peer traps the launch instead of hanging the GPU.
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace bess {
+
+struct PeerPtrs {
+  void* p[BESS_MAX_SHARD];
+};
+
+BESS_D void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+BESS_D int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void peer_signal_kernel(int32_t* counter, PeerPtrs peer_flags, int my_rank, int n) {
+  __shared__ int32_t seq;
+  if (threadIdx.x == 0) {
+    seq = *counter + 1;
+    *counter = seq;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    __threadfence_system();  // everything this GPU stored before (previous kernels) is visible first
+    st_release_sys(reinterpret_cast<int32_t*>(peer_flags.p[threadIdx.x]) + my_rank, seq);
+  }
+}
+
+__global__ void peer_wait_kernel(const int32_t* counter, const int32_t* my_flags, int n) {
+  const int32_t expected = *counter;
+  if ((int)threadIdx.x < n) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(my_flags + threadIdx.x) < expected) {
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s
+        printf("besskge_b200 peer_wait: rank flag %d stuck at %d, expected %d\n", (int)threadIdx.x,
+               ld_acquire_sys(my_flags + threadIdx.x), expected);
+        __trap();
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+// block (j, *) copies src + j * src_stride_bytes -> dst[j], bytes_each bytes (16-byte multiples)
+__global__ void __launch_bounds__(256) peer_push_kernel(const uint8_t* __restrict__ src,
+                                                        int64_t src_stride_bytes, PeerPtrs dst,
+                                                        int64_t bytes_each) {
+  const int j = blockIdx.y;
+  const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)j * src_stride_bytes);
+  uint4* d = reinterpret_cast<uint4*>(dst.p[j]);
+  const int64_t n16 = bytes_each >> 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (int64_t)gridDim.x * blockDim.x)
+    st_stream(d + i, ld_stream(s + i));
+}
+
+// out[i] = scale * sum_j slots[j * count + i], j ascending (same order on every rank)
+__global__ void peer_reduce_kernel(const float* __restrict__ slots, int n, int64_t count, float scale,
+                                   float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc += slots[(int64_t)j * count + i];
+    out[i] = acc * scale;
+  }
+}
+
+}  // namespace bess
+
+using namespace bess;
+
+static int fill_ptrs(PeerPtrs& pp, void* const* ptrs, int n, const char* what) {
+  if (n < 1 || n > BESS_MAX_SHARD) {
+    bess_set_error("%s: n=%d out of range (1..%d)", what, n, BESS_MAX_SHARD);
+    return BESS_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < BESS_MAX_SHARD; ++i) pp.p[i] = i < n ? ptrs[i] : nullptr;
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_signal(int32_t* counter, void* const* peer_flags, int my_rank, int n,
+                                void* stream) {
+  PeerPtrs pp;
+  if (int e = fill_ptrs(pp, peer_flags, n, "bess_peer_signal")) return e;
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, pp, my_rank, n);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n, void* stream) {
+  BESS_CHECK_ARG(n >= 1 && n <= 32, "bess_peer_wait: n=%d out of range", n);
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, my_flags, n);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_push(const void* src, int64_t src_stride_bytes, void* const* dst, int n,
+                              int64_t bytes_each, void* stream) {
+  if (bytes_each <= 0) return BESS_OK;
+  PeerPtrs pp;
+  if (int e = fill_ptrs(pp, dst, n, "bess_peer_push")) return e;
+  BESS_CHECK_ARG(bytes_each % 16 == 0 && src_stride_bytes % 16 == 0 && ((uintptr_t)src & 15) == 0,
+                 "bess_peer_push: 16-byte alignment required");
+  const int64_t n16 = bytes_each >> 4;
+  int bx = (int)((n16 + 255) / 256);
+  const int cap = (8 * kNumSM + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  peer_push_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, src_stride_bytes,
+                                                                 pp, bytes_each);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_reduce(const float* slots, int n, int64_t count, float scale, float* out,
+                                void* stream) {
+  if (count <= 0) return BESS_OK;
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > 4 * kNumSM) blocks = 4 * kNumSM;
+  peer_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(slots, n, count, scale, out);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}

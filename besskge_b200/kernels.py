@@ -284,6 +284,30 @@ def topk_finalize(score: torch.Tensor, idx: torch.Tensor, n_shard: int, n_query:
          out_score.data_ptr(), out_id.data_ptr(), _st(score))
 
 
+# ------------------------------------------------------ peer exchange -------
+def _ptr_array(ptrs: Sequence[int]):
+    return (C.c_void_p * max(len(ptrs), 1))(*[C.c_void_p(p) for p in ptrs])
+
+
+def peer_signal(counter: torch.Tensor, peer_flag_ptrs: Sequence[int], my_rank: int) -> None:
+    call("bess_peer_signal", counter.data_ptr(), _ptr_array(peer_flag_ptrs), my_rank,
+         len(peer_flag_ptrs), _st(counter))
+
+
+def peer_wait(counter: torch.Tensor, my_flags: torch.Tensor, n: int) -> None:
+    call("bess_peer_wait", counter.data_ptr(), my_flags.data_ptr(), n, _st(counter))
+
+
+def peer_push(src: torch.Tensor, src_stride_bytes: int, dst_ptrs: Sequence[int],
+              bytes_each: int) -> None:
+    call("bess_peer_push", src.data_ptr(), src_stride_bytes, _ptr_array(dst_ptrs), len(dst_ptrs),
+         bytes_each, _st(src))
+
+
+def peer_reduce(slots: torch.Tensor, n: int, count: int, scale: float, out: torch.Tensor) -> None:
+    call("bess_peer_reduce", slots.data_ptr(), n, count, float(scale), out.data_ptr(), _st(out))
+
+
 def fill_f32(t: torch.Tensor, v: float) -> None:
     call("bess_fill_f32", t.data_ptr(), t.numel(), float(v), _st(t))
 

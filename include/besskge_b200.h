@@ -313,6 +313,25 @@ int bess_topk_finalize(const float* score, const int32_t* idx, int n_shard, int 
                        int max_entity_per_shard, int k, float bad_score, float* out_score,
                        int32_t* out_id, void* stream);
 
+/* ------------------------------------------- peer-memory exchange ---------
+ * One process per GPU, one entity shard per GPU: the balanced AllToAll of
+ * bess.py:348-350 (and its autograd transpose, and the all-reduce of the
+ * replicated relation gradient) without a collective library inside the step.
+ * bess_gather_route already stores rows through peer-mapped pointers; these
+ * four calls add the flag handshake and the pushes.  `peer_flags[j]` points at
+ * rank j's flag row (n int32, symmetric memory) of one channel, `counter` is a
+ * local int32 sequence counter of the same channel.
+ *   signal: seq = ++*counter; flag row of every rank [my_rank] := seq (release.sys)
+ *   wait  : until all n local flags >= *counter (acquire.sys; traps after ~10 s)
+ *   push  : dst[j] <- src + j * src_stride_bytes, bytes_each bytes, for j < n
+ *   reduce: out[i] = scale * sum_j slots[j * count + i], j ascending */
+int bess_peer_signal(int32_t* counter, void* const* peer_flags /* host array [n] */, int my_rank,
+                     int n, void* stream);
+int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n, void* stream);
+int bess_peer_push(const void* src, int64_t src_stride_bytes, void* const* dst /* host array [n] */,
+                   int n, int64_t bytes_each, void* stream);
+int bess_peer_reduce(const float* slots, int n, int64_t count, float scale, float* out, void* stream);
+
 /* utility */
 int bess_fill_f32(float* p, int64_t n, float v, void* stream);
 int bess_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);
