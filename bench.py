@@ -285,18 +285,40 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "shard_bs": sbs, "negatives_per_triple": prob["negatives"],
-                   "n_shard": 1},
+        "config": {"workload": args.workload, "dataset_shape": prob["shape"],
+                   "n_entity": prob["ds"].n_entity, "n_shard": 1, "shard_bs": sbs,
+                   "negatives_per_triple": prob["negatives"], "loss": "LogSigmoid(12, adversarial)",
+                   "optimizer": "SGD(1e-3)", "score_fn": prob["fam"], "embedding_size": prob["d"],
+                   "sample": f"bounded sample of the workload: micro-batches of {sbs} triples "
+                             f"(the B200 arm uses {prob['shard_bs']}) on the host cores"},
         "cpu_baseline": {"value": value, "unit": "triples/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps of shard_bs={sbs} (oracle port of the reference's "
                                    "plain-PyTorch n_shard=1 path: forward + autograd + dense SGD)"},
         "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else any library prints to
+    fd 1 during the run (e.g. NCCL's version banner) was redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main() -> None:
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -334,10 +356,15 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # -------- kernel-only leg: inputs resident in HBM ------------------------
+    from besskge_b200 import _lib as L_
     staged = [step.stage(**b) for b in host_batches]
     torch.cuda.synchronize()
+    launches_per_step = 0
     for i in range(args.warmup):
+        c0 = L_.call("bess_launch_count")
         step.run_staged(staged[i])
+        if i == 0:  # the first call runs eagerly: every kernel launch of one step is counted
+            launches_per_step = L_.call("bess_launch_count") - c0
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -406,26 +433,13 @@ def main() -> None:
             "gather": gather,
             "cpu_baseline": cpu,
         }
-        line["gpu_launches"] = estimate_launches(model, n_shard) * args.steps
-        print(json.dumps(line))
+        # kernels of this library per step (counted by the library on the eager first step;
+        # later steps replay the same launches from the captured CUDA graph) x timed steps
+        line["gpu_launches"] = int(launches_per_step) * args.steps
+        line["gpu_launches_per_step"] = int(launches_per_step)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
-
-
-def estimate_launches(model, n_shard: int) -> int:
-    """Kernels of OUR library launched per step and per local replica (counted from
-    the launch sequence in bess.py for this configuration: shared 't' negatives)."""
-    per_replica = (1      # gather_route
-                   + 1    # score_triple fwd
-                   + 2    # prologue + shared fwd
-                   + 2    # loss + sum
-                   + 1    # score_triple bwd
-                   + 5    # prologue, bwd_query, bwd_cand, reduce, prologue bwd
-                   )
-    key_bits = max(1, int(model.score_fn.entity_embedding.shape[1] - 1).bit_length())
-    sort = 3 * ((key_bits + 7) // 8)
-    rel_sort = 3
-    return per_replica + sort + 1 + rel_sort + 2  # + scatter_sgd, relation reduce + update
 
 
 if __name__ == "__main__":

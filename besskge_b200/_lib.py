@@ -58,6 +58,7 @@ _CFG = C.POINTER(ScoreCfg)
 # name -> argtypes; every function returns int (0 = ok) unless listed in _RESTYPE
 SIGNATURES = {
     "bess_version": [],
+    "bess_launch_count": [],
     "bess_entity_width": [_CFG],
     "bess_relation_width": [_CFG],
     "bess_query_nvec": [_CFG],
@@ -111,8 +112,9 @@ _RESTYPE = {
     "bess_shared_bwd_cand_workspace": C.c_int64,
     "bess_sort_workspace": C.c_int64,
     "bess_dot_gemm_workspace": C.c_int64,
+    "bess_launch_count": C.c_int64,
 }
-_NO_STATUS = {"bess_version", "bess_entity_width", "bess_relation_width", "bess_query_nvec",
+_NO_STATUS = {"bess_version", "bess_launch_count", "bess_entity_width", "bess_relation_width", "bess_query_nvec",
               "bess_shared_bwd_cand_workspace", "bess_sort_workspace", "bess_dot_gemm_workspace"}
 
 _lib: Optional[C.CDLL] = None

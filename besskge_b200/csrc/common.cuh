@@ -153,8 +153,13 @@ void bess_set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
+// kernels launched by this library since load (host-side count; bess_launch_count())
+extern unsigned long long g_bess_launches;
+#define BESS_LAUNCHED(n) (g_bess_launches += (unsigned long long)(n))
+
 #define BESS_CHECK_LAUNCH()                                             \
   do {                                                                  \
+    BESS_LAUNCHED(1);                                                   \
     cudaError_t _e = cudaPeekAtLastError();                             \
     if (_e != cudaSuccess) {                                            \
       bess_set_error("CUDA launch failed: %s", cudaGetErrorString(_e)); \

@@ -210,7 +210,9 @@ void bess_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+unsigned long long g_bess_launches = 0;
 extern "C" const char* bess_last_error(void) { return g_err; }
+extern "C" int64_t bess_launch_count(void) { return (int64_t)g_bess_launches; }
 extern "C" int bess_version(void) { return 100; }
 extern "C" int bess_entity_width(const bess_score_cfg_t* cfg) { return ent_width(to_cfg(cfg)); }
 extern "C" int bess_relation_width(const bess_score_cfg_t* cfg) { return rel_width(to_cfg(cfg)); }

@@ -297,6 +297,7 @@ extern "C" int bess_sort_keys(const int32_t* keys, int n, int key_bits, int32_t*
     rs_scatter_kernel<<<n_blocks, RS_THREADS, 0, st>>>(kin, vin, n, 8 * p, n_blocks, hist, kout, vout);
     kin = kout; vin = vout;
   }
+  BESS_LAUNCHED(3 * passes - 1);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

@@ -81,6 +81,8 @@ typedef struct {
 
 const char* bess_last_error(void);
 int bess_version(void);
+/* number of kernels this library has launched in this process (host-side count) */
+int64_t bess_launch_count(void);
 /* entity / relation row widths (elements) implied by a config */
 int bess_entity_width(const bess_score_cfg_t* cfg);
 int bess_relation_width(const bess_score_cfg_t* cfg);

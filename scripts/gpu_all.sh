@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for f in tests/test_gpu_gemm.py tests/test_gpu_kernels.py tests/test_gpu_bess.py; do
+for f in tests/test_gpu_gemm.py tests/test_gpu_kernels.py tests/test_gpu_bess.py tests/test_gpu_fullsize.py; do
   timeout 900 python -m pytest $f -q -m gpu --timeout 600 > gpurun_out/$(basename $f .py).log 2>&1
   echo "exit $? for $f"; tail -15 gpurun_out/$(basename $f .py).log
 done
