@@ -23,6 +23,7 @@
 //   warps 2..5  epilogue (TMEM lane quarter = warp_idx % 4)
 #include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -60,9 +61,12 @@ struct ModeTraits {
 };
 
 constexpr int kBarrierBytes = 256;
+// epilogue staging for TMA stores: per epilogue warp two [32 rows x 128 B] swizzled chunks
+constexpr int kEpiChunkBytes = 32 * 128;
+constexpr int kEpiBytes = 4 * 2 * kEpiChunkBytes;
 template <int MODE>
 constexpr int smem_bytes() {
-  return kStages * ModeTraits<MODE>::kStageBytes + kBarrierBytes + 1024 /* alignment slack */;
+  return kStages * ModeTraits<MODE>::kStageBytes + kEpiBytes + kBarrierBytes + 1024 /* alignment slack */;
 }
 
 // ------------------------------------------------------------------ PTX ----
@@ -116,6 +120,39 @@ BESS_D void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int 
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast: the box lands at the same CTA-relative offset in every CTA of `mask`, and each
+// destination's mbarrier (same offset) receives the complete_tx
+BESS_D void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+BESS_D void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+BESS_D void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+BESS_D uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+BESS_D void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+BESS_D void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+BESS_D void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+BESS_D void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 BESS_D void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -213,17 +250,22 @@ struct GemmParams {
   int accumulate;
   float* partial;   // ... or [n_split, M, ld_partial] partial sums
   int64_t ld_partial;
+  int tma_store;    // epilogue stages 32 x 32 chunks in smem and TMA-stores them (map_out)
 };
 
-template <int MODE, bool A_MN>
+// CS = cluster size along M: the CS CTAs of a cluster work on CS consecutive m-blocks of the
+// same (split, n-block); each loads 1/CS of the B tile and multicasts it to the whole cluster,
+// which divides the L2 -> SM traffic of the shared operand by CS.
+template <int MODE, bool A_MN, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
   using T = ModeTraits<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * T::kStageBytes;
+  const uint32_t epi_base = smem_base + kStages * T::kStageBytes;
+  const uint32_t bar_base = epi_base + kEpiBytes;
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -236,19 +278,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (p.M + kBlockM - 1) / kBlockM;
   const int n_blocks = (p.N + kBlockN - 1) / kBlockN;
-  const int tiles_per_split = m_blocks * n_blocks;
+  const int m_super = (m_blocks + CS - 1) / CS;
+  const int tiles_per_split = m_super * n_blocks;      // super-tiles (CS m-blocks each)
   const int n_tiles = tiles_per_split * p.n_split;
+  const int cta_rank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int first_tile = (int)blockIdx.x / CS, tile_step = (int)gridDim.x / CS;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
     tma_prefetch_desc(&map_b_hi);
+    if (p.tma_store) tma_prefetch_desc(&map_out);
     if (MODE == GEMM_TF32X3) {
       tma_prefetch_desc(&map_a_lo);
       tma_prefetch_desc(&map_b_lo);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CS);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -259,6 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -267,9 +315,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < n_tiles; t += tile_step) {
         const int split = t / tiles_per_split, r = t - split * tiles_per_split;
-        const int m0 = (r / n_blocks) * kBlockM, n0 = (r % n_blocks) * kBlockN;
+        const int m0 = ((r / n_blocks) * CS + cta_rank) * kBlockM, n0 = (r % n_blocks) * kBlockN;
         const int k_begin = split * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
         for (int k = k_begin; k < k_end; k += T::kBlockK) {
@@ -289,8 +337,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_2d(sa, &map_a_hi, full_bar(stage), k, m0);
             if (MODE == GEMM_TF32X3) tma_load_2d(sa + T::kATile, &map_a_lo, full_bar(stage), k, m0);
           }
-          tma_load_2d(sb, &map_b_hi, full_bar(stage), k, n0);
-          if (MODE == GEMM_TF32X3) tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
+          if (CS > 1) {
+            constexpr int kSliceRows = kBlockN / CS;
+            const uint32_t off = (uint32_t)(cta_rank * kSliceRows * T::kRowBytes);
+            tma_load_2d_mc(sb + off, &map_b_hi, full_bar(stage), k, n0 + cta_rank * kSliceRows, kMcMask);
+            if (MODE == GEMM_TF32X3)
+              tma_load_2d_mc(sb + T::kBTile + off, &map_b_lo, full_bar(stage), k,
+                             n0 + cta_rank * kSliceRows, kMcMask);
+          } else {
+            tma_load_2d(sb, &map_b_hi, full_bar(stage), k, n0);
+            if (MODE == GEMM_TF32X3) tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -304,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+      for (int t = first_tile; t < n_tiles; t += tile_step, ++local) {
         const int split = t / tiles_per_split;
         const int k_begin = split * p.k_per_split;
         const int k_end = min(p.K, k_begin + p.k_per_split);
@@ -335,7 +392,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             first = 0;
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+          // frees the smem stage (in every CTA of the cluster: peers multicast into it)
+          if (CS > 1) umma_commit_mc(empty_bar(stage), kMcMask);
+          else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(buf));  // accumulator ready for the epilogue
@@ -345,9 +404,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ============================== epilogue ==============================
     const int quarter = warp & 3;  // TMEM lanes [32 * quarter, +32)
     int local = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+    for (int t = first_tile; t < n_tiles; t += tile_step, ++local) {
       const int split = t / tiles_per_split, r = t - split * tiles_per_split;
-      const int m0 = (r / n_blocks) * kBlockM, n0 = (r % n_blocks) * kBlockN;
+      const int m0 = ((r / n_blocks) * CS + cta_rank) * kBlockM, n0 = (r % n_blocks) * kBlockN;
       const int buf = local & 1;
       const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
       mbar_wait(tfull_bar(buf), acc_phase);
@@ -366,6 +425,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kAccCols);
+      if (p.tma_store) {
+        // TMEM -> registers -> swizzled smem chunk -> one coalesced TMA store per 32 x 32 chunk
+        const uint32_t my_epi = epi_base + (uint32_t)(warp - 2) * 2 * kEpiChunkBytes;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN; c += 32) {
+          if (n0 + c >= p.N) break;  // chunk entirely out of range (warp-uniform)
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+          const uint32_t chunk = my_epi + (uint32_t)((c >> 5) & 1) * kEpiChunkBytes;
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this chunk has read it
+          __syncwarp();
+          const uint32_t row_addr = chunk + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = row_addr + (uint32_t)((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_out, chunk, n0 + c, m0 + quarter * 32);
+            tma_store_commit();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < kBlockN; c += 32) {
         uint32_t v[32];
@@ -388,13 +475,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -566,7 +656,7 @@ static int choose_split(int M, int N, int K, int block_k, int* k_per_split) {
   return split;
 }
 
-template <int MODE, bool A_MN>
+template <int MODE, bool A_MN, int CS>
 static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
                        int64_t ldb, int M, int N, int K, float* out, bess_rowmap_t out_map, int64_t ld_out,
                        int col0, int accumulate, float* workspace, int64_t workspace_bytes,
@@ -575,11 +665,11 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int e = A_MN ? make_map_mn<MODE>(&ma_hi, a_hi, M, K, lda) : make_map<MODE>(&ma_hi, a_hi, M, K, lda, kBlockM))
     return e;
-  if (int e = make_map<MODE>(&mb_hi, b_hi, N, K, ldb, kBlockN)) return e;
+  if (int e = make_map<MODE>(&mb_hi, b_hi, N, K, ldb, kBlockN / CS)) return e;
   if (MODE == GEMM_TF32X3) {
     if (int e = A_MN ? make_map_mn<MODE>(&ma_lo, a_lo, M, K, lda) : make_map<MODE>(&ma_lo, a_lo, M, K, lda, kBlockM))
       return e;
-    if (int e = make_map<MODE>(&mb_lo, b_lo, N, K, ldb, kBlockN)) return e;
+    if (int e = make_map<MODE>(&mb_lo, b_lo, N, K, ldb, kBlockN / CS)) return e;
   } else {
     ma_lo = ma_hi;
     mb_lo = mb_hi;
@@ -595,19 +685,53 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   }
   p.out = out; p.out_map = out_map; p.ld_out = ld_out; p.col0 = col0; p.accumulate = accumulate;
   p.partial = workspace;
+  // coalesced TMA-store epilogue when the output is a plain (row-identity) 16-byte aligned matrix
+  CUtensorMap m_out = ma_hi;
+  p.tma_store = 0;
+  // (bulk tensor stores clip the inner dimension at 16-byte granularity: N must be a multiple of 4)
+  if (p.n_split == 1 && !accumulate && out_map.group <= 0 && out_map.offset == 0 && ld_out % 4 == 0 &&
+      col0 % 4 == 0 && N % 4 == 0 && ((uintptr_t)out & 15) == 0) {
+    EncodeTiledFn fn = encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_out * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&m_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out + col0, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) p.tma_store = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes<MODE>());
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN, CS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE>());
     if (e != cudaSuccess) {
       bess_set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
       return BESS_ERR_CUDA;
     }
     attr_set = true;
   }
-  const int n_tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN) * p.n_split;
-  const int grid = min(n_tiles, kNumSM);
-  gemm_tc_kernel<MODE, A_MN><<<grid, kThreads, smem_bytes<MODE>(), stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  const int n_super = ceil_div(ceil_div(M, kBlockM), CS) * ceil_div(N, kBlockN) * p.n_split;
+  // resident clusters: 148 SMs pair up completely; clusters of 4 only fit 132 SMs (GPC sizes)
+  const int max_clusters = CS == 1 ? kNumSM : (CS == 2 ? kNumSM / 2 : 33);
+  const int grid = min(n_super, max_clusters) * CS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes<MODE>();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, A_MN, CS>, ma_hi, ma_lo, mb_hi, mb_lo, m_out, p);
+  if (le != cudaSuccess) {
+    bess_set_error("gemm_tc_kernel launch failed: %s", cudaGetErrorString(le));
+    return BESS_ERR_CUDA;
+  }
   BESS_CHECK_LAUNCH();
   if (p.n_split > 1) {
     const int64_t total = (int64_t)M * N;
@@ -648,13 +772,19 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
   BESS_CHECK_ARG(((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) % 16 == 0,
                  "bess_dot_gemm: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-#define GEMM_GO(MODE)                                                                                   \
-  return a_mn_major ? launch_gemm<MODE, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, \
-                                              ld_out, col0, accumulate, (float*)workspace,             \
-                                              workspace_bytes, st)                                     \
-                    : launch_gemm<MODE, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, \
-                                               ld_out, col0, accumulate, (float*)workspace,            \
-                                               workspace_bytes, st)
+  // cluster size along M (B-tile multicast); BESSKGE_GEMM_CLUSTER overrides for experiments
+  const int m_blocks_ = ceil_div(M, kBlockM);
+  int cs = m_blocks_ >= 4 ? 2 : 1;
+  if (const char* env = getenv("BESSKGE_GEMM_CLUSTER")) {
+    const int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4) cs = v;
+  }
+#define GEMM_ARGS a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0, accumulate, \
+                  (float*)workspace, workspace_bytes, st
+#define GEMM_GO(MODE)                                                                    \
+  if (cs == 4) return a_mn_major ? launch_gemm<MODE, true, 4>(GEMM_ARGS) : launch_gemm<MODE, false, 4>(GEMM_ARGS); \
+  if (cs == 2) return a_mn_major ? launch_gemm<MODE, true, 2>(GEMM_ARGS) : launch_gemm<MODE, false, 2>(GEMM_ARGS); \
+  return a_mn_major ? launch_gemm<MODE, true, 1>(GEMM_ARGS) : launch_gemm<MODE, false, 1>(GEMM_ARGS)
   switch (dtype) {
     case BESS_F32: GEMM_GO(GEMM_TF32X3);
     case BESS_F16: GEMM_GO(GEMM_F16);
@@ -664,6 +794,7 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
       return BESS_ERR_INVALID_ARG;
   }
 #undef GEMM_GO
+#undef GEMM_ARGS
 }
 
 extern "C" int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,

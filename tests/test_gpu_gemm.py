@@ -95,9 +95,10 @@ SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("aligned", [False, True])  # True: TMA-store epilogue; False: direct stores
 @pytest.mark.parametrize("name", ["f32", "bf16", "f16"])
 @pytest.mark.parametrize("M,N,Kd", SHAPES)
-def test_dot_gemm_matches_fp64(name, M, N, Kd):
+def test_dot_gemm_matches_fp64(name, M, N, Kd, aligned):
     L, K = _imports()
     dtype = DTYPES[name]
     g = torch.Generator().manual_seed(M * 7 + N * 3 + Kd)
@@ -105,21 +106,22 @@ def test_dot_gemm_matches_fp64(name, M, N, Kd):
     b = torch.randn(N, Kd, generator=g).cuda()
     a_hi, a_lo, lda, *_ = _operands(K, L, a, dtype)
     b_hi, b_lo, ldb, *_ = _operands(K, L, b, dtype)
-    ld_out = N + 5
+    c0 = 4 if aligned else 1
+    ld_out = (N + 11) // 4 * 4 if aligned else N + 5
     out = torch.full((M, ld_out), 7.0, device="cuda")
     ws_bytes = K.dot_gemm_workspace(M, N, Kd)
     ws = torch.empty(max(ws_bytes // 4, 1), device="cuda")
     K.dot_gemm(L.dtype_code(dtype), a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, Kd, out, L.IDENT, ld_out,
-               1, False, ws)
+               c0, False, ws)
     # the same product with A handed over transposed ([K, M], MN-major UMMA descriptors)
     at_hi, at_lo, ldat, *_ = _operands(K, L, a.t().contiguous(), dtype)
     out_mn = torch.full((M, ld_out), 7.0, device="cuda")
     K.dot_gemm(L.dtype_code(dtype), at_hi, at_lo, ldat, b_hi, b_lo, ldb, M, N, Kd, out_mn, L.IDENT,
-               ld_out, 1, False, ws, a_mn_major=True)
+               ld_out, c0, False, ws, a_mn_major=True)
     torch.cuda.synchronize()
-    assert torch.all(out[:, 0] == 7.0) and torch.all(out[:, N + 1:] == 7.0)  # untouched columns
+    assert torch.all(out[:, :c0] == 7.0) and torch.all(out[:, N + c0:] == 7.0)  # untouched columns
     assert torch.equal(out, out_mn)  # same operand values, same accumulation order
-    got = out[:, 1:N + 1].double()
+    got = out[:, c0:N + c0].double()
     if dtype == torch.float32:
         ref = a.double() @ b.double().t()
         bound = a.double().abs() @ b.double().abs().t()
