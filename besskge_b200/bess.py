@@ -304,6 +304,11 @@ class BessKGE(torch.nn.Module, ABC):
             self._placement = _Placement(self.sharding.n_shard)
         return self._ws, self._placement
 
+    def _side_stream(self, dev: torch.device) -> "torch.cuda.Stream":
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(dev)
+        return self._side
+
     # -------------------------------------------------------------- forward
     def forward(
         self,
@@ -597,8 +602,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                 nbytes = max(K.shared_bwd_cand_workspace(cfg, ps.n_query, ps.n_cand)
                              for ps in passes if ps.shared)
                 cand_ws = ws.get("cand_ws", (max(nbytes // 4, 1),), torch.float32)
-            sk = ws.get("sort_keys", (G,), torch.int32)
-            sp = ws.get("sort_perm", (G,), torch.int32)
+            sk = ws.get("sort_keys", (R, G), torch.int32)
+            sp = ws.get("sort_perm", (R, G), torch.int32)
             sort_ws = ws.get("sort_ws", (K.sort_workspace(max(G, R * S)) // 4 + 64,), torch.int32)
             rk = ws.get("rel_keys", (R * S,), torch.int32)
             rp = ws.get("rel_perm", (R * S,), torch.int32)
@@ -638,7 +643,21 @@ class EmbeddingMovingBessKGE(BessKGE):
         flat = self.negative_sampler.flat_negative_format
         scheme = self.negative_sampler.corruption_scheme
 
+        side = self._side_stream(dev) if train else None
         for s, step_rows in enumerate(self._step_rows(pl, bps)):
+            if train:
+                # The sort permutations of the scatter depend only on the step's indices:
+                # compute them on a side stream while the main stream gathers and scores
+                # (fork / join is captured into the CUDA graph like any other dependency).
+                main = torch.cuda.current_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for li, row in enumerate(step_rows):
+                        K.sort_keys(gidx[row], G, key_bits, sk[li], sp[li], sort_ws)
+                    rows_this_step = rel[step_rows[0]:step_rows[-1] + 1]
+                    if not rows_this_step.is_contiguous() or len(step_rows) != R:
+                        rows_this_step = rows_this_step.contiguous()
+                    K.sort_keys(rows_this_step.view(-1), R * S, rel_bits, rk, rp, sort_ws)
             # ================= gather (+ exchange) =================
             for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                 table = ent[shard]
@@ -804,20 +823,16 @@ class EmbeddingMovingBessKGE(BessKGE):
                 self._opt_state.setdefault("step", 0)
                 self._opt_state["step"] += 1
                 step_no = self._opt_state["step"]
+                torch.cuda.current_stream(dev).wait_stream(side)  # join: permutations ready
                 for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
-                    K.sort_keys(gidx[row], G, key_bits, sk, sp, sort_ws)
                     if pl.distributed:
                         g_dst, stride_rows = dBACK.data_ptr(), per
                     else:
                         g_dst = dTN.data_ptr() + li * per * W * 4
                         stride_rows = n * per
-                    self._update_entity(optimizer, ent[shard], shard, sk, sp, G, n_loc_rows, per,
+                    self._update_entity(optimizer, ent[shard], shard, sk[li], sp[li], G, n_loc_rows, per,
                                         dH[li], g_dst, stride_rows, step_no, ws)
                 # relation table (replicated): reduce per-query rows of all local replicas
-                rows_this_step = rel[step_rows[0]:step_rows[-1] + 1]
-                if not rows_this_step.is_contiguous() or len(step_rows) != R:
-                    rows_this_step = rows_this_step.contiguous()
-                K.sort_keys(rows_this_step.view(-1), R * S, rel_bits, rk, rp, sort_ws)
                 K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
                                        rel_table.shape[0], d_rel_table)
                 mean = getattr(optimizer, "relation_grad_reduction", "mean") == "mean"
