@@ -58,6 +58,11 @@ __all__ = [
 # ---------------------------------------------------------------------------
 # replica placement
 # ---------------------------------------------------------------------------
+# Tests only: run all shards on this process's GPU even though torch.distributed
+# is initialised (the local-mode result is the reference for the distributed one).
+FORCE_LOCAL = False
+
+
 class _Placement:
     """Which shards this process computes and how blocks are exchanged."""
 
@@ -65,7 +70,8 @@ class _Placement:
         self.n_shard = n_shard
         dist = torch.distributed
         self.distributed = bool(
-            dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            not FORCE_LOCAL and dist.is_available() and dist.is_initialized()
+            and dist.get_world_size() > 1
         )
         if self.distributed:
             if dist.get_world_size() != n_shard:
@@ -952,8 +958,6 @@ class ScoreMovingBessKGE(BessKGE):
         if optimizer is not None:
             raise NotImplementedError("ScoreMovingBessKGE is inference-only in this build")
         ws, pl = self._setup()
-        if pl.distributed:
-            raise NotImplementedError("ScoreMovingBessKGE: distributed mode not implemented yet")
         dev = ws.device
         ent, rel_table = self._tables()
         n = self.sharding.n_shard
@@ -970,59 +974,91 @@ class ScoreMovingBessKGE(BessKGE):
         flat = self.negative_sampler.flat_negative_format
         triple_based = isinstance(self.negative_sampler, TripleBasedShardedNegativeSampler)
         shared = bool(self.score_fn.negative_sample_sharing)
+        R = pl.n_local
+        dist = pl.distributed
+
+        def put(name, t, dtype):
+            if t is None:
+                return None
+            if dist:  # this rank only needs its own rows
+                t = t[pl.rank::n]
+            return self._stage(name, t, dtype, dev)
 
         h2 = _as_i32(head).reshape(L_rows, S)
         t2 = _as_i32(tail).reshape(L_rows, S)
-        gidx = self._stage("gidx", torch.cat([h2, t2], dim=1), torch.int32, dev)
-        rel = self._stage("rel", relation.reshape(L_rows, S), torch.int32, dev)
-        nidx = self._stage("nidx", negative.reshape(L_rows, n, B, Nn), torch.int32, dev)
-        tw = self._stage("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
-                         torch.float32, dev)
+        gidx = put("gidx", torch.cat([h2, t2], dim=1), torch.int32)
+        rel = put("rel", relation.reshape(L_rows, S), torch.int32)
+        nidx = put("nidx", negative.reshape(L_rows, n, B, Nn), torch.int32)
+        tw = put("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
+                 torch.float32)
         nmask = None
         if negative_mask is not None:
-            nmask = self._stage("nmask", negative_mask.reshape(L_rows, negative_mask.shape[1], -1),
-                                torch.bool, dev)
-        tmask = self._stage("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
-                            torch.bool, dev)
+            nmask = put("nmask", negative_mask.reshape(L_rows, negative_mask.shape[1], -1),
+                        torch.bool)
+        tmask = put("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
+                    torch.bool)
         one = ws.get("one", (1,), torch.float32)
         one.fill_(1.0)
 
-        # candidates per (scoring shard r): X columns contributed to every query
-        if flat and triple_based:
-            X = Nn  # one replicated list (bess.py:511-517)
-        elif flat:
-            X = n * Nn if scheme != "ht" else n * Nn  # all destinations' lists are shared
-        else:
-            X = Nn
+        # candidates per scoring shard: X columns contributed to every query
+        X = Nn if (flat and triple_based) or not flat else n * Nn
         N = n * X
-        H = ws.get("H", (n, S, W), tdt)
-        T = ws.get("TN", (n, n, p, W), tdt)  # received tails [replica][src][p]
+        # rows of the replicated query arrays are ordered (query shard j, q)
+        H = ws.get("H", (n, S, W), tdt)        # head rows of every shard's queries
+        T = ws.get("TN", (n, n, p, W), tdt)    # tails received by every replica [replica][src][p]
+        rel_all = ws.get("rel_all", (n * S,), torch.int32)
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         qv = ws.get("qv", (n * S, nvec, W), torch.float32)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        aux = ws.get("aux", (n * S, N), torch.float32) if need_aux else None
         need_scale = cfg.family == L.PAIRRE and cfg.normalize
-
-        n_out = bps * n
+        # local mode: the score matrix of all replicas is written in place, column block r*X by
+        # scoring shard r.  distributed: this rank scores all n*S queries against ITS candidates
+        # ([n*S, X]) and the scores travel back to the shards that own the queries (AllToAll).
+        ld_sc = N if not dist else X
+        aux = ws.get("aux", (n * S, ld_sc), torch.float32) if need_aux else None
+        n_out = bps * R
         pos_out = torch.empty(n_out * S, dtype=torch.float32, device=dev)
         neg_out = torch.empty(n_out * S, N, dtype=torch.float32, device=dev)
         loss_out = (torch.empty(n_out, dtype=torch.float32, device=dev)
                     if self.loss_fn is not None else None)
+        if dist:
+            SEND_T = ws.get("SEND", (n, p, W), tdt)
+            sc_local = ws.get("sc_local", (n * S, X), torch.float32)
+            sc_recv = ws.get("sc_recv", (n, S, X), torch.float32)
         acc: Dict[str, List] = {}
         half = p // 2
 
         for s in range(bps):
-            base = s * n
-            for r in range(n):
-                K.gather_route(ent[r], gidx[base + r], S, p, H[r], [T[j].data_ptr() for j in range(n)], r)
-            pos = pos_out[base * S:(base + n) * S]
-            neg = neg_out[base * S:(base + n) * S]  # [n*S, N] rows ordered (replica j, q)
-            rel_all = rel[base:base + n].reshape(-1)  # [n*S]
-            Hall = H.view(n * S, W)
-            Tall = T.view(n * S, W)
-            K.triple_fwd(cfg, dt, L.rows(Hall), L.rows(Tall), rel_table, rel_all, L.IDENT, n * S,
-                         pos, L.IDENT)
-            # (mode, query map over the n*S queries, fixed source)
+            if dist:
+                row0 = s
+                me = pl.rank
+                # own heads -> H[me]; tails routed to the replica that scores the positive
+                K.gather_route(ent[me], gidx[row0], S, p, H[me],
+                               [SEND_T[j].data_ptr() for j in range(n)], 0)
+                pl.all_to_all(T[me], SEND_T)
+                pos = pos_out[s * S:(s + 1) * S]
+                K.triple_fwd(cfg, dt, L.rows(H[me]), L.rows(T[me].view(S, W)), rel_table, rel[row0],
+                             L.IDENT, S, pos, L.IDENT)
+                # replicate the queries (bess.py:519-545)
+                torch.distributed.all_gather_into_tensor(rel_all, rel[row0].contiguous())
+                if scheme in ("t", "ht"):
+                    torch.distributed.all_gather_into_tensor(H.view(-1), H[me].reshape(-1).clone())
+                if scheme in ("h", "ht"):
+                    torch.distributed.all_gather_into_tensor(T.view(-1), T[me].reshape(-1).clone())
+                score_buf, scorers = sc_local, [(me, row0, 0)]
+            else:
+                base = s * n
+                for r in range(n):
+                    K.gather_route(ent[r], gidx[base + r], S, p, H[r],
+                                   [T[j].data_ptr() for j in range(n)], r)
+                    rel_all[r * S:(r + 1) * S].copy_(rel[base + r])
+                pos = pos_out[base * S:(base + n) * S]
+                K.triple_fwd(cfg, dt, L.rows(H.view(n * S, W)), L.rows(T.view(n * S, W)), rel_table,
+                             rel_all, L.IDENT, n * S, pos, L.IDENT)
+                score_buf = neg_out[base * S:(base + n) * S]  # [n*S, N]
+                scorers = [(r, base + r, r * X) for r in range(n)]
+            Hall, Tall = H.view(n * S, W), T.view(n * S, W)
+            # (mode, query map over the n*S queries, number of queries, fixed rows, flat-list id)
             if scheme == "t":
                 groups = [(L.MODE_TAILS, L.IDENT, n * S, Hall, 0)]
             elif scheme == "h":
@@ -1035,12 +1071,12 @@ class ScoreMovingBessKGE(BessKGE):
             for mode, qmap, nq, fixed_buf, bsel in groups:
                 K.prologue_fwd(cfg, dt, mode, L.rows(fixed_buf, rmap=qmap), rel_table, rel_all,
                                qmap, nq, qv)
-                for r in range(n):
-                    idx_r = nidx[base + r]  # [n(dst), B, Nn]
-                    table = ent[r]
+                for shard, row, col0 in scorers:
+                    idx_r = nidx[row]  # [n(query shard), B, Nn]: candidates stored on `shard`
+                    table = ent[shard]
                     if flat:
                         if triple_based:
-                            # replicated list; "ht": b selects heads / tails list
+                            # one replicated list; "ht": b selects the heads / tails list
                             sel = idx_r[0, bsel if scheme == "ht" else 0]
                             n_c = Nn
                         elif scheme == "ht":
@@ -1054,8 +1090,8 @@ class ScoreMovingBessKGE(BessKGE):
                         if need_scale:
                             scale = ws.get("cand_scale", (n_c,), torch.float32)
                             K.cand_inv_norm(dt, cand, n_c, W, scale)
-                        K.shared_fwd(cfg, dt, mode, qv, nq, cand, scale, n_c, neg, qmap, N, r * X,
-                                     aux)
+                        K.shared_fwd(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, qmap,
+                                     ld_sc, col0, aux)
                     else:
                         if shared:
                             raise NotImplementedError(
@@ -1063,21 +1099,27 @@ class ScoreMovingBessKGE(BessKGE):
                             )
                         # query at position (j, q): its Nn candidates are idx_r[j, q, :]
                         cand = L.rows(table, idx=idx_r.reshape(-1))
-                        K.pertriple_fwd(cfg, dt, mode, qv, nq, cand, Nn, Nn, neg, qmap, N, r * X,
-                                        aux)
-            for r in range(n):
-                o = base + r
-                pos_r, neg_r = pos[r * S:(r + 1) * S], neg[r * S:(r + 1) * S]
+                        K.pertriple_fwd(cfg, dt, mode, qv, nq, cand, Nn, Nn, score_buf, qmap,
+                                        ld_sc, col0, aux)
+            if dist:
+                # scores back to the shards that own the queries (bess.py:583-592)
+                torch.distributed.all_to_all_single(sc_recv.view(-1), sc_local.view(-1))
+                neg_out[s * S:(s + 1) * S].view(S, n, X).copy_(sc_recv.transpose(0, 1))
+                finals = [(s, s, pos_out[s * S:(s + 1) * S], neg_out[s * S:(s + 1) * S])]
+            else:
+                finals = [(base + r, base + r, pos[r * S:(r + 1) * S],
+                           score_buf[r * S:(r + 1) * S]) for r in range(n)]
+            for o, row, pos_r, neg_r in finals:
                 if nmask is not None:
-                    EmbeddingMovingBessKGE._mask_block(neg_r, S, N, p, n, X, nmask[o], flat,
+                    EmbeddingMovingBessKGE._mask_block(neg_r, S, N, p, n, X, nmask[row], flat,
                                                        scheme, 0)
                 if self.loss_fn is not None:
-                    w = tw[o] if tw is not None else one
+                    w = tw[row] if tw is not None else one
                     loss, _, _ = self.loss_fn.fwd_bwd(pos_r, neg_r, w)
                     loss_out[o] = loss
                 if self.evaluation is not None:
-                    self._finish_metrics({}, pos_r, neg_r, tmask[o] if tmask is not None else None,
-                                         acc)
+                    self._finish_metrics({}, pos_r, neg_r,
+                                         tmask[row] if tmask is not None else None, acc)
         out: Dict[str, Any] = {}
         if self.return_scores:
             out["positive_score"] = pos_out if tdt == torch.float32 else pos_out.to(tdt)

@@ -62,8 +62,84 @@ def main() -> None:
                                    atol=2e-6)
         if rank == 0:
             print(f"distributed parity ok: {fam} {scheme} flat={flat} n={n}")
+    inference_parity(rank, n)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def inference_parity(rank: int, n: int) -> None:
+    """ScoreMovingBessKGE and TopKQueryBessKGE: the distributed result of this rank equals
+    rows [rank] of the same module run in local mode (all shards on this GPU)."""
+    import besskge_b200.bess as bess_mod
+    from besskge_b200.bess import ScoreMovingBessKGE, TopKQueryBessKGE
+    from besskge_b200.metric import Evaluation
+    from besskge_b200.negative_sampler import PlaceholderNegativeSampler
+
+    d, n_rel, n_ent, p_part, Nn, k = 32, 5, 60 * n, 6, 9, 4
+    S = n * p_part
+    sh = Sharding.create(n_ent, n, seed=3)
+    lo = int(sh.shard_counts.min())
+    for fam, p, scheme, flat in [("TransE", 1, "t", True), ("DistMult", 2, "ht", True),
+                                 ("RotatE", 1, "h", False), ("PairRE", 1, "t", False)]:
+        gen = torch.Generator().manual_seed(23)
+        ew = 2 if fam in ("RotatE", "ComplEx") else 1
+        rw = 2 * d if fam in ("ComplEx", "PairRE") else d
+        ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen) * 0.5
+        rel = torch.randn(n_rel, rw, generator=gen) * 0.5
+        Bn = (2 if scheme == "ht" else 1) if flat else S
+        batch = dict(
+            head=torch.randint(lo, (2 * n, n, p_part), generator=gen, dtype=torch.int32),
+            tail=torch.randint(lo, (2 * n, n, p_part), generator=gen, dtype=torch.int32),
+            relation=torch.randint(n_rel, (2 * n, n, p_part), generator=gen, dtype=torch.int32),
+            negative=torch.randint(lo, (2 * n, n, Bn, Nn), generator=gen, dtype=torch.int32))
+        results = []
+        for force_local in (True, False):
+            bess_mod.FORCE_LOCAL = force_local
+            sf = H.make_score_fn(fam, flat, p, sh, n_rel, d, ent, rel)
+            ev = Evaluation(["mrr", "hits@3"], mode="average", reduction="sum", return_ranks=True)
+            model = ScoreMovingBessKGE(H.fake_sampler(scheme, flat, triple_based=False), sf,
+                                       evaluation=ev, return_scores=True)
+            res = model(**batch)
+            torch.cuda.synchronize()
+            results.append(res)
+        bess_mod.FORCE_LOCAL = False
+        loc, dis = results
+        rows = torch.cat([torch.arange(S) + (st * n + rank) * S for st in range(2)])
+        torch.testing.assert_close(dis["positive_score"].cpu(), loc["positive_score"].cpu()[rows],
+                                   rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(dis["negative_score"].cpu(), loc["negative_score"].cpu()[rows],
+                                   rtol=1e-6, atol=1e-6)
+        assert dis["metrics"].shape[0] == 2
+        if rank == 0:
+            print(f"distributed ScoreMoving == local: {fam} {scheme} flat={flat} n={n}")
+
+    for fam, p, scheme in [("DistMult", 2, "t"), ("TransE", 1, "h"), ("ComplEx", 2, "t")]:
+        gen = torch.Generator().manual_seed(29)
+        ew = 2 if fam in ("RotatE", "ComplEx") else 1
+        rw = 2 * d if fam in ("ComplEx", "PairRE") else d
+        ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen)
+        rel = torch.randn(n_rel, rw, generator=gen)
+        q = dict(relation=torch.randint(n_rel, (2 * n, S), generator=gen, dtype=torch.int32),
+                 head=torch.randint(lo, (2 * n, S), generator=gen, dtype=torch.int32),
+                 tail=torch.randint(lo, (2 * n, S), generator=gen, dtype=torch.int32))
+        results = []
+        for force_local in (True, False):
+            bess_mod.FORCE_LOCAL = force_local
+            sf = H.make_score_fn(fam, True, p, sh, n_rel, d, ent, rel)
+            model = TopKQueryBessKGE(k=k, candidate_sampler=PlaceholderNegativeSampler(scheme),
+                                     score_fn=sf, return_scores=True)
+            model.device_window = 16
+            res = model(**q)
+            torch.cuda.synchronize()
+            results.append(res)
+        bess_mod.FORCE_LOCAL = False
+        loc, dis = results
+        rows = torch.cat([torch.arange(S) + (st * n + rank) * S for st in range(2)])
+        torch.testing.assert_close(dis["topk_scores"].cpu(), loc["topk_scores"].cpu()[rows],
+                                   rtol=1e-6, atol=1e-6)
+        assert torch.equal(dis["topk_global_id"].cpu(), loc["topk_global_id"].cpu()[rows])
+        if rank == 0:
+            print(f"distributed TopKQuery == local: {fam} {scheme} n={n}")
 
 
 if __name__ == "__main__":
