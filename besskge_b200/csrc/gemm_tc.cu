@@ -64,9 +64,18 @@ constexpr int kBarrierBytes = 256;
 // epilogue staging for TMA stores: per epilogue warp two [32 rows x 128 B] swizzled chunks
 constexpr int kEpiChunkBytes = 32 * 128;
 constexpr int kEpiBytes = 4 * 2 * kEpiChunkBytes;
-template <int MODE>
+// TWO (cta_group::2): a CTA pair runs one 256 x 256 MMA; each CTA stages its 128 rows of A and
+// HALF of the B tile (the tensor core reads the other half from the peer's shared memory), so a
+// stage shrinks to 32 KB and the ring deepens to 6 stages.
+template <int MODE, bool TWO>
+constexpr int stage_bytes() {
+  return ModeTraits<MODE>::kOperandTiles * (ModeTraits<MODE>::kATile + ModeTraits<MODE>::kBTile / (TWO ? 2 : 1));
+}
+template <bool TWO>
+constexpr int num_stages() { return TWO ? 6 : kStages; }
+template <int MODE, bool TWO = false>
 constexpr int smem_bytes() {
-  return kStages * ModeTraits<MODE>::kStageBytes + kEpiBytes + kBarrierBytes + 1024 /* alignment slack */;
+  return num_stages<TWO>() * stage_bytes<MODE, TWO>() + kEpiBytes + kBarrierBytes + 1024 /* alignment slack */;
 }
 
 // ------------------------------------------------------------------ PTX ----
@@ -134,6 +143,54 @@ BESS_D void umma_commit_mc(uint32_t bar, uint16_t mask) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(bar), "h"(mask)
       : "memory");
+}
+BESS_D uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+BESS_D void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's smem, the bytes are credited to the pair leader's barrier
+BESS_D void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+BESS_D void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+BESS_D void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+BESS_D void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+template <int MODE>
+BESS_D void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == GEMM_TF32X3) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 BESS_D void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -256,15 +313,19 @@ struct GemmParams {
 // CS = cluster size along M: the CS CTAs of a cluster work on CS consecutive m-blocks of the
 // same (split, n-block); each loads 1/CS of the B tile and multicasts it to the whole cluster,
 // which divides the L2 -> SM traffic of the shared operand by CS.
-template <int MODE, bool A_MN, int CS>
+template <int MODE, bool A_MN, int CS, bool TWO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
   using T = ModeTraits<MODE>;
+  static_assert(!TWO || CS == 2, "cta_group::2 needs a cluster of two");
+  constexpr int kStages = num_stages<TWO>();
+  constexpr int kStageBytes = stage_bytes<MODE, TWO>();
+  constexpr int kBTileCta = T::kBTile / (TWO ? 2 : 1);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + kStages * T::kStageBytes;
+  const uint32_t epi_base = smem_base + kStages * kStageBytes;
   const uint32_t bar_base = epi_base + kEpiBytes;
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -295,15 +356,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CS);
+      mbar_init(empty_bar(s), TWO ? 1 : CS);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), TWO ? 8 : 4);  // TWO: the epilogue warps of both CTAs report to the leader
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) {
+    if (TWO) tmem_alloc_2sm(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -322,9 +386,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int k_end = min(p.K, k_begin + p.k_per_split);
         for (int k = k_begin; k < k_end; k += T::kBlockK) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * T::kStageBytes;
+          const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + T::kOperandTiles * T::kATile;
-          mbar_expect_tx(full_bar(stage), T::kStageBytes);
+          if (TWO) {
+            // both CTAs' loads are credited to the leader's barrier (it alone issues the MMAs)
+            const uint32_t lbar = mapa_rank(full_bar(stage), 0);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * kStageBytes);
+            if (A_MN) {
+#pragma unroll
+              for (int i = 0; i < T::kMnAtoms; ++i) {
+                tma_load_2d_2sm(sa + i * T::kMnSlab, &map_a_hi, lbar, m0 + i * T::kMnAtom, k);
+                if (MODE == GEMM_TF32X3)
+                  tma_load_2d_2sm(sa + T::kATile + i * T::kMnSlab, &map_a_lo, lbar, m0 + i * T::kMnAtom, k);
+              }
+            } else {
+              tma_load_2d_2sm(sa, &map_a_hi, lbar, k, m0);
+              if (MODE == GEMM_TF32X3) tma_load_2d_2sm(sa + T::kATile, &map_a_lo, lbar, k, m0);
+            }
+            const int nb0 = n0 + cta_rank * (kBlockN / 2);
+            tma_load_2d_2sm(sb, &map_b_hi, lbar, k, nb0);
+            if (MODE == GEMM_TF32X3) tma_load_2d_2sm(sb + kBTileCta, &map_b_lo, lbar, k, nb0);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_expect_tx(full_bar(stage), kStageBytes);
           if (A_MN) {
 #pragma unroll
             for (int i = 0; i < T::kMnAtoms; ++i) {
@@ -354,10 +439,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ============================= MMA issuer =============================
-    if (lane == 0) {
+    if (lane == 0 && (!TWO || cta_rank == 0)) {
       // instruction descriptor: D = F32, A/B format, K-major both, N >> 3, M >> 4
       const uint32_t idesc = (1u << 4) | (T::kFmt << 7) | (T::kFmt << 10) | ((A_MN ? 1u : 0u) << 15) |
-                             ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+                             ((uint32_t)(kBlockN >> 3) << 17) |
+                             ((uint32_t)((TWO ? 2 * kBlockM : kBlockM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -374,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int k = k_begin; k < k_end; k += T::kBlockK) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * T::kStageBytes;
+          const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + T::kOperandTiles * T::kATile;
 #pragma unroll
           for (int ks = 0; ks < T::kKSteps; ++ks) {
@@ -383,21 +469,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (MODE == GEMM_TF32X3) {
               const uint64_t a_lo = A_MN ? smem_desc_mn<MODE>(sa + T::kATile + ks * T::kMnKStep)
                                          : smem_desc<MODE>(sa + T::kATile + ks * 32);
-              const uint64_t b_lo = smem_desc<MODE>(sb + T::kBTile + ks * 32);
-              umma<MODE>(tmem_d, a_lo, b_hi, idesc, first ? 0u : 1u);
-              umma<MODE>(tmem_d, a_hi, b_lo, idesc, 1u);
-              umma<MODE>(tmem_d, a_hi, b_hi, idesc, 1u);
+              const uint64_t b_lo = smem_desc<MODE>(sb + kBTileCta + ks * 32);
+              if (TWO) {
+                umma_2sm<MODE>(tmem_d, a_lo, b_hi, idesc, first ? 0u : 1u);
+                umma_2sm<MODE>(tmem_d, a_hi, b_lo, idesc, 1u);
+                umma_2sm<MODE>(tmem_d, a_hi, b_hi, idesc, 1u);
+              } else {
+                umma<MODE>(tmem_d, a_lo, b_hi, idesc, first ? 0u : 1u);
+                umma<MODE>(tmem_d, a_hi, b_lo, idesc, 1u);
+                umma<MODE>(tmem_d, a_hi, b_hi, idesc, 1u);
+              }
             } else {
-              umma<MODE>(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
+              if (TWO) umma_2sm<MODE>(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
+              else umma<MODE>(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
             }
             first = 0;
           }
-          // frees the smem stage (in every CTA of the cluster: peers multicast into it)
-          if (CS > 1) umma_commit_mc(empty_bar(stage), kMcMask);
+          // frees the smem stage (in every CTA of the cluster: peers multicast into it / the
+          // pair's MMA read both CTAs' stage)
+          if (TWO) umma_commit_2sm(empty_bar(stage));
+          else if (CS > 1) umma_commit_mc(empty_bar(stage), kMcMask);
           else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs of a pair)
+        if (TWO) umma_commit_2sm(tfull_bar(buf));
+        else umma_commit(tfull_bar(buf));
       }
     }
   } else {
@@ -478,7 +575,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) {
+        if (TWO) mbar_arrive_cluster(mapa_rank(tempty_bar(buf), 0));
+        else mbar_arrive(tempty_bar(buf));
+      }
     }
     if (p.tma_store && lane == 0) tma_store_wait_all();  // smem must outlive the bulk stores
   }
@@ -487,7 +587,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (CS > 1) cluster_sync_all();  // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (TWO) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -656,7 +757,7 @@ static int choose_split(int M, int N, int K, int block_k, int* k_per_split) {
   return split;
 }
 
-template <int MODE, bool A_MN, int CS>
+template <int MODE, bool A_MN, int CS, bool TWO = false>
 static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
                        int64_t ldb, int M, int N, int K, float* out, bess_rowmap_t out_map, int64_t ld_out,
                        int col0, int accumulate, float* workspace, int64_t workspace_bytes,
@@ -703,8 +804,8 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN, CS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE>());
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, A_MN, CS, TWO>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<MODE, TWO>());
     if (e != cudaSuccess) {
       bess_set_error("cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
       return BESS_ERR_CUDA;
@@ -718,7 +819,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes<MODE>();
+  cfg.dynamicSmemBytes = smem_bytes<MODE, TWO>();
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -727,7 +828,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, A_MN, CS>, ma_hi, ma_lo, mb_hi, mb_lo, m_out, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, A_MN, CS, TWO>, ma_hi, ma_lo, mb_hi, mb_lo, m_out, p);
   if (le != cudaSuccess) {
     bess_set_error("gemm_tc_kernel launch failed: %s", cudaGetErrorString(le));
     return BESS_ERR_CUDA;
@@ -775,14 +876,19 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
   // cluster size along M (B-tile multicast); BESSKGE_GEMM_CLUSTER overrides for experiments
   const int m_blocks_ = ceil_div(M, kBlockM);
   int cs = m_blocks_ >= 4 ? 2 : 1;
+  // cta_group::2 pair MMA (256 x 256 per CTA pair, half of B per CTA): measured 5-8 % faster than
+  // cluster multicast for the L2-bound 3xTF32 contractions, slower for the epilogue-bound half ones
+  bool two = cs == 2 && dtype == BESS_F32;
   if (const char* env = getenv("BESSKGE_GEMM_CLUSTER")) {
     const int v = atoi(env);
-    if (v == 1 || v == 2 || v == 4) cs = v;
+    if (v == 1 || v == 2 || v == 4) { cs = v; two = false; }
+    if (v == 22) { cs = 2; two = true; }
   }
 #define GEMM_ARGS a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0, accumulate, \
                   (float*)workspace, workspace_bytes, st
 #define GEMM_GO(MODE)                                                                    \
   if (cs == 4) return a_mn_major ? launch_gemm<MODE, true, 4>(GEMM_ARGS) : launch_gemm<MODE, false, 4>(GEMM_ARGS); \
+  if (cs == 2 && two) return a_mn_major ? launch_gemm<MODE, true, 2, true>(GEMM_ARGS) : launch_gemm<MODE, false, 2, true>(GEMM_ARGS); \
   if (cs == 2) return a_mn_major ? launch_gemm<MODE, true, 2>(GEMM_ARGS) : launch_gemm<MODE, false, 2>(GEMM_ARGS); \
   return a_mn_major ? launch_gemm<MODE, true, 1>(GEMM_ARGS) : launch_gemm<MODE, false, 1>(GEMM_ARGS)
   switch (dtype) {
