@@ -68,6 +68,17 @@ BESS_HD int pair_nvec(const FamCfg& c) {
 BESS_HD float nacc(int p, float e) { return p == 1 ? fabsf(e) : e * e; }
 BESS_HD float nfin(int p, float a) { return p == 1 ? a : sqrtf(a); }
 BESS_HD float fsign(float e) { return (float)((e > 0.f) - (e < 0.f)); }
+// coef * sign(e) with sign(0) = 0 (the L1 sub-gradient torch uses).  Device: one LOP3 on the
+// sign bit + a select instead of two compares, an int->float conversion and a multiply — the
+// inner loop of the L1 backward tile kernels is issue-bound on exactly this.
+BESS_HD float sign_mul(float coef, float e) {
+#ifdef __CUDA_ARCH__
+  const float t = __int_as_float(__float_as_int(coef) ^ (__float_as_int(e) & (int)0x80000000));
+  return e != 0.f ? t : 0.f;
+#else
+  return coef * fsign(e);
+#endif
+}
 // d(norm)/de given the finished norm value nv
 BESS_HD float ndiff(int p, float e, float nv) {
   if (p == 1) return fsign(e);
@@ -606,11 +617,11 @@ BESS_HD void pair_elem_bwd(int p, int apply_tanh, float q0, float q1, float q2, 
     dq0 = coef * cv; dcv = coef * q0; dq1 = dq2 = 0.f;
   } else if (OP == OP_DIST) {
     const float e = q0 - cv;
-    const float de = coef * (p == 1 ? fsign(e) : e);
+    const float de = p == 1 ? sign_mul(coef, e) : coef * e;
     dq0 = de; dcv = -de; dq1 = dq2 = 0.f;
   } else if (OP == OP_PAIRRE) {
     const float e = cv * q1 - q0;
-    const float de = coef * (p == 1 ? fsign(e) : e);
+    const float de = p == 1 ? sign_mul(coef, e) : coef * e;
     dq0 = -de; dq1 = de * cv; dcv = de * q1; dq2 = 0.f;
   } else {
     const BoxDist f = boxe_dist(apply_tanh, q0 + cv, q1, q2, -1);
