@@ -641,6 +641,12 @@ class EmbeddingMovingBessKGE(BessKGE):
             use_tc and train and passes
             and all(ps.shared and ps.qmap.group <= 0 and ps.qmap.offset == 0 and ps.n_query == S
                     and ps.col0 % 8 == 0 for ps in passes))
+        # Distributed 't'-type steps: the gradient rows that travel back (tails from
+        # score_triple, negatives from the dC contractions) are complete before the dQ
+        # contractions and the prologue backward run, so their push over NVLink and the
+        # handshake go to the side stream and overlap that remaining compute.
+        early_push = bool(px is not None and direct_ds and R == 1
+                          and all(ps.fixed_from_head for ps in passes))
         ds_hi = ds_lo = None
         if direct_ds:
             ds_hi = ws.get("tc_dsd_hi", (S, ldN), tdt)
@@ -757,6 +763,20 @@ class EmbeddingMovingBessKGE(BessKGE):
                                  pos, d_pos[li], L.IDENT, L.rows(dHl),
                                  L.rows(dTNl, rmap=L.rowmap(p, per, 0)), dRq[li], False, False,
                                  False)
+                    if early_push:
+                        for pi, ps in enumerate(passes):
+                            d_cand = self._cand_rows(ps, dHl, dTNl, local)
+                            K.dot_gemm(dt, ds_hi, ds_lo, ldN, tc_q[pi].hit, tc_q[pi].lot,
+                                       tc_q[pi].ldt, ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
+                                       d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base,
+                                       a_mn_major=True, a_offset_elems=ps.col0)
+                        main = torch.cuda.current_stream(dev)
+                        side.wait_stream(main)
+                        with torch.cuda.stream(side):
+                            blk = per * W * 4
+                            K.peer_push(dTN[0], blk,
+                                        [q + px.off_grad + pl.rank * blk for q in px.ptrs], blk)
+                            px.handshake(1)
                     for pi, ps in enumerate(passes):
                         fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
                                  else L.rows(TNl, rmap=ps.fixed_map))
@@ -775,10 +795,12 @@ class EmbeddingMovingBessKGE(BessKGE):
                                 K.dot_gemm(dt, ds_hi, ds_lo, ldN, c_op.hit, c_op.lot, c_op.ldt,
                                            ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
                                            gemm_ws, a_offset_elems=ps.col0)
-                                K.dot_gemm(dt, ds_hi, ds_lo, ldN, q_op.hit, q_op.lot, q_op.ldt,
-                                           ps.n_cand, W, ps.n_query, d_qv, d_cand.map, d_cand.pitch,
-                                           0, ps.aug, gemm_ws, out_ptr=d_cand.base,
-                                           a_mn_major=True, a_offset_elems=ps.col0)
+                                if not early_push:
+                                    K.dot_gemm(dt, ds_hi, ds_lo, ldN, q_op.hit, q_op.lot, q_op.ldt,
+                                               ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
+                                               d_cand.pitch, 0, ps.aug, gemm_ws,
+                                               out_ptr=d_cand.base, a_mn_major=True,
+                                               a_offset_elems=ps.col0)
                             else:
                                 ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True)
                                 ds.fill(L.F32, L.rows(d_neg[li], rmap=ps.qmap, pitch=N,
@@ -820,16 +842,38 @@ class EmbeddingMovingBessKGE(BessKGE):
             if px is not None and not train:
                 px.handshake(1)  # every rank is done reading its receive buffer
             if train:
-                if px is not None:
+                if px is not None and not early_push:
                     blk = per * W * 4
-                    K.peer_push(dTN[0], blk, [p + px.off_grad + pl.rank * blk for p in px.ptrs], blk)
+                    K.peer_push(dTN[0], blk, [q + px.off_grad + pl.rank * blk for q in px.ptrs], blk)
                     px.handshake(1)
-                elif pl.distributed:
+                elif pl.distributed and px is None:
                     pl.all_to_all(dBACK, dTN[0])
                 self._opt_state.setdefault("step", 0)
                 self._opt_state["step"] += 1
                 step_no = self._opt_state["step"]
-                torch.cuda.current_stream(dev).wait_stream(side)  # join: permutations ready
+                main = torch.cuda.current_stream(dev)
+                main.wait_stream(side)  # join: permutations ready (and the early gradient push)
+                # relation table (replicated): reduce per-query rows of all local replicas; its
+                # all-reduce over peer memory runs on the side stream under the entity scatter
+                K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
+                                       rel_table.shape[0], d_rel_table)
+                mean = getattr(optimizer, "relation_grad_reduction", "mean") == "mean"
+                if px is not None:
+                    # every rank pushes its partial into slot [rank] of every rank, then sums the
+                    # n slots in rank order (bit-identical tables on all ranks)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        cnt = _up(rel_table.numel() * 4, 16) // 4
+                        K.peer_push(d_rel_table, 0,
+                                    [q + px.off_rel + pl.rank * cnt * 4 for q in px.ptrs], cnt * 4)
+                        px.handshake(2)
+                        K.peer_reduce(px.view(px.off_rel, (n, cnt), torch.float32), n, cnt,
+                                      1.0 / n if mean else 1.0, d_rel_table)
+                else:
+                    if pl.distributed:
+                        torch.distributed.all_reduce(d_rel_table)
+                    if mean and n > 1:
+                        d_rel_table.mul_(1.0 / n)
                 for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                     if pl.distributed:
                         g_dst, stride_rows = dBACK.data_ptr(), per
@@ -838,25 +882,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                         stride_rows = n * per
                     self._update_entity(optimizer, ent[shard], shard, sk[li], sp[li], G, n_loc_rows, per,
                                         dH[li], g_dst, stride_rows, step_no, ws)
-                # relation table (replicated): reduce per-query rows of all local replicas
-                K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
-                                       rel_table.shape[0], d_rel_table)
-                mean = getattr(optimizer, "relation_grad_reduction", "mean") == "mean"
                 if px is not None:
-                    # all-reduce of the replicated relation gradient: every rank pushes its
-                    # partial into slot [rank] of every rank, then sums the n slots in rank
-                    # order (bit-identical tables on all ranks)
-                    cnt = _up(rel_table.numel() * 4, 16) // 4
-                    K.peer_push(d_rel_table, 0, [p + px.off_rel + pl.rank * cnt * 4 for p in px.ptrs],
-                                cnt * 4)
-                    px.handshake(2)
-                    K.peer_reduce(px.view(px.off_rel, (n, cnt), torch.float32), n, cnt,
-                                  1.0 / n if mean else 1.0, d_rel_table)
-                else:
-                    if pl.distributed:
-                        torch.distributed.all_reduce(d_rel_table)
-                    if mean and n > 1:
-                        d_rel_table.mul_(1.0 / n)
+                    main.wait_stream(side)  # relation all-reduce done
                 self._update_relation(optimizer, rel_table, d_rel_table, step_no, ws)
 
         out: Dict[str, Any] = {}

@@ -24,6 +24,7 @@ def main() -> None:
     rank, n = dist.get_rank(), dist.get_world_size()
     for fam, p, scheme, flat, shared, lkind in [
         ("TransE", 1, "t", True, True, "logsigmoid"),
+        ("DistMult", 2, "t", True, True, "logsigmoid"),  # tensor-core path with the early gradient push
         ("DistMult", 2, "ht", True, True, "margin_ranking"),
         ("RotatE", 2, "h", False, False, "logsigmoid"),
     ]:
