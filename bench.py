@@ -34,6 +34,9 @@ WORKLOADS = {
     "biokg-distmult-d256-fp32": ("ogbl-biokg", "DistMult", 256, 2, "fp32", 16384, 2048),
     "biokg-transe-l2-d128-fp32": ("ogbl-biokg", "TransE", 128, 2, "fp32", 8192, 64),
     "wikikg2-transe-l1-d256-bf16": ("ogbl-wikikg2", "TransE", 256, 1, "bf16", 8192, 256),
+    # BASELINE.json configs[2]: top-10 tail prediction against ALL entities (inference);
+    # metric = queries/s; shard_bs = queries per GPU per step; "negatives" unused
+    "yago-complex-d256-topk": ("yago3-10", "ComplEx", 256, 2, "fp32", 2048, 0),
 }
 DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
@@ -313,12 +316,128 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+def run_topk(args) -> None:
+    """configs[2]: TopKQueryBessKGE, ComplEx d=256 (row 512) fp32, k=10, every query scored
+    against all entities of a YAGO3-10-shaped graph; one step = shard_bs queries per GPU."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import besskge_b200  # noqa: F401
+    from besskge_b200 import _lib as L_, scoring
+    from besskge_b200.bess import TopKQueryBessKGE
+    from besskge_b200.dataset import DATASET_SHAPES
+    from besskge_b200.metric import Evaluation
+    from besskge_b200.negative_sampler import PlaceholderNegativeSampler
+    from besskge_b200.sharding import Sharding
+
+    pk = peaks()
+    shape, fam, d, _, dt, sbs, _ = WORKLOADS[args.workload]
+    S = args.shard_bs or sbs
+    n_entity, n_rel, _ = DATASET_SHAPES[shape]
+    n = world
+    sh = Sharding.create(n_entity, n, seed=1234)
+    torch.manual_seed(1234)
+    sf = scoring.ComplEx(True, sh, n_rel, d).to(device=dev, dtype=DTYPES[dt])
+    ev = Evaluation(["mrr", "hits@10"], worst_rank_infty=True, reduction="sum")
+    model = TopKQueryBessKGE(k=10, candidate_sampler=PlaceholderNegativeSampler("t"), score_fn=sf,
+                             evaluation=ev, return_scores=True, window_size=500)
+    g = torch.Generator().manual_seed(1234 + rank)
+    total = args.warmup + args.steps
+    lo = int(sh.shard_counts.min())
+    batches = []
+    for _ in range(total):  # [n_shard, S] host layout; distributed ranks read their own row
+        batches.append(dict(
+            relation=torch.randint(n_rel, (n, S), generator=g, dtype=torch.int32).pin_memory(),
+            head=torch.randint(lo, (n, S), generator=g, dtype=torch.int32).pin_memory(),
+            tail=torch.randint(n_entity, (n, S), generator=g, dtype=torch.int32).pin_memory()))
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(read_back: bool):
+        for i in range(args.warmup):
+            model(**batches[i])
+        barrier()
+        c0 = L_.call("bess_launch_count")
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        d2h = 0
+        for i in range(args.warmup, total):
+            out = model(**batches[i])
+            if read_back:
+                ids = out["topk_global_id"].cpu()
+                d2h = ids.numel() * ids.element_size()
+        en.record()
+        barrier()
+        t = torch.tensor([st.elapsed_time(en) * 1e-3], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()), d2h, L_.call("bess_launch_count") - c0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_dev, _, launches = timed(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t_e2e, d2h, _ = timed(True)
+    if rank == 0:
+        Es, W = sh.max_entity_per_shard, 2 * d
+        local = 1 if world > 1 else n
+        # per GPU and step: all n*S queries against the local shard(s)
+        flops = 2.0 * (n * S) * Es * W * local
+        passes = 3 if dt == "fp32" else 1
+        queries = n * S * args.steps
+        line = {
+            "metric": "topk_queries_per_sec", "value": queries / t_dev, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32"}.get(dt, dt), "data": "synthetic",
+            "config": {"workload": args.workload, "dataset_shape": shape, "n_entity": n_entity,
+                       "n_shard": n, "queries_per_gpu_per_step": S, "k": 10, "score_fn": fam,
+                       "embedding_size": d, "candidates": "all entities",
+                       "l2": "no flush: every step streams the whole shard "
+                             f"({Es * W * 4 / 1e6:.0f} MB of fp32 rows + operand copies) > 126 MB L2"
+                             if Es * W * 12 > 126e6 else "shard operands are L2-resident "
+                             f"({Es * W * 12 / 1e6:.0f} MB incl. hi/lo copies); score windows "
+                             f"({n * S * 4096 * 4 / 1e6:.0f} MB each) are not"},
+            "e2e": {"value": queries / t_e2e, "unit": "queries/s",
+                    "h2d_bytes_per_step": 3 * S * 4 * local, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "gemm_tc_kernel (tcgen05 window scores = Q C^T) over the whole step",
+                         "bound": "tensor", "achieved": flops * args.steps / t_dev / 1e12,
+                         "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "traffic": None,
+                         "mma_passes": passes,
+                         "frac": flops * args.steps / t_dev / 1e12 / pk["tensor_sustained"],
+                         "note": "whole-step figure (GEMM + operand split + top-k merge); scores/s = "
+                                 f"{(n * S) * Es * local * args.steps / t_dev:.3e}",
+                         "peak_source": pk["source"]},
+            "cpu_baseline": None,
+        }
+        emit(line)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main() -> None:
     global _REAL_STDOUT
     args = parse()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+    if args.workload.endswith("-topk"):
+        if args.impl == "reference":
+            emit({"impl": "reference", "unavailable": "the reference arm is defined on the training "
+                                                      "workloads (configs[1]); run without --workload"})
+            return
+        run_topk(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
