@@ -81,6 +81,7 @@ SIGNATURES = {
     "bess_dot_gemm_workspace": [_I, _I, _I],
     "bess_dot_gemm": [_I, _P, _P, _L, _I, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P],
     "bess_split_operand": [_I, Rows, _I, _I, _P, _I, _P, _P, _L, _P, _P, _L, _P],
+    "bess_table_operand_refresh": [_P, _L, _I, _L, _P, _P, _L, _P, _I, _P],
     "bess_score_pertriple_fwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, RowMap, _L, _I, _P, _P],
     "bess_score_pertriple_bwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, _P, RowMap, _L, _I, _P, _P,
                                  Rows, _P],

@@ -1296,6 +1296,25 @@ class TopKQueryBessKGE(torch.nn.Module):
         self._ws: Optional[K.Workspace] = None
         self._placement: Optional[_Placement] = None
         self._maps: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        # cached 3xTF32 operands of each local fp32 shard: li -> (key, hi, lo, state)
+        self._table_ops: Dict[int, Tuple[Any, torch.Tensor, torch.Tensor, torch.Tensor]] = {}
+
+    def _table_operand(self, li: int, table: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """hi / lo [Es, ld] tensor-core operands of an fp32 shard.  The shard is constant
+        during inference, so the split is done once; every call re-checks a device-side
+        checksum of the table (one read-only pass) and rebuilds only if the bytes changed."""
+        ld = _pad8(table.shape[1])
+        key = (table.data_ptr(), tuple(table.shape), table.stride(0), table.device)
+        ent = self._table_ops.get(li)
+        force = ent is None or ent[0] != key
+        if force:
+            hi = torch.empty(table.shape[0], ld, dtype=torch.float32, device=table.device)
+            lo = torch.empty_like(hi)
+            state = torch.zeros(4, dtype=torch.int64, device=table.device)
+            ent = (key, hi, lo, state)
+            self._table_ops[li] = ent
+        K.table_operand_refresh(table, ent[1], ent[2], ld, ent[3], force)
+        return ent[1], ent[2], ld
 
     def _setup(self) -> Tuple[K.Workspace, _Placement]:
         dev = self.score_fn.entity_embedding.device
@@ -1423,6 +1442,13 @@ class TopKQueryBessKGE(torch.nn.Module):
             # ---- score where the candidates live, keep a running top-(k+1)
             for li, (row, shard) in enumerate(zip(rows, pl.shards)):
                 table = ent[shard]
+                tab_hi = tab_lo = None
+                if use_tc and negative is None:
+                    # whole-shard operands: the table itself for halves, cached hi / lo for fp32
+                    if tdt == torch.float32:
+                        tab_hi, tab_lo, tab_ld = self._table_operand(li, table)
+                    elif table.stride(0) == _pad8(W):
+                        tab_hi, tab_ld = table, table.stride(0)
                 for c0 in range(0, n_cand_total, win):
                     nc = min(win, n_cand_total - c0)
                     if negative is None:
@@ -1442,6 +1468,10 @@ class TopKQueryBessKGE(torch.nn.Module):
                     if per_query:
                         K.pertriple_fwd(cfg, dt, mode, qv, nS, cand, nc, nc, scores, L.IDENT, win,
                                         0, aux)
+                    elif use_tc and tab_hi is not None:
+                        K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, tab_hi[c0:c0 + nc],
+                                   None if tab_lo is None else tab_lo[c0:c0 + nc], tab_ld, nS, nc,
+                                   W, scores, L.IDENT, win, 0, False, gemm_ws)
                     elif use_tc:
                         c_op = _TcOperand(ws, "tkc", nc, W, tdt, False)
                         c_op.fill(dt, cand, dt, None, dev)

@@ -50,6 +50,10 @@ struct Elem<float> {
     float4 v = *reinterpret_cast<const float4*>(p);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
   }
+  static BESS_D void unpack(const uint4& v, float (&out)[4]) {
+    out[0] = __uint_as_float(v.x); out[1] = __uint_as_float(v.y);
+    out[2] = __uint_as_float(v.z); out[3] = __uint_as_float(v.w);
+  }
   static BESS_D float to_f(float v) { return v; }
   static BESS_D float from_f(float v) { return v; }
 };
@@ -65,6 +69,14 @@ struct Elem<__half> {
       out[2 * i] = f.x; out[2 * i + 1] = f.y;
     }
   }
+  static BESS_D void unpack(const uint4& v, float (&out)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      out[2 * i] = f.x; out[2 * i + 1] = f.y;
+    }
+  }
   static BESS_D float to_f(__half v) { return __half2float(v); }
   static BESS_D __half from_f(float v) { return __float2half_rn(v); }
 };
@@ -73,6 +85,14 @@ struct Elem<__nv_bfloat16> {
   static constexpr int kVec = 8;
   static BESS_D void load_vec(const __nv_bfloat16* p, float (&out)[8]) {
     uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      out[2 * i] = f.x; out[2 * i + 1] = f.y;
+    }
+  }
+  static BESS_D void unpack(const uint4& v, float (&out)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

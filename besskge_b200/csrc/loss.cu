@@ -2,6 +2,7 @@
 // score-gradient, ranks, deterministic sums, small utilities.
 // One CTA per query row of the [S, N] negative-score matrix.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -429,6 +430,91 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* win_score,
   }
 }
 
+// Same merge for k <= 32 (the usual k + 1 = 11): the best list lives in
+// registers (lane i = entry i), the window row is streamed with 128-bit loads,
+// TKR_U of them in flight per lane, and a chunk is skipped with one vote when
+// none of its TKR_U * 128 scores beats the current worst entry — the common case
+// once the list has warmed up, which makes the kernel a plain streaming read of
+// the [n_query, n_win] scores.  Entries are inserted in column order, so the
+// result (ties included) is identical to topk_merge_kernel.
+constexpr int TKR_WARPS = 8, TKR_U = 8;
+__global__ void __launch_bounds__(TKR_WARPS * 32) topk_merge_reg_kernel(
+    const float* __restrict__ win_score, int64_t ld, int n_query, int n_win,
+    const int32_t* __restrict__ win_ids, int64_t ld_ids, int win_id0, float* best_score,
+    int32_t* best_id, int k) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * TKR_WARPS + (threadIdx.x >> 5);
+  if (q >= n_query) return;  // warp-uniform
+  float sc = lane < k ? best_score[(int64_t)q * k + lane] : -CUDART_INF_F;
+  int32_t id = lane < k ? best_id[(int64_t)q * k + lane] : 0;
+  float thr = __shfl_sync(FULL, sc, k - 1);
+  const float* row = win_score + (int64_t)q * ld;
+  const int32_t* idrow =
+      win_ids != nullptr ? win_ids + (ld_ids == 0 ? (int64_t)0 : (int64_t)q * ld_ids) : nullptr;
+
+  // nv, c are warp-uniform
+  auto insert = [&](float nv, int c) {
+    if (!(nv > thr)) return;  // the list may have tightened since the vote
+    // entries that stay in front: the sorted prefix with score >= nv (ties keep the older entry)
+    const int pos = __popc(__ballot_sync(FULL, lane < k && sc >= nv));
+    const int32_t nid = idrow != nullptr ? __ldg(idrow + c) : win_id0 + c;
+    const float up_s = __shfl_up_sync(FULL, sc, 1);
+    const int32_t up_i = __shfl_up_sync(FULL, id, 1);
+    if (lane > pos) { sc = up_s; id = up_i; }
+    else if (lane == pos) { sc = nv; id = nid; }
+    thr = __shfl_sync(FULL, sc, k - 1);
+  };
+
+  int c0 = 0;
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    constexpr int CH = TKR_U * 128;
+    for (; c0 + CH <= n_win; c0 += CH) {
+      float v[TKR_U][4];
+#pragma unroll
+      for (int u = 0; u < TKR_U; ++u) {
+        const uint4 r = ld_stream(reinterpret_cast<const uint4*>(row + c0 + u * 128) + lane);
+        v[u][0] = __uint_as_float(r.x); v[u][1] = __uint_as_float(r.y);
+        v[u][2] = __uint_as_float(r.z); v[u][3] = __uint_as_float(r.w);
+      }
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int u = 0; u < TKR_U; ++u)
+        m = fmaxf(m, fmaxf(fmaxf(v[u][0], v[u][1]), fmaxf(v[u][2], v[u][3])));
+      if (!__any_sync(FULL, m > thr)) continue;
+#pragma unroll
+      for (int u = 0; u < TKR_U; ++u) {
+        unsigned mj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mj[j] = __ballot_sync(FULL, v[u][j] > thr);
+        unsigned any = mj[0] | mj[1] | mj[2] | mj[3];
+        while (any) {  // lanes in order, then the lane's four columns in order = column order
+          const int src = __ffs(any) - 1;
+          any &= any - 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((mj[j] >> src) & 1u)
+              insert(__shfl_sync(FULL, v[u][j], src), c0 + u * 128 + src * 4 + j);
+        }
+      }
+    }
+  }
+  for (; c0 < n_win; c0 += 32) {  // tail of the window / rows that are not 16-byte aligned
+    const int c = c0 + lane;
+    const float v = c < n_win ? row[c] : -CUDART_INF_F;
+    unsigned pending = __ballot_sync(FULL, v > thr);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      insert(__shfl_sync(FULL, v, src), c0 + src);
+    }
+  }
+  if (lane < k) {
+    best_score[(int64_t)q * k + lane] = sc;
+    best_id[(int64_t)q * k + lane] = id;
+  }
+}
+
 // Final merge of the per-shard best lists (bess.py:866-891): discard padding
 // rows of each scoring shard (score += bad where idx >= shard_counts[j]), map
 // local ids to global ids and select the k best of the n * kb entries.  Order:
@@ -633,8 +719,14 @@ extern "C" int bess_topk_merge(const float* win_score, int64_t ld, int n_query, 
                                float* best_score, int32_t* best_id, int k, void* stream) {
   if (n_query == 0 || n_win == 0) return BESS_OK;
   BESS_CHECK_ARG(k >= 1 && k <= TK_MAXK, "k=%d out of range (max %d)", k, TK_MAXK);
-  topk_merge_kernel<<<ceil_div(n_query, 4), 128, 0, (cudaStream_t)stream>>>(
-      win_score, ld, n_query, n_win, win_ids, ld_ids, win_id0, best_score, best_id, k);
+  // BESS_TOPK_MERGE_V1=1 forces the shared-memory list kernel (A/B switch)
+  static const bool force_v1 = [] { const char* e = getenv("BESS_TOPK_MERGE_V1"); return e && e[0] == '1'; }();
+  if (k <= 32 && !force_v1)
+    topk_merge_reg_kernel<<<ceil_div(n_query, TKR_WARPS), TKR_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        win_score, ld, n_query, n_win, win_ids, ld_ids, win_id0, best_score, best_id, k);
+  else
+    topk_merge_kernel<<<ceil_div(n_query, 4), 128, 0, (cudaStream_t)stream>>>(
+        win_score, ld, n_query, n_win, win_ids, ld_ids, win_id0, best_score, best_id, k);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

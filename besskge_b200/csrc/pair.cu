@@ -14,6 +14,8 @@
 // The DOT / L2 cases also have a tcgen05 tensor-core implementation
 // (gemm_tc.cu); this file is the exact-fp32 CUDA-core path and the only path
 // for L1 / PairRE / BoxE.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "families.cuh"
 
@@ -578,6 +580,108 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pertriple_fwd_kernel(PerArgs a,
   }
 }
 
+// Same computation for rows of up to 1024 elements that allow 128-bit loads
+// (every BASELINE shape: RotatE d=512 -> 1024, PairRE d=512 -> 512): a warp
+// pulls its WHOLE candidate row into registers with PT_U independent streaming
+// 128-bit loads per lane (4 KB in flight per warp for fp32), so the kernel is a
+// pure HBM stream of randomly placed rows; PairRE's row norm comes from the
+// registers instead of a second pass over the row, and the query vectors are
+// read from shared memory as 128-bit words (conflict-free) when the BoxE
+// rotation keeps a lane's elements contiguous.
+template <int OP, int P, typename CT>
+__global__ void __launch_bounds__(PT_WARPS * 32) pertriple_fwd_row_kernel(PerArgs a, int64_t q_stride) {
+  constexpr int NV = OpTraits<OP>::NV;
+  constexpr int NSEG = OpTraits<OP>::NSEG;
+  constexpr int V = Elem<CT>::kVec;
+  constexpr int PT_U = 1024 / (32 * V);  // row chunks per lane: 8 (fp32) / 4 (halves)
+  extern __shared__ __align__(16) float sq[];  // [NV][W]
+  const int q = blockIdx.x;
+  const int W = a.W;
+  for (int i = threadIdx.x; i < NV * W; i += blockDim.x) sq[i] = a.qv[(int64_t)q * NV * W + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int qpos = map_row(a.score_map, q);
+  const int64_t orow = (int64_t)qpos * a.ld + a.col0;
+  const int inv_rot = a.rot == 0 ? 0 : W - a.rot;  // coordinate of element e is (e + inv_rot) % W
+  const bool sq_vec = (inv_rot % V) == 0 && (W & 3) == 0;
+
+  for (int c = w; c < a.n_per; c += PT_WARPS) {
+    int lr = map_row(a.cand.map, c) + (int)(qpos * q_stride);
+    if (a.cand.idx != nullptr) lr = __ldg(a.cand.idx + lr);
+    const CT* row = static_cast<const CT*>(a.cand.base) + (int64_t)lr * a.cand.pitch;
+    uint4 raw[PT_U];
+#pragma unroll
+    for (int u = 0; u < PT_U; ++u) {
+      const int e = (u * 32 + lane) * V;
+      raw[u] = e < W ? ld_stream(reinterpret_cast<const uint4*>(row + e)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float vals[PT_U][V];
+#pragma unroll
+    for (int u = 0; u < PT_U; ++u) Elem<CT>::unpack(raw[u], vals[u]);
+    float scale = 1.f;
+    if (OP == OP_PAIRRE && a.normalize) {
+      float n2 = 0.f;
+#pragma unroll
+      for (int u = 0; u < PT_U; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) n2 += vals[u][i] * vals[u][i];  // chunks beyond W are zero
+      scale = 1.f / fmaxf(sqrtf(warp_sum(n2)), 1e-12f);
+    }
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int u = 0; u < PT_U; ++u) {
+      const int e0 = (u * 32 + lane) * V;
+      if (e0 < W) {
+        int k0 = e0 + inv_rot;
+        if (k0 >= W) k0 -= W;
+        float qa[NV][V];
+        if (sq_vec) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int i = 0; i < V; i += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(&sq[v * W + k0 + i]);
+              qa[v][i] = t.x; qa[v][i + 1] = t.y; qa[v][i + 2] = t.z; qa[v][i + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              int k = k0 + i;
+              if (k >= W) k -= W;
+              qa[v][i] = sq[v * W + k];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float t = pair_elem<OP>(P, a.apply_tanh, qa[0][i], NV > 1 ? qa[NV > 1 ? 1 : 0][i] : 0.f,
+                                        NV > 2 ? qa[NV > 2 ? 2 : 0][i] : 0.f, vals[u][i] * scale);
+          if (NSEG == 2) {
+            int k = k0 + i;
+            if (k >= W) k -= W;
+            if (k >= W / 2) acc1 += t; else acc0 += t;
+          } else {
+            acc0 += t;
+          }
+        }
+      }
+    }
+    acc0 = warp_sum(acc0);
+    if (NSEG == 2) acc1 = warp_sum(acc1);
+    if (lane == 0) {
+      float s;
+      if (OP == OP_DOT) s = acc0;
+      else if (NSEG == 2) {
+        const float n0 = nfin(P, acc0);
+        s = -(n0 + nfin(P, acc1));
+        if (a.aux != nullptr) a.aux[orow + c] = n0;
+      } else s = -nfin(P, acc0);
+      a.out[orow + c] = s;
+    }
+  }
+}
+
 template <int OP, int P, typename CT>
 __global__ void __launch_bounds__(PT_WARPS * 32) pertriple_bwd_kernel(PerArgs a, int64_t q_stride) {
   constexpr int NV = OpTraits<OP>::NV;
@@ -817,8 +921,16 @@ extern "C" int bess_score_pertriple_fwd(const bess_score_cfg_t* cfg, int dtype, 
   a.out = out; a.aux = aux;
   const size_t smem = (size_t)pair_nvec(f) * a.W * sizeof(float);
   BESS_CHECK_ARG(smem <= 48 * 1024, "row too wide for the per-triple kernel");
-  PAIR_DISPATCH(op, f.norm_p, dtype,
-                pertriple_fwd_kernel<OP, P, CT><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride));
+  // whole-row-in-registers variant: 128-bit loads possible and the row has <= 1024 elements
+  static const bool force_v1 = [] { const char* e = getenv("BESS_PERTRIPLE_V1"); return e && e[0] == '1'; }();
+  const int vec_elems = dtype == BESS_F32 ? 4 : 8;
+  const bool row_regs = !force_v1 && a.vec_ok && a.W % vec_elems == 0 && a.W <= 1024;
+  PAIR_DISPATCH(op, f.norm_p, dtype, {
+    if (row_regs)
+      pertriple_fwd_row_kernel<OP, P, CT><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
+    else
+      pertriple_fwd_kernel<OP, P, CT><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
+  });
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

@@ -149,6 +149,15 @@ def split_operand(src_dt: int, src: Rows, n_rows: int, width: int,
          ld, ptr(hi_t), ptr(lo_t), ld_t, torch.cuda.current_stream(device).cuda_stream)
 
 
+def table_operand_refresh(table: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, ld: int,
+                          state: torch.Tensor, force: bool) -> None:
+    """fp32 table [rows, W] -> cached hi / lo operand arrays, rebuilt only when the table's
+    bytes changed (device-side checksum compare); see bess_table_operand_refresh."""
+    require_cuda(table, hi, lo, state)
+    call("bess_table_operand_refresh", table.data_ptr(), table.shape[0], table.shape[1],
+         table.stride(0), hi.data_ptr(), lo.data_ptr(), ld, state.data_ptr(), int(force), _st(table))
+
+
 def dot_gemm(dt: int, a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], lda: int,
              b_hi: torch.Tensor, b_lo: Optional[torch.Tensor], ldb: int, m: int, n: int, k: int,
              out: torch.Tensor, out_map: RowMap, ld_out: int, col0: int, accumulate: bool,

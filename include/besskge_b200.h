@@ -202,6 +202,16 @@ int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, in
 int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,
                        const float* row_scale, int out_dtype, void* hi, void* lo, int64_t ld,
                        void* hiT, void* loT, int64_t ldT, void* stream);
+/* Cached 3xTF32 operands of a whole fp32 table for inference (TopKQueryBessKGE scores
+ * every window of a constant shard on every call, bess.py:771-853): streams the
+ * table once to form a 64-bit position-dependent checksum, compares it ON THE
+ * DEVICE with the one kept in state[1] and re-builds hi = rna_tf32(x) /
+ * lo = rna_tf32(x - hi) [n_rows, ld] only when the bytes changed or force != 0.
+ * state: 4 x uint64 owned by the caller, zero-initialised; after the call
+ * state[3] == 1 iff the operands were rebuilt.  Stream-ordered, no host sync. */
+int bess_table_operand_refresh(const float* table, int64_t n_rows, int width, int64_t pitch,
+                               float* hi, float* lo, int64_t ld, uint64_t* state, int force,
+                               void* stream);
 
 /* ------------------------------------------ per-triple negative scoring ---
  * negative_sample_sharing == False: reduce_embedding(v1.unsqueeze(1) - v2)

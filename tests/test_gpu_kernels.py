@@ -260,3 +260,99 @@ def test_loss_kernel_vs_oracle_long_rows(kind, n_neg):
     assert_close(row_loss.sum().cpu(), want.detach(), rtol=1e-5, atol=1e-5)
     assert_close(grad.cpu(), negr.grad, rtol=2e-5, atol=1e-7)
     assert_close(d_pos.cpu(), posr.grad, rtol=2e-5, atol=1e-7)
+
+
+def _merge_reference(win, ids, best_s, best_i):
+    """stable descending merge: current list first, then window columns in order"""
+    k = best_s.shape[1]
+    cat_s = torch.cat([best_s, win], dim=1)
+    cat_i = torch.cat([best_i, ids], dim=1)
+    order = torch.sort(cat_s, dim=1, descending=True, stable=True).indices[:, :k]
+    return torch.gather(cat_s, 1, order), torch.gather(cat_i, 1, order)
+
+
+@pytest.mark.parametrize("k", [1, 11, 32, 33, 64])
+@pytest.mark.parametrize("n_win,ld,off", [(4096, 4096, 0), (1024, 1032, 0), (1500, 1504, 0),
+                                          (777, 777, 0), (2048, 2052, 1), (5, 8, 0)])
+@pytest.mark.parametrize("id_mode", ["base", "shared", "per_query"])
+def test_topk_merge_stable_with_ties(k, n_win, ld, off, id_mode):
+    """bess_topk_merge (register-list kernel for k <= 32, shared-memory list above) ==
+    stable sort of cat([current list, window]); quantised scores force ties"""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(k * 7919 + n_win)
+    nq = 37
+    buf = torch.full((nq * ld + off,), float("nan"))
+    win = (torch.randn(nq, n_win, generator=g) * 4).round() / 4  # heavy ties
+    view = buf[off:].view(nq, ld)
+    view[:, :n_win] = win
+    buf = buf.cuda()
+    best_s = torch.full((nq, k), -50000.0)
+    best_i = torch.full((nq, k), 123456, dtype=torch.int32)
+    want_s, want_i = best_s.clone(), best_i.clone()
+    best_s, best_i = best_s.cuda(), best_i.cuda()
+    for rnd in range(3):  # three windows folded into the same running list
+        if id_mode == "base":
+            ids_dev, ld_ids, id0 = None, 0, 1000 * rnd
+            ids = (torch.arange(n_win, dtype=torch.int32) + id0).expand(nq, n_win)
+        elif id_mode == "shared":
+            row = torch.randint(1 << 20, (n_win,), generator=g, dtype=torch.int32)
+            ids_dev, ld_ids, id0 = row.cuda(), 0, 0
+            ids = row.expand(nq, n_win)
+        else:
+            ids = torch.randint(1 << 20, (nq, n_win), generator=g, dtype=torch.int32)
+            ids_dev, ld_ids, id0 = ids.cuda(), n_win, 0
+        K.topk_merge(buf[off:], ld, nq, n_win, ids_dev, ld_ids, id0, best_s, best_i, k)
+        torch.cuda.synchronize()
+        want_s, want_i = _merge_reference(win, ids, want_s, want_i)
+        assert torch.equal(best_s.cpu(), want_s), f"round {rnd}"
+        assert torch.equal(best_i.cpu(), want_i), f"round {rnd}"
+        win = (torch.randn(nq, n_win, generator=g) * 4).round() / 4 + 0.5 * rnd
+        view = torch.full((nq * ld + off,), float("nan"))
+        view[off:].view(nq, ld)[:, :n_win] = win
+        buf = view.cuda()
+
+
+@pytest.mark.parametrize("rows,W", [(1, 4), (1000, 512), (4099, 260)])
+def test_table_operand_cache_rebuilds_only_on_change(rows, W):
+    """bess_table_operand_refresh: hi / lo == bess_split_operand; the device-side checksum gates
+    the rebuild (an untouched table leaves poisoned outputs alone, a one-word change rebuilds)"""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(rows)
+    table = torch.randn(rows, W, generator=g).cuda()
+    ld = (W + 7) // 8 * 8
+    hi = torch.zeros(rows, ld, device="cuda")
+    lo = torch.zeros(rows, ld, device="cuda")
+    state = torch.zeros(4, dtype=torch.int64, device="cuda")
+    want_hi, want_lo = torch.zeros_like(hi), torch.zeros_like(lo)
+
+    def expect():
+        K.split_operand(L.F32, L.rows(table), rows, W, None, L.F32, want_hi, want_lo, ld, None, None,
+                        0, table.device)
+
+    K.table_operand_refresh(table, hi, lo, ld, state, True)
+    expect()
+    torch.cuda.synchronize()
+    assert int(state[3]) == 1
+    assert torch.equal(hi[:, :W], want_hi[:, :W]) and torch.equal(lo[:, :W], want_lo[:, :W])
+    # products are fp32-grade: hi + lo reproduces x to ~2^-22 relative
+    assert_close(hi[:, :W] + lo[:, :W], table, rtol=2.0 ** -21, atol=0)
+    digest = int(state[1])
+    hi.fill_(7.0)
+    K.table_operand_refresh(table, hi, lo, ld, state, False)
+    torch.cuda.synchronize()
+    assert int(state[3]) == 0 and int(state[1]) == digest and int(state[0]) == 0 and int(state[2]) == 0
+    assert bool((hi == 7.0).all())  # not rebuilt
+    flat = table.view(-1)
+    flat[flat.numel() // 2] += 1.0  # one word changes
+    K.table_operand_refresh(table, hi, lo, ld, state, False)
+    expect()
+    torch.cuda.synchronize()
+    assert int(state[3]) == 1 and int(state[1]) != digest
+    assert torch.equal(hi[:, :W], want_hi[:, :W]) and torch.equal(lo[:, :W], want_lo[:, :W])
+    # swapping two different words is a change too (position-dependent checksum)
+    if flat.numel() > 2 and float(flat[0]) != float(flat[1]):
+        a, b = float(flat[0]), float(flat[1])
+        flat[0], flat[1] = b, a
+        K.table_operand_refresh(table, hi, lo, ld, state, False)
+        torch.cuda.synchronize()
+        assert int(state[3]) == 1
