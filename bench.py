@@ -37,6 +37,11 @@ WORKLOADS = {
     # BASELINE.json configs[2]: top-10 tail prediction against ALL entities (inference);
     # metric = queries/s; shard_bs = queries per GPU per step; "negatives" unused
     "yago-complex-d256-topk": ("yago3-10", "ComplEx", 256, 2, "fp32", 2048, 0),
+    # BASELINE.json configs[4]: score-moving inference against 500 triple-specific candidate
+    # tails (TripleBasedShardedNegativeSampler, negatives scored where they are stored);
+    # metric = queries/s + gather GB/s; shard_bs = queries per GPU per step
+    "wikikg2-rotate-d512-scoremoving": ("ogbl-wikikg2", "RotatE", 512, 1, "fp32", 2048, 500),
+    "wikikg2-pairre-d512-scoremoving": ("ogbl-wikikg2", "PairRE", 512, 1, "fp32", 2048, 500),
 }
 DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 
@@ -425,12 +430,143 @@ def run_topk(args) -> None:
         torch.distributed.destroy_process_group()
 
 
+def run_scoremoving(args) -> None:
+    """configs[4]: ScoreMovingBessKGE, RotatE / PairRE d=512 fp32 (entity rows 1024 / 512 wide),
+    500 candidate tails per query split by owning shard (TripleBasedShardedNegativeSampler),
+    ranks -> MRR / Hits@10.  The dominant kernel is the fused gather + score stream over the
+    candidate rows (pertriple_fwd): Q * Nn rows of W * 4 bytes read in place from the shard."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import besskge_b200  # noqa: F401
+    from besskge_b200 import _lib as L_, kernels as K, scoring
+    from besskge_b200.batch_sampler import RigidShardedBatchSampler
+    from besskge_b200.bess import ScoreMovingBessKGE
+    from besskge_b200.dataset import synthetic_kg
+    from besskge_b200.metric import Evaluation
+    from besskge_b200.negative_sampler import TripleBasedShardedNegativeSampler
+    from besskge_b200.sharding import PartitionedTripleSet, Sharding
+
+    pk = peaks()
+    shape, fam, d, p, dt, sbs, n_cand = WORKLOADS[args.workload]
+    S = args.shard_bs or sbs
+    n = world
+    total = args.warmup + args.steps
+    n_query = n * S * total
+    ds = synthetic_kg(shape, seed=1234, n_triple=n_query)
+    ds.neg_tails = {"train": np.random.default_rng(4321).integers(
+        ds.n_entity, size=(n_query, args.negatives or n_cand), dtype=np.int32)}
+    sh = Sharding.create(ds.n_entity, n, seed=1234)
+    pts = PartitionedTripleSet.create_from_dataset(ds, "train", sh)
+    ns = TripleBasedShardedNegativeSampler(pts.neg_heads, pts.neg_tails, sh, "t", 1234)
+    bs = RigidShardedBatchSampler(pts, ns, shard_bs=S, batches_per_step=1, seed=1234)
+    torch.manual_seed(1234)
+    sf = getattr(scoring, fam)(False, p, sh, ds.n_relation_type, d)
+    sf = sf.to(device=dev, dtype=DTYPES[dt])
+    ev = Evaluation(["mrr", "hits@10"], reduction="sum")
+    model = ScoreMovingBessKGE(ns, sf, evaluation=ev)
+    size = bs.partition_sample_size
+    span = len(bs)
+    batches = []
+    for i in range(total):
+        idx = [(i * size + j) % span for j in range(size)]
+        batches.append({k: v.flatten(end_dim=1).pin_memory() for k, v in bs[idx].items()})
+    Nn = int(ns.padded_shard_length)
+    W = sf.entity_embedding.shape[-1]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(read_back: bool):
+        for i in range(args.warmup):
+            model(**batches[i])
+        barrier()
+        c0 = L_.call("bess_launch_count")
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        d2h = 0
+        for i in range(args.warmup, total):
+            out = model(**batches[i])
+            if read_back:
+                m = out["metrics"].cpu()
+                d2h = m.numel() * m.element_size()
+        en.record()
+        barrier()
+        t = torch.tensor([st.elapsed_time(en) * 1e-3], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()), d2h, L_.call("bess_launch_count") - c0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_dev, _, launches = timed(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t_e2e, d2h, _ = timed(True)
+    if rank == 0:
+        # dominant kernel alone: the fused gather + score stream of one step on this GPU
+        cfg = sf.kernel_cfg()
+        dtc = L_.dtype_code(sf.entity_embedding.dtype)
+        nvec = K.call("bess_query_nvec", L_.C.byref(cfg))
+        local = 1 if world > 1 else n
+        Q = n * S  # every query of every shard is scored against this shard's candidates
+        table = sf.entity_embedding.data[0]
+        g = torch.Generator().manual_seed(0)
+        idx = torch.randint(int(sh.shard_counts.min()), (Q * Nn,), generator=g, dtype=torch.int32).to(dev)
+        qv = torch.randn(Q, nvec, W, device=dev)
+        sc = torch.empty(Q, Nn, device=dev)
+        t_k = time_kernel(lambda: K.pertriple_fwd(cfg, dtc, L_.MODE_TAILS, qv, Q, L_.rows(table, idx=idx),
+                                                  Nn, Nn, sc, L_.IDENT, Nn, 0, None))
+        es = table.element_size()
+        kbytes = Q * Nn * (W * es + 4) + Q * Nn * 4 + Q * nvec * W * 4
+        h2d = sum(v.numel() * v.element_size() for v in batches[0].values()) // (n if world > 1 else 1)
+        queries = n * S * args.steps
+        line = {
+            "metric": "scoremoving_queries_per_sec", "value": queries / t_dev, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32"}.get(dt, dt), "data": "synthetic",
+            "config": {"workload": args.workload, "dataset_shape": shape, "n_entity": ds.n_entity,
+                       "n_shard": n, "queries_per_gpu_per_step": S, "candidates_per_query": n_cand,
+                       "padded_candidates_per_shard": Nn, "score_fn": fam, "embedding_size": d,
+                       "entity_row_bytes": W * es, "negative_sample_sharing": False,
+                       "l2": f"no flush: one step streams {kbytes * local / 1e6:.0f} MB of randomly "
+                             "placed candidate rows per GPU (> 126 MB L2)"},
+            "e2e": {"value": queries / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "pertriple_fwd_row_kernel (fused gather + score of per-query candidates)",
+                         "bound": "hbm", "achieved": kbytes / t_k / 1e9, "peak": pk["hbm"],
+                         "unit": "GB/s", "traffic": None, "frac": kbytes / t_k / 1e9 / pk["hbm"],
+                         "launch_us": t_k * 1e6, "rows_per_launch": Q * Nn,
+                         "step_share": t_k * local / (t_dev / args.steps),
+                         "peak_source": pk["source"]},
+            "cpu_baseline": None,
+        }
+        emit(line)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main() -> None:
     global _REAL_STDOUT
     args = parse()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
+    if args.workload.endswith("-scoremoving"):
+        if args.impl == "reference":
+            emit({"impl": "reference", "unavailable": "the reference arm is defined on the training "
+                                                      "workloads (configs[1]); run without --workload"})
+            return
+        run_scoremoving(args)
+        return
     if args.workload.endswith("-topk"):
         if args.impl == "reference":
             emit({"impl": "reference", "unavailable": "the reference arm is defined on the training "

@@ -100,6 +100,9 @@ SIGNATURES = {
     "bess_relation_grad_reduce": [_P, _I, _P, _P, _I, _I, _P, _P],
     "bess_topk_merge": [_P, _L, _I, _I, _P, _L, _I, _P, _P, _I, _P],
     "bess_topk_finalize": [_P, _P, _I, _I, _I, _P, _P, _I, _I, _F, _P, _P, _P],
+    "bess_select_scores": [_P, _L, _P, _I, _P, _I, _F, _P, _L, _P],
+    "bess_pairs_get": [_P, _L, _P, _P, _I, _P, _P],
+    "bess_pairs_set": [_P, _L, _P, _P, _I, _P, _F, _P],
     "bess_peer_signal": [_P, C.POINTER(_P), _I, _I, _P],
     "bess_peer_wait": [_P, _P, _I, _P],
     "bess_peer_push": [_P, _L, C.POINTER(_P), _I, _L, _P],

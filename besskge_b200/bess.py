@@ -1520,3 +1520,202 @@ class TopKQueryBessKGE(torch.nn.Module):
         if "metrics" in acc:
             out["metrics"] = torch.cat(acc["metrics"], dim=0)
         return out
+
+
+class AllScoresBESS(torch.nn.Module):
+    """Scores of (h, r, ?) / (?, r, t) queries against the entities of every
+    shard, returned in blocks (reference: bess.py:924-1062).  Queries are
+    replicated (AllGather), scored on the shard that stores the candidates and
+    the scores travel back to the shard that owns the query (AllToAll).
+
+    `forward(step, relation, head|tail)` is the reference call: block `step` of
+    `window_size` local entities per shard, result `[L * S, n_shard * window_size]`
+    (column `j * window_size + l` = entity `min(step * window_size + l, Es - 1)`
+    of shard j; the clamp repeats the last entity in the final block exactly as
+    bess.py:1030-1036 does).  `score_all` is the B200 form the pipeline uses:
+    every local entity of every shard in one pass through the tcgen05 GEMM
+    (DistMult / ComplEx) or the tile scorers, `[L * S, n_shard * Es]`.
+    Inference only."""
+
+    device_window = 4096
+
+    def __init__(self, candidate_sampler: PlaceholderNegativeSampler,
+                 score_fn: BaseScoreFunction, window_size: int = 1000) -> None:
+        super().__init__()
+        self.sharding = score_fn.sharding
+        self.score_fn = score_fn
+        self.negative_sampler = candidate_sampler
+        self.window_size = window_size
+        if not score_fn.negative_sample_sharing:
+            raise ValueError("AllScoresBESS requires using negative sample sharing")
+        if self.negative_sampler.corruption_scheme not in ["h", "t"]:
+            raise ValueError("AllScoresBESS only support 'h', 't' corruption scheme")
+        if not isinstance(self.negative_sampler, PlaceholderNegativeSampler):
+            raise ValueError(
+                "AllScoresBESS requires a `PlaceholderNegativeSampler` candidate_sampler"
+            )
+        self.entity_embedding = self.score_fn.entity_embedding
+        self.entity_embedding_size: int = self.entity_embedding.shape[-1]
+        self.candidate = torch.arange(self.window_size, dtype=torch.int32)
+        self.n_step = int(np.ceil(self.sharding.max_entity_per_shard / self.window_size))
+        # the windowed scorer (query replication, prologue, GEMM / tile kernels, cached
+        # table operands) is the one TopKQueryBessKGE runs; only the reduction differs
+        self._engine = TopKQueryBessKGE(1, candidate_sampler, score_fn, None, False, window_size)
+
+    def _queries(self, relation: torch.Tensor, head: Optional[torch.Tensor],
+                 tail: Optional[torch.Tensor]):
+        scheme = self.negative_sampler.corruption_scheme
+        fixed = head if scheme == "t" else tail
+        if fixed is None:
+            raise ValueError("queries need the known entity: head for 't', tail for 'h'")
+        L_rows, S = relation.shape[0], relation.shape[-1]
+        n = self.sharding.n_shard
+        if L_rows % n != 0:
+            raise ValueError(f"leading axis {L_rows} is not a multiple of n_shard={n}")
+        return fixed.reshape(L_rows, S), relation.reshape(L_rows, S), L_rows, S
+
+    def _score(self, relation: torch.Tensor, fixed_h: torch.Tensor, L_rows: int, S: int,
+               windows: List[Tuple[int, int]], clamp_to: int) -> torch.Tensor:
+        """Scores of all queries against local entities [c0, c0 + width) of every shard, for
+        each (c0, width) in `windows`; rows beyond the shard (>= Es) repeat row Es - 1 when
+        `clamp_to` > 0.  Returns [bps * R * S, n * sum(width)] on the device (R = local shards)."""
+        eng = self._engine
+        ws, pl = eng._setup()
+        dev = ws.device
+        ent = self.score_fn.entity_embedding.data
+        rel_table = self.score_fn.relation_embedding.data
+        n = self.sharding.n_shard
+        Es, W = ent.shape[1], ent.shape[-1]
+        cfg = self.score_fn.kernel_cfg()
+        tdt = ent.dtype
+        dt = L.dtype_code(tdt)
+        mode = L.MODE_TAILS if self.negative_sampler.corruption_scheme == "t" else L.MODE_HEADS
+        bps = L_rows // n
+        nS = n * S
+        R = pl.n_local
+        total_w = sum(w for _, w in windows)
+
+        def to_dev(t):
+            if pl.distributed:
+                t = t[pl.rank::n]
+            return t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+
+        rel = to_dev(relation)
+        fixed = to_dev(fixed_h)
+        nvec = K.call("bess_query_nvec", L.C.byref(cfg))
+        use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX)
+        need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
+        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        max_w = max(min(self.device_window, w) for _, w in windows)
+        Q = ws.get("as_Q", (nS, W), tdt)
+        rel_all = ws.get("as_rel", (nS,), torch.int32)
+        qv = ws.get("as_qv", (nS, nvec, W), torch.float32)
+        aux = ws.get("as_aux", (nS, _pad8(max_w)), torch.float32) if need_aux else None
+        scale = ws.get("as_scale", (max_w,), torch.float32) if need_scale else None
+        gemm_ws = None
+        if use_tc:
+            gemm_ws = ws.get("gemm_ws", (max(K.dot_gemm_workspace(nS, _pad8(max_w), W) // 4, 1),),
+                             torch.float32)
+        # local mode: scoring shard r writes column block r of every query row directly;
+        # distributed: [n*S, total_w] local scores, AllToAll, transposed copy to [S, n, total_w]
+        ld_out = n * total_w
+        out = torch.empty(bps * R * S, ld_out, dtype=torch.float32, device=dev)
+        if pl.distributed:
+            sc_local = ws.get("as_local", (nS, total_w), torch.float32)
+            sc_recv = ws.get("as_recv", (n, S, total_w), torch.float32)
+
+        for s in range(bps):
+            rows = [s] if pl.distributed else [s * n + r for r in pl.shards]
+            if pl.distributed:
+                mine = ws.get("as_Qmine", (S, W), tdt)
+                K.gather_rows(ent[pl.rank], fixed[rows[0]], mine)
+                torch.distributed.all_gather_into_tensor(Q.view(-1), mine.view(-1))
+                torch.distributed.all_gather_into_tensor(rel_all, rel[rows[0]].contiguous())
+            else:
+                for li, (row, shard) in enumerate(zip(rows, pl.shards)):
+                    K.gather_rows(ent[shard], fixed[row], Q[li * S:(li + 1) * S])
+                    rel_all[li * S:(li + 1) * S].copy_(rel[row])
+            K.prologue_fwd(cfg, dt, mode, L.rows(Q), rel_table, rel_all, L.IDENT, nS, qv)
+            q_op = None
+            if use_tc:
+                q_op = _TcOperand(ws, "asq", nS, W, tdt, False)
+                q_op.fill(L.F32, L.rows(qv.view(nS, W)), dt, None, dev)
+            for li, shard in enumerate(pl.shards):
+                table = ent[shard]
+                if pl.distributed:
+                    dst, ld, base_col = sc_local, total_w, 0
+                else:
+                    dst, ld, base_col = out[s * nS:(s + 1) * nS], ld_out, shard * total_w
+                tab_hi = tab_lo = None
+                tab_ld = 0
+                if use_tc:
+                    if tdt == torch.float32:
+                        tab_hi, tab_lo, tab_ld = eng._table_operand(li, table)
+                    elif table.stride(0) == _pad8(W):
+                        tab_hi, tab_ld = table, table.stride(0)
+                col = base_col
+                for c_start, width in windows:
+                    for c0 in range(c_start, c_start + width, self.device_window):
+                        nc = min(self.device_window, c_start + width - c0)
+                        real = max(0, min(nc, Es - c0))  # columns that are real local rows
+                        if real > 0:
+                            cand = L.rows(table, offset_elems=c0 * table.stride(0))
+                            if use_tc and tab_hi is not None:
+                                K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, tab_hi[c0:c0 + real],
+                                           None if tab_lo is None else tab_lo[c0:c0 + real], tab_ld,
+                                           nS, real, W, dst, L.IDENT, ld, col, False, gemm_ws)
+                            elif use_tc:
+                                c_op = _TcOperand(ws, "asc", real, W, tdt, False)
+                                c_op.fill(dt, cand, dt, None, dev)
+                                K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
+                                           nS, real, W, dst, L.IDENT, ld, col, False, gemm_ws)
+                            else:
+                                sc_ = None
+                                if need_scale:
+                                    sc_ = scale[:real]
+                                    K.cand_inv_norm(dt, cand, real, W, sc_)
+                                K.shared_fwd(cfg, dt, mode, qv, nS, cand, sc_, real, dst, L.IDENT, ld,
+                                             col, aux)
+                        if real < nc:  # clamped tail of the last block: entity Es - 1 again
+                            assert clamp_to > 0
+                            last = dst[:, col + real - 1:col + real] if real > 0 else None
+                            if last is None:
+                                last = self._last_entity_scores(table, Es, cfg, dt, mode, qv, nS, ws,
+                                                                need_scale, aux)
+                            dst[:, col + real:col + nc] = last
+                        col += nc
+            if pl.distributed:
+                torch.distributed.all_to_all_single(sc_recv.view(-1), sc_local.view(-1))
+                out[s * S:(s + 1) * S].view(S, n, total_w).copy_(sc_recv.transpose(0, 1))
+        return out
+
+    def _last_entity_scores(self, table, Es, cfg, dt, mode, qv, nS, ws, need_scale, aux):
+        """[nS, 1] scores against local entity Es - 1 (a block that lies entirely beyond the
+        shard; only reachable when window_size does not divide into the shard evenly)."""
+        cand = L.rows(table, offset_elems=(Es - 1) * table.stride(0))
+        one = ws.get("as_last", (nS, 8), torch.float32)
+        sc_ = None
+        if need_scale:
+            sc_ = ws.get("as_scale1", (1,), torch.float32)
+            K.cand_inv_norm(dt, cand, 1, table.shape[-1], sc_)
+        K.shared_fwd(cfg, dt, mode, qv, nS, cand, sc_, 1, one, L.IDENT, 8, 0, aux)
+        return one[:, 0:1]
+
+    def forward(self, step: torch.Tensor, relation: torch.Tensor,
+                head: Optional[torch.Tensor] = None,
+                tail: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """relation / head / tail [L, S] (L = bps * n_shard); step: the block index (the same
+        for every row, bess.py:984-1062).  Returns [L * S, n_shard * window_size] (this rank's
+        rows in distributed mode)."""
+        fixed, rel, L_rows, S = self._queries(relation, head, tail)
+        i = int(torch.as_tensor(step).reshape(-1)[0])
+        return self._score(rel, fixed, L_rows, S, [(i * self.window_size, self.window_size)],
+                           clamp_to=self.sharding.max_entity_per_shard)
+
+    def score_all(self, relation: torch.Tensor, head: Optional[torch.Tensor] = None,
+                  tail: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Every block at once: [L * S, n_shard * Es], column j * Es + l = local entity l of
+        shard j (padding rows of a shard included; the caller maps columns to global ids)."""
+        fixed, rel, L_rows, S = self._queries(relation, head, tail)
+        Es = self.sharding.max_entity_per_shard
+        return self._score(rel, fixed, L_rows, S, [(0, Es)], clamp_to=0)

@@ -555,6 +555,43 @@ __global__ void topk_finalize_kernel(const float* __restrict__ score, const int3
   }
 }
 
+// ---------------------------------------------------------------------------
+// AllScores post-processing (pipeline.py:227-298): the reference re-orders the
+// [query, n_shard * n_step * window] block scores into global-entity order on the
+// host (np.unique over the scored ids), drops padding queries, writes -inf on
+// non-candidate / filtered completions and reads / restores the ground-truth
+// scores with fancy indexing.  Here these are three small device kernels.
+//   select: out[i, e] = col_idx[e] >= 0 ? src[row_idx[i], col_idx[e]] : fill
+//   pairs_get / pairs_set: v[t] = mat[rows[t], cols[t]] (rows == NULL -> t)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_scores_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                            const int32_t* __restrict__ row_idx,
+                                                            const int32_t* __restrict__ col_idx,
+                                                            int n_cols, float fill,
+                                                            float* __restrict__ out, int64_t ld_out) {
+  const int i = blockIdx.y;
+  const float* srow = src + (int64_t)(row_idx != nullptr ? row_idx[i] : i) * ld_src;
+  float* orow = out + (int64_t)i * ld_out;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < n_cols; e += gridDim.x * 256) {
+    const int32_t c = __ldg(col_idx + e);
+    orow[e] = c >= 0 ? __ldg(srow + c) : fill;
+  }
+}
+__global__ void pairs_get_kernel(const float* __restrict__ mat, int64_t ld,
+                                 const int32_t* __restrict__ rows, const int32_t* __restrict__ cols,
+                                 int n, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  out[t] = mat[(int64_t)(rows != nullptr ? rows[t] : t) * ld + cols[t]];
+}
+__global__ void pairs_set_kernel(float* __restrict__ mat, int64_t ld, const int32_t* __restrict__ rows,
+                                 const int32_t* __restrict__ cols, int n,
+                                 const float* __restrict__ values, float value) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  mat[(int64_t)(rows != nullptr ? rows[t] : t) * ld + cols[t]] = values != nullptr ? values[t] : value;
+}
+
 }  // namespace bess
 
 using namespace bess;
@@ -727,6 +764,34 @@ extern "C" int bess_topk_merge(const float* win_score, int64_t ld, int n_query, 
   else
     topk_merge_kernel<<<ceil_div(n_query, 4), 128, 0, (cudaStream_t)stream>>>(
         win_score, ld, n_query, n_win, win_ids, ld_ids, win_id0, best_score, best_id, k);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_select_scores(const float* src, int64_t ld_src, const int32_t* row_idx, int n_rows,
+                                  const int32_t* col_idx, int n_cols, float fill, float* out,
+                                  int64_t ld_out, void* stream) {
+  if (n_rows == 0 || n_cols == 0) return BESS_OK;
+  BESS_CHECK_ARG(col_idx != nullptr, "bess_select_scores: column map required");
+  BESS_CHECK_ARG(n_rows <= 65535, "bess_select_scores: at most 65535 rows per call (got %d)", n_rows);
+  const int gx = ceil_div(n_cols, 256) < 64 ? ceil_div(n_cols, 256) : 64;
+  select_scores_kernel<<<dim3(gx, n_rows), 256, 0, (cudaStream_t)stream>>>(src, ld_src, row_idx, col_idx,
+                                                                           n_cols, fill, out, ld_out);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+extern "C" int bess_pairs_get(const float* mat, int64_t ld, const int32_t* rows, const int32_t* cols,
+                              int n, float* out, void* stream) {
+  if (n == 0) return BESS_OK;
+  pairs_get_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(mat, ld, rows, cols, n, out);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+extern "C" int bess_pairs_set(float* mat, int64_t ld, const int32_t* rows, const int32_t* cols, int n,
+                              const float* values, float value, void* stream) {
+  if (n == 0) return BESS_OK;
+  pairs_set_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(mat, ld, rows, cols, n, values,
+                                                                        value);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

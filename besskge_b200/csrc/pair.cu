@@ -118,17 +118,29 @@ __global__ void __launch_bounds__(256) pair_fwd_kernel(PairArgs a) {
 #pragma unroll
     for (int j = 0; j < SZ; ++j) tot[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < W; k0 += F_KC) {
-    // ---- query tile: Qs[v][k][q] (transposed so the inner loop reads float4 over q)
-    for (int s = tid; s < NV * F_TQ * (F_KC / 4); s += 256) {
-      const int kv = s % (F_KC / 4);
-      const int q = (s / (F_KC / 4)) % F_TQ;
-      const int v = s / ((F_KC / 4) * F_TQ);
+  // Software pipeline: the K chunk after the one being reduced is already on its way from
+  // global memory into registers (ncu: the un-pipelined loop stalled on long_scoreboard for
+  // 0.87 issue slots per issued instruction with 8 warps / SM).  Lane -> tile row, so the
+  // transposed shared-memory stores are bank-conflict free.
+  constexpr int QL = NV * F_TQ * (F_KC / 4) / 256;  // float4 loads per thread (query tile)
+  constexpr int CL = F_TC * (F_KC / V) / 256;       // 128-bit loads per thread (candidate tile)
+  static_assert(QL * 256 == NV * F_TQ * (F_KC / 4) && CL * 256 == F_TC * (F_KC / V), "tile split");
+  float4 qreg[QL];
+  float creg[CL][V];
+  const bool q_vec = (W & 3) == 0;
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < QL; ++l) {
+      const int s = tid + l * 256;
+      const int q = s % F_TQ;
+      const int kv = (s / F_TQ) % (F_KC / 4);
+      const int v = s / (F_TQ * (F_KC / 4));
       const int k = k0 + kv * 4;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
       if (q0 + q < a.n_query) {
         const float* src = a.qv + (int64_t)(q0 + q) * qv_row + v * W + k;
-        if (k + 4 <= W && (W & 3) == 0) {
+        if (k + 4 <= W && q_vec) {
           val = *reinterpret_cast<const float4*>(src);
         } else {
           if (k + 0 < W) val.x = src[0];
@@ -137,29 +149,53 @@ __global__ void __launch_bounds__(256) pair_fwd_kernel(PairArgs a) {
           if (k + 3 < W) val.w = src[3];
         }
       }
-      Qs[v][kv * 4 + 0][q] = val.x; Qs[v][kv * 4 + 1][q] = val.y;
-      Qs[v][kv * 4 + 2][q] = val.z; Qs[v][kv * 4 + 3][q] = val.w;
+      qreg[l] = val;
     }
-    // ---- candidate tile: Cs[k][c]
-    for (int s = tid; s < F_TC * (F_KC / V); s += 256) {
-      const int kv = s % (F_KC / V);
-      const int c = s / (F_KC / V);
-      float vals[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) vals[i] = 0.f;
+    for (int l = 0; l < CL; ++l) {
+      const int s = tid + l * 256;
+      const int c = s % F_TC;
+      const int kv = s / F_TC;
+#pragma unroll
+      for (int i = 0; i < V; ++i) creg[l][i] = 0.f;
       if (c0 + c < a.n_cand) {
         const CT* row = static_cast<const CT*>(a.cand.base) + src_row(a.cand, c0 + c) * a.cand.pitch;
-        load_cand_vec<CT>(row, k0 + kv * V, W, a.rot, a.vec_ok, vals);
+        load_cand_vec<CT>(row, k0 + kv * V, W, a.rot, a.vec_ok, creg[l]);
         if (OP == OP_PAIRRE && a.cand_scale != nullptr) {
           const float sc = a.cand_scale[c0 + c];
 #pragma unroll
-          for (int i = 0; i < V; ++i) vals[i] *= sc;
+          for (int i = 0; i < V; ++i) creg[l][i] *= sc;
         }
       }
-#pragma unroll
-      for (int i = 0; i < V; ++i) Cs[kv * V + i][c] = vals[i];
     }
-    __syncthreads();
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int l = 0; l < QL; ++l) {
+      const int s = tid + l * 256;
+      const int q = s % F_TQ;
+      const int kv = (s / F_TQ) % (F_KC / 4);
+      const int v = s / (F_TQ * (F_KC / 4));
+      Qs[v][kv * 4 + 0][q] = qreg[l].x; Qs[v][kv * 4 + 1][q] = qreg[l].y;
+      Qs[v][kv * 4 + 2][q] = qreg[l].z; Qs[v][kv * 4 + 3][q] = qreg[l].w;
+    }
+#pragma unroll
+    for (int l = 0; l < CL; ++l) {
+      const int s = tid + l * 256;
+      const int c = s % F_TC;
+      const int kv = s / F_TC;
+#pragma unroll
+      for (int i = 0; i < V; ++i) Cs[kv * V + i][c] = creg[l][i];
+    }
+  };
+
+  load_tiles(0);
+  store_tiles();
+  __syncthreads();
+
+  for (int k0 = 0; k0 < W; k0 += F_KC) {
+    const bool has_next = k0 + F_KC < W;
+    if (has_next) load_tiles(k0 + F_KC);
 
     if (NSEG == 2 && k0 == W / 2) {  // BoxE: first box finished, start the second
 #pragma unroll
@@ -171,7 +207,7 @@ __global__ void __launch_bounds__(256) pair_fwd_kernel(PairArgs a) {
         }
     }
 
-#pragma unroll
+#pragma unroll 4
     for (int k = 0; k < F_KC; ++k) {
       float qf[NV][8], cf[8];
 #pragma unroll
@@ -195,6 +231,10 @@ __global__ void __launch_bounds__(256) pair_fwd_kernel(PairArgs a) {
                                      NV > 2 ? qf[NV > 2 ? 2 : 0][i] : 0.f, cf[j]);
     }
     __syncthreads();
+    if (has_next) {
+      store_tiles();
+      __syncthreads();
+    }
   }
 
   // ---- epilogue
@@ -242,17 +282,21 @@ BESS_D float pair_coef(float g, float score, float aux, int seg) {
 // ---------------------------------------------------------------------------
 constexpr int B_T = 64, B_TK = 64, B_CH = 32, B_GS = B_T + 4;
 
-template <int OP, int P, typename CT>
-__global__ void __launch_bounds__(256) pair_bwd_q_kernel(PairArgs a, float* d_qv) {
+// NT threads own [NT / 4 queries x 64 coordinates]; NT = 128 halves the tile when that fills
+// the 148 SMs more evenly (bwd_q_threads()).
+template <int OP, int P, typename CT, int NT>
+__global__ void __launch_bounds__(NT) pair_bwd_q_kernel(PairArgs a, float* d_qv) {
+  constexpr int BT = NT / 4;       // queries per CTA
+  constexpr int BGS = BT + 4;
   constexpr int NV = OpTraits<OP>::NV;
   constexpr int NSEG = OpTraits<OP>::NSEG;
   constexpr int V = Elem<CT>::kVec;
-  __shared__ __align__(16) float Gs[NSEG][B_CH][B_GS];  // coef[c][q]
+  __shared__ __align__(16) float Gs[NSEG][B_CH][BGS];  // coef[c][q]
   __shared__ __align__(16) float Cs[B_CH][B_TK];        // cand[c][k]
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int q0 = blockIdx.x * B_T, k0 = blockIdx.y * B_TK;
+  const int q0 = blockIdx.x * BT, k0 = blockIdx.y * B_TK;
   const int W = a.W, qv_row = NV * W;
 
   float qr[NV][4][4], acc[NV][4][4];
@@ -275,7 +319,7 @@ __global__ void __launch_bounds__(256) pair_bwd_q_kernel(PairArgs a, float* d_qv
     // coef tile: warp w loads query rows w, w+8, ...; lane = candidate (coalesced)
     {
       const int lane = tid & 31, w = tid >> 5;
-      for (int q = w; q < B_T; q += 8) {
+      for (int q = w; q < BT; q += NT / 32) {
         const int c = c0 + lane;
         float cf0 = 0.f, cf1 = 0.f;
         if (q0 + q < a.n_query && c < a.n_cand) {
@@ -291,7 +335,7 @@ __global__ void __launch_bounds__(256) pair_bwd_q_kernel(PairArgs a, float* d_qv
       }
     }
     // candidate tile
-    for (int s = tid; s < B_CH * (B_TK / V); s += 256) {
+    for (int s = tid; s < B_CH * (B_TK / V); s += NT) {
       const int kv = s % (B_TK / V);
       const int c = s / (B_TK / V);
       float vals[V];
@@ -842,9 +886,20 @@ extern "C" int bess_score_shared_bwd_query(const bess_score_cfg_t* cfg, int dtyp
   if (n_query == 0) return BESS_OK;
   PairArgs a = make_pair_args(f, dtype, rot, qv, n_query, cand, cand_scale, n_cand, score_map, ld, col0);
   a.score = score; a.d_score = d_score; a.aux = const_cast<float*>(aux);
-  dim3 grid(ceil_div(n_query, B_T), ceil_div(a.W, B_TK));
-  PAIR_DISPATCH(op, f.norm_p, dtype,
-                pair_bwd_q_kernel<OP, P, CT><<<grid, 256, 0, (cudaStream_t)stream>>>(a, d_qv));
+  // 64- or 32-query tiles: whichever leaves the busiest SM with less work (every CTA streams all
+  // candidates, so the grid is fixed by the shape and quantises against the 148 SMs)
+  const int kt = ceil_div(a.W, B_TK);
+  const int64_t t64 = (int64_t)ceil_div(n_query, 64) * kt, t32 = (int64_t)ceil_div(n_query, 32) * kt;
+  const int64_t cost64 = 2 * ceil_div(t64, (int64_t)kNumSM), cost32 = ceil_div(t32, (int64_t)kNumSM);
+  if (cost32 < cost64) {
+    dim3 grid(ceil_div(n_query, 32), kt);
+    PAIR_DISPATCH(op, f.norm_p, dtype,
+                  pair_bwd_q_kernel<OP, P, CT, 128><<<grid, 128, 0, (cudaStream_t)stream>>>(a, d_qv));
+  } else {
+    dim3 grid(ceil_div(n_query, 64), kt);
+    PAIR_DISPATCH(op, f.norm_p, dtype,
+                  pair_bwd_q_kernel<OP, P, CT, 256><<<grid, 256, 0, (cudaStream_t)stream>>>(a, d_qv));
+  }
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

@@ -293,6 +293,35 @@ def topk_finalize(score: torch.Tensor, idx: torch.Tensor, n_shard: int, n_query:
          out_score.data_ptr(), out_id.data_ptr(), _st(score))
 
 
+def select_scores(src: torch.Tensor, row_idx: Optional[torch.Tensor], n_rows: int,
+                  col_idx: torch.Tensor, fill: float, out: torch.Tensor) -> None:
+    """out[i, e] = src[row_idx[i], col_idx[e]] (fill where col_idx[e] < 0); see bess_select_scores."""
+    require_cuda(src, col_idx, out)
+    for r0 in range(0, n_rows, 65535):  # grid.y limit
+        nr = min(65535, n_rows - r0)
+        if row_idx is not None:
+            src_ptr, ridx = src.data_ptr(), row_idx.data_ptr() + 4 * r0
+        else:
+            src_ptr, ridx = src.data_ptr() + 4 * r0 * src.stride(0), None
+        call("bess_select_scores", src_ptr, src.stride(0), ridx, nr, col_idx.data_ptr(),
+             col_idx.numel(), float(fill), out.data_ptr() + 4 * r0 * out.stride(0), out.stride(0),
+             _st(src))
+
+
+def pairs_get(mat: torch.Tensor, rows_: Optional[torch.Tensor], cols: torch.Tensor,
+              out: torch.Tensor) -> None:
+    require_cuda(mat, cols, out)
+    call("bess_pairs_get", mat.data_ptr(), mat.stride(0), ptr(rows_), cols.data_ptr(), cols.numel(),
+         out.data_ptr(), _st(mat))
+
+
+def pairs_set(mat: torch.Tensor, rows_: Optional[torch.Tensor], cols: torch.Tensor,
+              values: Optional[torch.Tensor], value: float = 0.0) -> None:
+    require_cuda(mat, cols)
+    call("bess_pairs_set", mat.data_ptr(), mat.stride(0), ptr(rows_), cols.data_ptr(), cols.numel(),
+         ptr(values), float(value), _st(mat))
+
+
 # ------------------------------------------------------ peer exchange -------
 def _ptr_array(ptrs: Sequence[int]):
     return (C.c_void_p * max(len(ptrs), 1))(*[C.c_void_p(p) for p in ptrs])

@@ -325,6 +325,23 @@ int bess_topk_finalize(const float* score, const int32_t* idx, int n_shard, int 
                        int max_entity_per_shard, int k, float bad_score, float* out_score,
                        int32_t* out_id, void* stream);
 
+/* ------------------------------------------------ AllScores post-processing ---
+ * Device forms of the host fancy-indexing in AllScoresPipeline.forward
+ * (pipeline.py:266-298).
+ * bess_select_scores: out[i, e] = col_idx[e] >= 0 ? src[row_idx[i], col_idx[e]] : fill
+ *   for i < n_rows, e < n_cols (row_idx NULL = identity): block-column scores ->
+ *   global-entity order, padding queries dropped, non-candidates filled (-inf).
+ * bess_pairs_get / bess_pairs_set: out[t] = mat[rows[t], cols[t]] and
+ *   mat[rows[t], cols[t]] = values ? values[t] : value (rows NULL = t): ground-truth
+ *   score read / restore, sparse (query, entity) filters. */
+int bess_select_scores(const float* src, int64_t ld_src, const int32_t* row_idx, int n_rows,
+                       const int32_t* col_idx, int n_cols, float fill, float* out, int64_t ld_out,
+                       void* stream);
+int bess_pairs_get(const float* mat, int64_t ld, const int32_t* rows, const int32_t* cols, int n,
+                   float* out, void* stream);
+int bess_pairs_set(float* mat, int64_t ld, const int32_t* rows, const int32_t* cols, int n,
+                   const float* values, float value, void* stream);
+
 /* ------------------------------------------- peer-memory exchange ---------
  * One process per GPU, one entity shard per GPU: the balanced AllToAll of
  * bess.py:348-350 (and its autograd transpose, and the all-reduce of the
