@@ -627,17 +627,23 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pertriple_fwd_kernel(PerArgs a,
 // Same computation for rows of up to 1024 elements that allow 128-bit loads
 // (every BASELINE shape: RotatE d=512 -> 1024, PairRE d=512 -> 512): a warp
 // pulls its WHOLE candidate row into registers with PT_U independent streaming
-// 128-bit loads per lane (4 KB in flight per warp for fp32), so the kernel is a
-// pure HBM stream of randomly placed rows; PairRE's row norm comes from the
+// 128-bit loads per lane, and the loads of the warp's NEXT row (and the index
+// of the one after) are issued before the current row is reduced, so two rows
+// per warp are in flight: the kernel is a pure HBM stream of randomly placed
+// rows (measured before the prefetch: 4 KB rows 6.9 TB/s, 2 KB rows only
+// 3.2 TB/s — too few bytes in flight per SM).  PT_U = ceil(W / (32 * V)) rounded
+// to {1/4, 1/2, 1} of the 1024-element maximum (template parameter F) keeps the
+// register count proportional to the row.  PairRE's row norm comes from the
 // registers instead of a second pass over the row, and the query vectors are
 // read from shared memory as 128-bit words (conflict-free) when the BoxE
 // rotation keeps a lane's elements contiguous.
-template <int OP, int P, typename CT>
+template <int OP, int P, typename CT, int F>
 __global__ void __launch_bounds__(PT_WARPS * 32) pertriple_fwd_row_kernel(PerArgs a, int64_t q_stride) {
   constexpr int NV = OpTraits<OP>::NV;
   constexpr int NSEG = OpTraits<OP>::NSEG;
   constexpr int V = Elem<CT>::kVec;
-  constexpr int PT_U = 1024 / (32 * V);  // row chunks per lane: 8 (fp32) / 4 (halves)
+  constexpr int PT_U = 1024 / (32 * V) / F;  // row chunks per lane
+  static_assert(PT_U >= 1, "row chunk factor");
   extern __shared__ __align__(16) float sq[];  // [NV][W]
   const int q = blockIdx.x;
   const int W = a.W;
@@ -648,17 +654,32 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pertriple_fwd_row_kernel(PerArg
   const int64_t orow = (int64_t)qpos * a.ld + a.col0;
   const int inv_rot = a.rot == 0 ? 0 : W - a.rot;  // coordinate of element e is (e + inv_rot) % W
   const bool sq_vec = (inv_rot % V) == 0 && (W & 3) == 0;
+  const int qbase = (int)(qpos * q_stride);
 
-  for (int c = w; c < a.n_per; c += PT_WARPS) {
-    int lr = map_row(a.cand.map, c) + (int)(qpos * q_stride);
+  auto row_index = [&](int c) -> int {
+    int lr = map_row(a.cand.map, c) + qbase;
     if (a.cand.idx != nullptr) lr = __ldg(a.cand.idx + lr);
+    return lr;
+  };
+  auto load_row = [&](int lr, uint4 (&raw)[PT_U]) {
     const CT* row = static_cast<const CT*>(a.cand.base) + (int64_t)lr * a.cand.pitch;
-    uint4 raw[PT_U];
 #pragma unroll
     for (int u = 0; u < PT_U; ++u) {
       const int e = (u * 32 + lane) * V;
       raw[u] = e < W ? ld_stream(reinterpret_cast<const uint4*>(row + e)) : make_uint4(0u, 0u, 0u, 0u);
     }
+  };
+
+  uint4 raw[PT_U], raw_next[PT_U];
+  int lr_next = 0;  // storage row of candidate c + PT_WARPS (its loads go out one iteration ahead)
+  if (w < a.n_per) load_row(row_index(w), raw);
+  if (w + PT_WARPS < a.n_per) lr_next = row_index(w + PT_WARPS);
+
+  for (int c = w; c < a.n_per; c += PT_WARPS) {
+    const bool has_next = c + PT_WARPS < a.n_per;
+    if (has_next) load_row(lr_next, raw_next);
+    if (c + 2 * PT_WARPS < a.n_per) lr_next = row_index(c + 2 * PT_WARPS);
+
     float vals[PT_U][V];
 #pragma unroll
     for (int u = 0; u < PT_U; ++u) Elem<CT>::unpack(raw[u], vals[u]);
@@ -722,6 +743,10 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pertriple_fwd_row_kernel(PerArg
         if (a.aux != nullptr) a.aux[orow + c] = n0;
       } else s = -nfin(P, acc0);
       a.out[orow + c] = s;
+    }
+    if (has_next) {
+#pragma unroll
+      for (int u = 0; u < PT_U; ++u) raw[u] = raw_next[u];
     }
   }
 }
@@ -980,9 +1005,15 @@ extern "C" int bess_score_pertriple_fwd(const bess_score_cfg_t* cfg, int dtype, 
   static const bool force_v1 = [] { const char* e = getenv("BESS_PERTRIPLE_V1"); return e && e[0] == '1'; }();
   const int vec_elems = dtype == BESS_F32 ? 4 : 8;
   const bool row_regs = !force_v1 && a.vec_ok && a.W % vec_elems == 0 && a.W <= 1024;
+  // row chunk factor: registers for a quarter / half / all of the 1024-element maximum
+  const int fct = a.W <= 256 ? 4 : (a.W <= 512 ? 2 : 1);
   PAIR_DISPATCH(op, f.norm_p, dtype, {
-    if (row_regs)
-      pertriple_fwd_row_kernel<OP, P, CT><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
+    if (row_regs && fct == 4)
+      pertriple_fwd_row_kernel<OP, P, CT, 4><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
+    else if (row_regs && fct == 2)
+      pertriple_fwd_row_kernel<OP, P, CT, 2><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
+    else if (row_regs)
+      pertriple_fwd_row_kernel<OP, P, CT, 1><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
     else
       pertriple_fwd_kernel<OP, P, CT><<<n_query, PT_WARPS * 32, smem, (cudaStream_t)stream>>>(a, cand_q_stride);
   });

@@ -84,6 +84,10 @@ class Evaluation:
                 "`pos_score` and `candidate_score` need to have same size at dimension 0"
             )
         K.require_cuda(pos, candidate_score)
+        # metric.py:151: in place on the caller's tensor, torch defaults for the infinities
+        # (nan -> -inf, +-inf -> +-FLT_MAX) — a positive masked to -inf still outranks -inf
+        # candidates, and AllScoresPipeline returns -FLT_MAX for it
+        pos.nan_to_num_(-torch.inf)
         pos = pos.float().contiguous()
         cand = candidate_score
         if cand.dtype != torch.float32 or cand.stride(-1) != 1:

@@ -262,8 +262,12 @@ def ranks_from_scores(pos: torch.Tensor, cand: torch.Tensor, mode: str,
                       worst_rank_infty: bool) -> torch.Tensor:
     """metric.py:129-183."""
     n_neg = cand.shape[1]
-    pos = torch.nan_to_num(pos.reshape(-1, 1).clone(), nan=-torch.inf) if torch.isnan(pos).any() \
-        else pos.reshape(-1, 1)
+    # metric.py:151 — IN PLACE on (a view of) the caller's tensor, and with torch's defaults for
+    # the infinities: nan -> -inf, but +inf / -inf -> +FLT_MAX / -FLT_MAX.  A positive whose score
+    # was masked to -inf therefore still outranks -inf candidates, and the pipeline (which
+    # restores the true scores afterwards, pipeline.py:296-301) returns -FLT_MAX for it.
+    pos = pos.reshape(-1, 1)
+    pos.nan_to_num_(-torch.inf)
     gt = torch.sum(cand > pos, dim=-1).float()
     ge = torch.sum(cand >= pos, dim=-1).float()
     if mode == "optimistic":
@@ -457,6 +461,38 @@ def topk_forward(cfg: Dict[str, Any], ent: torch.Tensor, rel_table: torch.Tensor
         sc_out.append(top.values)
         ids_out.append(gi[top.indices])
     return torch.stack(ids_out), torch.stack(sc_out)
+
+
+def all_scores_pipeline(cfg: Dict[str, Any], ent_unsharded: torch.Tensor, rel_table: torch.Tensor,
+                        triples: torch.Tensor, scheme: str, filter_triples: Optional[torch.Tensor],
+                        candidate_ents: Optional[np.ndarray], k: int, mode: str = "average"
+                        ) -> Dict[str, torch.Tensor]:
+    """pipeline.py:192-320 restated densely for triples given with GLOBAL ids [x, 3]:
+    scores of every completion against the un-sharded table, -inf on non-candidates
+    (:262-265), true scores read (:266-271), -inf on filtered completions (:272-279,
+    utils.py:36-69), ranks with the true completion masked (:285-292), true scores
+    restored (:296-301), top-k (:304-309).  Row order = order of `triples`."""
+    x = triples.shape[0]
+    gt_col = 0 if scheme == "h" else 2
+    fixed = ent_unsharded[triples[:, 2 - gt_col].long()]
+    sc = score_candidates(cfg, "t" if scheme == "t" else "h", fixed, rel_table, triples[:, 1],
+                          ent_unsharded.unsqueeze(0), True).clone()
+    ar = torch.arange(x)
+    truth = triples[:, gt_col].long()
+    if candidate_ents is not None:
+        drop = np.setdiff1d(np.arange(ent_unsharded.shape[0]), candidate_ents)
+        sc[:, torch.from_numpy(drop)] = -torch.inf
+    true = sc[ar, truth].clone()
+    if filter_triples is not None:
+        ent_col = 0 if scheme == "t" else 2
+        hit = ((filter_triples[:, 1] == triples[:, 1].view(-1, 1))
+               & (filter_triples[:, ent_col] == triples[:, ent_col].view(-1, 1))).nonzero()
+        sc[hit[:, 0], filter_triples[hit[:, 1], 2 - ent_col].long()] = -torch.inf
+    sc[ar, truth] = -torch.inf
+    ranks = ranks_from_scores(true, sc, mode, False)
+    sc[ar, truth] = true
+    top = torch.topk(sc, k=k, dim=1).indices
+    return dict(scores=sc, ranks=ranks, topk_global_id=top, true_scores=true)
 
 
 # =============================================================================

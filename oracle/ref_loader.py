@@ -95,9 +95,55 @@ def _install_stubs() -> None:
         return xs
 
     pt.for_loop = _for_loop
-    pt.Options = object
-    pt.DataLoader = object
     pt.ipuHardwareIsAvailable = lambda num_ipus=1: False
+
+    # --- PopTorch runtime used by pipeline.py:130-144 (inferenceModel over n replicas,
+    # deviceIterations, OutputMode.All, async DataLoader): restated as "run the module once
+    # per (step, replica) on the (1, ...) slice of every input and concatenate the outputs"
+    class _Options:
+        def __init__(self) -> None:
+            self.replication_factor = 1
+            self.device_iterations = 1
+
+        def deviceIterations(self, n: int) -> "_Options":
+            self.device_iterations = int(n)
+            return self
+
+        def outputMode(self, *_a: Any) -> "_Options":
+            return self
+
+        def useIpuModel(self, *_a: Any) -> "_Options":
+            return self
+
+    class _Var:
+        def replicaGrouping(self, *_a: Any) -> None:
+            return None
+
+    class _InferenceModel:
+        def __init__(self, module: torch.nn.Module, options: "_Options") -> None:
+            self.module = module
+            self.options = options
+            self.entity_embedding = _Var()
+
+        def __call__(self, **inp: torch.Tensor) -> Any:
+            n = int(self.options.replication_factor)
+            bps = int(self.options.device_iterations)
+            batch = {k: v.reshape(bps, n, *v.shape[1:]) for k, v in inp.items()}
+            res = run_replicated(self.module, batch, n, bps)
+            return res["__tensor__"] if "__tensor__" in res else res
+
+    def _dataloader(options: Any = None, dataset: Any = None, batch_size: Any = None,
+                    sampler: Any = None, **_kw: Any) -> Any:
+        return torch.utils.data.DataLoader(dataset, batch_size=None, sampler=sampler)
+
+    pt.Options = _Options
+    pt.DataLoader = _dataloader
+    pt.inferenceModel = lambda module, options=None: _InferenceModel(module, options)
+    pt.OutputMode = types.SimpleNamespace(All=0)
+    pt.CommGroupType = types.SimpleNamespace(NoGrouping=0)
+    pt.VariableRetrievalMode = types.SimpleNamespace(OnePerGroup=0)
+    pt.DataLoaderMode = types.SimpleNamespace(Async=0)
+    pt.SharingStrategy = types.SimpleNamespace(SharedMemory=0)
 
     pea = types.ModuleType("poptorch_experimental_addons")
     pea.distance_matrix = lambda a, b, p: _pairwise_distance(a, b, p)
@@ -169,6 +215,7 @@ def load_reference() -> types.SimpleNamespace:
         "metric",
         "scoring",
         "bess",
+        "pipeline",
     ]
     ns = types.SimpleNamespace()
     for nm in names:
@@ -220,10 +267,12 @@ def run_replicated(
             for s in range(batches_per_step):
                 i = s * n_shard + r
                 kwargs = {k: v[i : i + 1] for k, v in flat.items()}
-                if "triple_weight" not in kwargs and hasattr(rep, "loss_fn"):
+                if "triple_weight" not in kwargs and getattr(rep, "loss_fn", None) is not None:
                     kwargs["triple_weight"] = torch.tensor([1.0])
                 with torch.set_grad_enabled(grad):
-                    results[s][r] = rep(**kwargs)
+                    res = rep(**kwargs)
+                    # AllScoresBESS.forward returns a bare tensor (bess.py:1062)
+                    results[s][r] = res if isinstance(res, dict) else {"__tensor__": res}
         except BaseException as e:  # pragma: no cover
             errors.append(e)
             if ex.barrier is not None:

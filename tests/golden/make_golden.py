@@ -421,6 +421,80 @@ def golden_topk(ref) -> None:
                  ranks=res["ranks"], metrics=res["metrics"])
 
 
+def golden_pipeline(ref) -> None:
+    """AllScoresPipeline / AllScoresBESS of the unmodified reference (pipeline.py, bess.py:924-1062)
+    under the replica emulation: the parameter grid of the reference's own tests/test_pipeline.py
+    (corruption scheme x filters x candidate subset) at a fixture-sized shape, for ComplEx (GEMM
+    path) and TransE-L1 (tile path).  n_entity is not a multiple of n_shard (padding entities)
+    and window_size does not divide the shard (clamped last block)."""
+    n_entity, n_rel, n_shard, n_triple, bps, shard_bs, d, window, k = 2003, 11, 4, 450, 2, 64, 16, 190, 7
+    sh = ref.sharding.Sharding.create(n_entity, n_shard, seed=SEED)
+    cand_ents = np.arange(0, n_entity - 1, step=3)
+    for fam, p in (("ComplEx", 0), ("TransE", 1)):
+        for scheme in ("t", "h"):
+            for filt, extra_only in ((True, True), (True, False), (False, False)):
+                for use_cand in (True, False):
+                    rng = np.random.default_rng(SEED + 7)
+                    h = rng.choice(n_entity - 1, size=n_triple, replace=False)
+                    t = rng.choice(n_entity - 1, size=n_triple, replace=False)
+                    r = rng.integers(n_rel, size=n_triple)
+                    triples = np.stack([h, r, t], axis=1)
+                    ds = ref.dataset.KGDataset(
+                        n_entity=n_entity, n_relation_type=n_rel, entity_dict=None, relation_dict=None,
+                        type_offsets=None, triples={"test": triples},
+                        original_triple_ids={"test": np.arange(n_triple)})
+                    mode = "h_shard" if scheme == "t" else "t_shard"
+                    pts = ref.sharding.PartitionedTripleSet.create_from_dataset(ds, "test", sh, mode)
+                    gen = torch.Generator().manual_seed(SEED)
+                    W = FAMILIES[fam]["ew"] * d
+                    ent = torch.randn(n_entity, W, generator=gen)
+                    rel = torch.randn(n_rel, FAMILIES[fam]["rw"](d), generator=gen)
+                    sf = build_score_fn(ref, fam, True, p, sh, n_rel, d, ent, rel)
+                    ns = ref.negative_sampler.PlaceholderNegativeSampler(corruption_scheme=scheme, seed=SEED)
+                    bs = ref.batch_sampler.RigidShardedBatchSampler(
+                        pts, ns, shard_bs=shard_bs, batches_per_step=bps, seed=SEED,
+                        return_triple_idx=True)
+                    ev = ref.metric.Evaluation(["mrr", "hits@10"], mode="average", reduction="sum",
+                                               return_ranks=True)
+                    gt_col = 0 if scheme == "h" else 2
+                    to_filter = None
+                    if filt:
+                        extra = np.copy(triples)
+                        extra[:, gt_col] += 1
+                        to_filter = [extra] if extra_only else [triples, extra]
+                    pipe = ref.pipeline.AllScoresPipeline(
+                        bs, scheme, sf, ev, filter_triples=to_filter,
+                        candidate_ents=cand_ents if use_cand else None, return_scores=True,
+                        return_topk=True, k=k, window_size=window, use_ipu_model=True)
+                    with torch.no_grad():
+                        out = pipe()
+                        # one raw block of AllScoresBESS (the clamped last one) for the first batch
+                        batch = bs[list(bs.get_dataloader_sampler(shuffle=False))[0]]
+                        for key in ("triple_mask", "triple_idx"):
+                            batch.pop(key)
+                        batch.pop("head" if scheme == "h" else "tail")
+                        last = pipe.bess_module.n_step - 1
+                        step = torch.full((bps, n_shard, 1), last, dtype=torch.int32)
+                        block = ref_loader.run_replicated(
+                            pipe.bess_module, dict(batch, step=step), n_shard, bps)["__tensor__"]
+                    sc = out["scores"]
+                    finite = torch.isfinite(sc)
+                    tag = f"pipeline_{fam}_{scheme}_f{int(filt)}{int(extra_only)}_c{int(use_cand)}"
+                    save(tag, dict(family=fam, p=p, scheme=scheme, d=d, n_rel=n_rel, n_entity=n_entity,
+                                   n_shard=n_shard, n_triple=n_triple, bps=bps, shard_bs=shard_bs,
+                                   window=window, k=k, filter=filt, extra_only=extra_only,
+                                   use_candidates=use_cand, seed=SEED, score_col_stride=61,
+                                   block_row_stride=4, block_col_stride=7),
+                         triples=triples, cand_ents=cand_ents,
+                         # tables are torch.randn(generator seeded SEED): regenerated by the test, pinned here
+                         ent_probe=ent[::97, ::5], rel_probe=rel[:, ::5],
+                         scores_sub=sc[:, ::61], neg_inf_count=(~finite).sum(dim=1),
+                         topk_global_id=out["topk_global_id"], triple_idx=out["triple_idx"],
+                         ranks=out["ranks"], mrr=out["metrics"]["mrr"], hits10=out["metrics"]["hits@10"],
+                         mrr_avg=out["metrics_avg"]["mrr"],
+                         **{f"in_{kk}": v for kk, v in batch.items()}, block_last_sub=block[::4, ::7])
+
+
 def main() -> None:
     ref = ref_loader.load_reference()
     torch.manual_seed(SEED)
@@ -431,6 +505,7 @@ def main() -> None:
     golden_bess(ref)
     golden_train(ref)
     golden_topk(ref)
+    golden_pipeline(ref)
 
 
 if __name__ == "__main__":

@@ -356,3 +356,37 @@ def test_table_operand_cache_rebuilds_only_on_change(rows, W):
         K.table_operand_refresh(table, hi, lo, ld, state, False)
         torch.cuda.synchronize()
         assert int(state[3]) == 1
+
+
+def test_select_and_pairs_kernels():
+    """bess_select_scores / bess_pairs_get / bess_pairs_set == torch fancy indexing (bit-exact)"""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(50, 1203, generator=g)
+    rows = torch.randint(50, (37,), generator=g, dtype=torch.int32)
+    cols = torch.randint(-1, 1203, (2000,), generator=g, dtype=torch.int32)
+    out = torch.zeros(37, 2000 + 8, device="cuda")[:, :2000]  # row pitch != width
+    K.select_scores(src.cuda(), rows.cuda(), 37, cols.cuda(), float("-inf"), out)
+    want = src[rows.long()][:, cols.clamp(min=0).long()]
+    want[:, cols < 0] = float("-inf")
+    assert torch.equal(out.cpu(), want)
+    out2 = torch.zeros(50, 2000, device="cuda")
+    K.select_scores(src.cuda(), None, 50, cols.cuda(), 7.0, out2)
+    want2 = src[:, cols.clamp(min=0).long()]
+    want2[:, cols < 0] = 7.0
+    assert torch.equal(out2.cpu(), want2)
+    mat = src.cuda().clone()
+    pc = torch.randint(1203, (50,), generator=g, dtype=torch.int32)
+    got = torch.empty(50, device="cuda")
+    K.pairs_get(mat, None, pc.cuda(), got)
+    assert torch.equal(got.cpu(), src[torch.arange(50), pc.long()])
+    pr = torch.randint(50, (300,), generator=g, dtype=torch.int32)
+    pc2 = torch.randint(1203, (300,), generator=g, dtype=torch.int32)
+    K.pairs_set(mat, pr.cuda(), pc2.cuda(), None, float("-inf"))
+    ref = src.clone()
+    ref[pr.long(), pc2.long()] = float("-inf")
+    assert torch.equal(mat.cpu(), ref)
+    vals = torch.randn(50, generator=g)
+    K.pairs_set(mat, None, pc.cuda(), vals.cuda())
+    ref[torch.arange(50), pc.long()] = vals
+    assert torch.equal(mat.cpu(), ref)

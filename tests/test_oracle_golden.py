@@ -164,3 +164,28 @@ def test_topk_oracle(name):
     mask = T(g["triple_mask"]).flatten()
     assert_close(torch.cat(scs)[mask], T(g["topk_scores"])[mask], rtol=1e-5, atol=1e-5)
     assert_array_equal(torch.cat(ids)[mask].numpy(), g["topk_global_id"][mask.numpy()])
+
+
+@pytest.mark.parametrize("name", golden_names("pipeline_"))
+def test_all_scores_pipeline_oracle(name):
+    """oracle dense restatement of AllScoresPipeline == the reference pipeline's outputs"""
+    from .pipeline_cases import filter_list, load_case
+    cfg, g, ent, rel = load_case(name)
+    c = score_cfg(cfg["family"], cfg["d"], dict(p=cfg["p"]))
+    sh = O.sharding_create(cfg["n_entity"], cfg["n_shard"], cfg["seed"])
+    mode = "h_shard" if cfg["scheme"] == "t" else "t_shard"
+    _, _, _, order = O.partition_triples(g["triples"], sh, mode)
+    tr = T(g["triples"][order[g["triple_idx"]]])
+    fl = filter_list(cfg, g["triples"])
+    res = O.all_scores_pipeline(c, ent, rel, tr, cfg["scheme"],
+                                None if fl is None else T(np.concatenate(fl, axis=0)),
+                                g["cand_ents"] if cfg["use_candidates"] else None, cfg["k"])
+    want = T(g["scores_sub"])
+    got = res["scores"][:, ::cfg["score_col_stride"]]
+    assert torch.equal(torch.isinf(got), torch.isinf(want))
+    fin = torch.isfinite(want)
+    assert_close(got[fin], want[fin], rtol=1e-5, atol=1e-5)
+    assert_array_equal((~torch.isfinite(res["scores"])).sum(dim=1).numpy(), g["neg_inf_count"])
+    assert_close(res["ranks"], T(g["ranks"]))
+    assert_array_equal(res["topk_global_id"].numpy(), g["topk_global_id"])
+    assert_close((1.0 / res["ranks"]).sum(), T(g["mrr"]), rtol=1e-5, atol=1e-6)
