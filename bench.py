@@ -224,8 +224,22 @@ def kernel_rooflines(model, sf, prob, pk):
         t_score = time_kernel(lambda: K.shared_fwd(cfg, dt, L.MODE_TAILS, qv, S, L.rows(cand), None, N,
                                                    scores, L.IDENT, N, 0, None))
         work = (S * nvec * W * 4) + N * W * es + S * N * 4
+        # the contract's roofline object (HBM bytes) + the roofline that actually binds this kernel:
+        # S*N*W pair elements x 2 FADD on the FP32 pipe (148 SMs x 128 lanes x SM clock), the
+        # algorithmic bytes being only ~17 MB per launch
+        try:
+            sm_ghz = torch.cuda.get_device_properties(dev).clock_rate * 1e-6
+        except AttributeError:
+            sm_ghz = 1.965
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        fp32_peak = n_sm * 128 * sm_ghz * 1e9
+        fp32_ach = 2.0 * S * N * W / t_score
         roof = dict(kernel="pair_fwd_kernel (shared-negative L1 scoring)", bound="hbm",
-                    achieved=work / t_score / 1e9, peak=pk["hbm"], unit="GB/s", traffic=None)
+                    achieved=work / t_score / 1e9, peak=pk["hbm"], unit="GB/s", traffic=None,
+                    note="bytes are negligible here; the binding roofline is fp32_pipe",
+                    fp32_pipe=dict(achieved=fp32_ach / 1e12, peak=fp32_peak / 1e12,
+                                   unit="T lane-instr/s", frac=fp32_ach / fp32_peak,
+                                   work="S*N*W pair elements x 2 FADD"))
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists() and prob["fam"] == "DistMult" and (S, N, W) == (16384, 2048, 256) and es == 4:
         roof["traffic"] = json.loads(tf.read_text()).get("gemm_tc_kernel<TF32X3> fwd S=16384 N=2048 W=256")

@@ -142,6 +142,34 @@ def inference_parity(rank: int, n: int) -> None:
         if rank == 0:
             print(f"distributed TopKQuery == local: {fam} {scheme} n={n}")
 
+    from besskge_b200.bess import AllScoresBESS
+    for fam, p, scheme in [("ComplEx", 2, "t"), ("TransE", 1, "h")]:
+        gen = torch.Generator().manual_seed(31)
+        ew = 2 if fam in ("RotatE", "ComplEx") else 1
+        rw = 2 * d if fam in ("ComplEx", "PairRE") else d
+        ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen)
+        rel = torch.randn(n_rel, rw, generator=gen)
+        q = dict(relation=torch.randint(n_rel, (2 * n, S), generator=gen, dtype=torch.int32))
+        q["head" if scheme == "t" else "tail"] = torch.randint(lo, (2 * n, S), generator=gen,
+                                                                dtype=torch.int32)
+        results = []
+        for force_local in (True, False):
+            bess_mod.FORCE_LOCAL = force_local
+            sf = H.make_score_fn(fam, True, p, sh, n_rel, d, ent, rel)
+            mod = AllScoresBESS(PlaceholderNegativeSampler(scheme), sf, window_size=25)
+            mod.device_window = 16
+            full = mod.score_all(**q)
+            blk = mod(step=torch.full((2 * n, 1), mod.n_step - 1, dtype=torch.int32), **q)
+            torch.cuda.synchronize()
+            results.append((full.cpu(), blk.cpu()))
+        bess_mod.FORCE_LOCAL = False
+        (loc_full, loc_blk), (dis_full, dis_blk) = results
+        rows = torch.cat([torch.arange(S) + (st * n + rank) * S for st in range(2)])
+        torch.testing.assert_close(dis_full, loc_full[rows], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(dis_blk, loc_blk[rows], rtol=1e-6, atol=1e-6)
+        if rank == 0:
+            print(f"distributed AllScoresBESS == local: {fam} {scheme} n={n}")
+
 
 if __name__ == "__main__":
     main()
