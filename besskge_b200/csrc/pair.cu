@@ -110,8 +110,12 @@ __global__ void __launch_bounds__(F_NT) pair_fwd_kernel(PairArgs a) {
   constexpr int NSEG = OpTraits<OP>::NSEG;
   constexpr int V = Elem<CT>::kVec;
   constexpr int TQ = 16 * MR;
-  __shared__ __align__(16) float Qs[NV][F_KC][16][8];  // [v][k][warp][row slot]; slots >= MR unused
-  __shared__ __align__(16) float Cs[F_KC][F_TC];
+  // two stages: the next chunk is stored while other warps still read the current one, so a
+  // chunk costs ONE barrier (ncu on the single-stage version: barrier 0.88 stalls per issue)
+  // (BoxE's three query vectors would exceed the 48 KB static limit: single stage, two barriers)
+  constexpr int NST = NV <= 2 ? 2 : 1;
+  __shared__ __align__(16) float Qs[NST][NV][F_KC][16][8];  // [stage][v][k][warp][row slot]; slots >= MR unused
+  __shared__ __align__(16) float Cs[NST][F_KC][F_TC];
 
   const int tid = threadIdx.x;
   const int tx = tid & 31, ty = tid >> 5;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(F_NT) pair_fwd_kernel(PairArgs a) {
       }
     }
   };
-  auto store_tiles = [&]() {
+  auto store_tiles = [&](int st) {
 #pragma unroll
     for (int l = 0; l < QL; ++l) {
       const int s = tid + l * F_NT;
@@ -188,23 +192,24 @@ __global__ void __launch_bounds__(F_NT) pair_fwd_kernel(PairArgs a) {
         const int kv = (s / TQ) % (F_KC / 4);
         const int v = s / (TQ * (F_KC / 4));
         const int wq = q / MR, slot = q - wq * MR;
-        Qs[v][kv * 4 + 0][wq][slot] = qreg[l].x; Qs[v][kv * 4 + 1][wq][slot] = qreg[l].y;
-        Qs[v][kv * 4 + 2][wq][slot] = qreg[l].z; Qs[v][kv * 4 + 3][wq][slot] = qreg[l].w;
+        Qs[st][v][kv * 4 + 0][wq][slot] = qreg[l].x; Qs[st][v][kv * 4 + 1][wq][slot] = qreg[l].y;
+        Qs[st][v][kv * 4 + 2][wq][slot] = qreg[l].z; Qs[st][v][kv * 4 + 3][wq][slot] = qreg[l].w;
       }
     }
     if (tid < C_LOADS) {
       const int c = tid % F_TC;
       const int kv = tid / F_TC;
 #pragma unroll
-      for (int i = 0; i < V; ++i) Cs[kv * V + i][c] = creg[i];
+      for (int i = 0; i < V; ++i) Cs[st][kv * V + i][c] = creg[i];
     }
   };
 
   load_tiles(0);
-  store_tiles();
+  store_tiles(0);
   __syncthreads();
 
-  for (int k0 = 0; k0 < W; k0 += F_KC) {
+  int st = 0;
+  for (int k0 = 0; k0 < W; k0 += F_KC, st = (st ^ 1) & (NST - 1)) {
     const bool has_next = k0 + F_KC < W;
     if (has_next) load_tiles(k0 + F_KC);
 
@@ -218,19 +223,19 @@ __global__ void __launch_bounds__(F_NT) pair_fwd_kernel(PairArgs a) {
         }
     }
 
-#pragma unroll 4
+#pragma unroll 8
     for (int k = 0; k < F_KC; ++k) {
       float qf[NV][8];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const float4 lo = *reinterpret_cast<const float4*>(&Qs[v][k][ty][0]);
+        const float4 lo = *reinterpret_cast<const float4*>(&Qs[st][v][k][ty][0]);
         qf[v][0] = lo.x; qf[v][1] = lo.y; qf[v][2] = lo.z; qf[v][3] = lo.w;
         if (MR > 4) {
-          const float4 hi = *reinterpret_cast<const float4*>(&Qs[v][k][ty][4]);
+          const float4 hi = *reinterpret_cast<const float4*>(&Qs[st][v][k][ty][4]);
           qf[v][4] = hi.x; qf[v][5] = hi.y; qf[v][6] = hi.z; qf[v][7] = hi.w;
         }
       }
-      const float4 c4 = *reinterpret_cast<const float4*>(&Cs[k][tx * 4]);
+      const float4 c4 = *reinterpret_cast<const float4*>(&Cs[st][k][tx * 4]);
       const float cf[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int i = 0; i < MR; ++i)
@@ -239,10 +244,17 @@ __global__ void __launch_bounds__(F_NT) pair_fwd_kernel(PairArgs a) {
           acc[i][j] += pair_elem<OP>(P, a.apply_tanh, qf[0][i], NV > 1 ? qf[NV > 1 ? 1 : 0][i] : 0.f,
                                      NV > 2 ? qf[NV > 2 ? 2 : 0][i] : 0.f, cf[j]);
     }
-    __syncthreads();
-    if (has_next) {
-      store_tiles();
+    // stage st^1 was last read two chunks ago; every warp has passed the barrier that followed
+    // those reads, so it can be overwritten now; one barrier publishes it for the next chunk
+    if (NST == 2) {
+      if (has_next) store_tiles(st ^ 1);
       __syncthreads();
+    } else {
+      __syncthreads();
+      if (has_next) {
+        store_tiles(0);
+        __syncthreads();
+      }
     }
   }
 
@@ -313,7 +325,8 @@ constexpr int B_T = 64, B_TK = 64, B_CH = 32, B_GS = B_T + 4;
 // NT threads own [NT / 4 queries x 64 coordinates]; NT = 128 halves the tile when that fills
 // the 148 SMs more evenly (bwd_q_threads()).
 template <int OP, int P, typename CT, int NT>
-__global__ void __launch_bounds__(NT) pair_bwd_q_kernel(PairArgs a, float* d_qv) {
+__global__ void __launch_bounds__(NT, OpTraits<OP>::NV == 1 ? (NT == 128 ? 7 : 3) : 1)
+pair_bwd_q_kernel(PairArgs a, float* d_qv) {
   constexpr int BT = NT / 4;       // queries per CTA
   constexpr int BGS = BT + 4;
   constexpr int NV = OpTraits<OP>::NV;
@@ -445,8 +458,8 @@ __global__ void __launch_bounds__(NT) pair_bwd_q_kernel(PairArgs a, float* d_qv)
 // order afterwards -> deterministic).
 // ---------------------------------------------------------------------------
 template <int OP, int P, typename CT>
-__global__ void __launch_bounds__(256) pair_bwd_c_kernel(PairArgs a, float* partial,
-                                                          int q_per_split) {
+__global__ void __launch_bounds__(256, OpTraits<OP>::NV == 1 ? 4 : 1)
+pair_bwd_c_kernel(PairArgs a, float* partial, int q_per_split) {
   constexpr int NV = OpTraits<OP>::NV;
   constexpr int NSEG = OpTraits<OP>::NSEG;
   __shared__ __align__(16) float Gs[NSEG][B_CH][B_T];      // coef[q][c]

@@ -149,6 +149,34 @@ BESS_D const float* grad_row(const GradSrc& g, int pos) {
   return g.dst + ((int64_t)d * g.dst_stride_rows + i) * g.row_elems;
 }
 
+// w[0..3] -= lr * s as ONE 128-bit (fp32) or 64-bit (half) read-modify-write
+template <typename T>
+BESS_D void segment_apply_sgd(T* row, const float4& s, float lr);
+template <>
+BESS_D void segment_apply_sgd<float>(float* row, const float4& s, float lr) {
+  float4 w = *reinterpret_cast<float4*>(row);
+  w.x -= lr * s.x; w.y -= lr * s.y; w.z -= lr * s.z; w.w -= lr * s.w;
+  *reinterpret_cast<float4*>(row) = w;
+}
+template <>
+BESS_D void segment_apply_sgd<__half>(__half* row, const float4& s, float lr) {
+  uint2 raw = *reinterpret_cast<uint2*>(row);
+  __half2* h = reinterpret_cast<__half2*>(&raw);
+  float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  h[0] = __halves2half2(__float2half_rn(a.x - lr * s.x), __float2half_rn(a.y - lr * s.y));
+  h[1] = __halves2half2(__float2half_rn(b.x - lr * s.z), __float2half_rn(b.y - lr * s.w));
+  *reinterpret_cast<uint2*>(row) = raw;
+}
+template <>
+BESS_D void segment_apply_sgd<__nv_bfloat16>(__nv_bfloat16* row, const float4& s, float lr) {
+  uint2 raw = *reinterpret_cast<uint2*>(row);
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  h[0] = __halves2bfloat162(__float2bfloat16_rn(a.x - lr * s.x), __float2bfloat16_rn(a.y - lr * s.y));
+  h[1] = __halves2bfloat162(__float2bfloat16_rn(b.x - lr * s.z), __float2bfloat16_rn(b.y - lr * s.w));
+  *reinterpret_cast<uint2*>(row) = raw;
+}
+
 // MODE 0: SGD update of the table row; MODE 1: store the segment sum
 template <int MODE, typename T>
 __global__ void __launch_bounds__(256) segment_kernel(T* table, int64_t pitch,
@@ -165,20 +193,26 @@ __global__ void __launch_bounds__(256) segment_kernel(T* table, int64_t pitch,
   while (end < n && sorted_keys[end] == key) ++end;
   const int W = g.row_elems;
   if (MODE == 1 && lane == 0) row_to_seg[key] = wid;
-  for (int k0 = lane * 4; k0 < W; k0 += 128) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  // two 128-column chunks per pass: their gradient loads (and the table row's) are independent,
+  // and the permutation entry is read once for both
+  for (int k0 = lane * 4; k0 < W; k0 += 256) {
+    const int k1 = k0 + 128;
+    const bool two = k1 < W;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), t = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = wid; i < end; ++i) {
-      const float4 v = *reinterpret_cast<const float4*>(grad_row(g, perm[i]) + k0);
+      const float* grow = grad_row(g, perm[i]);
+      const float4 v = *reinterpret_cast<const float4*>(grow + k0);
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (two) u = *reinterpret_cast<const float4*>(grow + k1);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
     if (MODE == 0) {
-      T* row = table + (int64_t)key * pitch + k0;
-      row[0] = Elem<T>::from_f(Elem<T>::to_f(row[0]) - lr * s.x);
-      row[1] = Elem<T>::from_f(Elem<T>::to_f(row[1]) - lr * s.y);
-      row[2] = Elem<T>::from_f(Elem<T>::to_f(row[2]) - lr * s.z);
-      row[3] = Elem<T>::from_f(Elem<T>::to_f(row[3]) - lr * s.w);
+      segment_apply_sgd<T>(table + (int64_t)key * pitch + k0, s, lr);
+      if (two) segment_apply_sgd<T>(table + (int64_t)key * pitch + k1, t, lr);
     } else {
       *reinterpret_cast<float4*>(seg_grad + (int64_t)wid * W + k0) = s;
+      if (two) *reinterpret_cast<float4*>(seg_grad + (int64_t)wid * W + k1) = t;
     }
   }
 }
@@ -239,7 +273,24 @@ __global__ void __launch_bounds__(256) relation_reduce_kernel(const float* rows,
   const int k0 = blockIdx.y * 128 + lane * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (k0 < width) {
-    for (int i = start + w; i < end; i += 8) {
+    int i = start + w;
+    if ((width & 3) == 0) {
+      // four rows of this warp's interleaved sequence in flight (the loop was a chain of
+      // dependent perm -> row loads: ~40 serial round trips per warp at biokg's 51 relations);
+      // they are added in sequence order, so the sum is the same as the one-at-a-time loop's
+      for (; i + 24 < end; i += 32) {
+        const int p0 = perm[i], p1 = perm[i + 8], p2 = perm[i + 16], p3 = perm[i + 24];
+        const float4 v0 = *reinterpret_cast<const float4*>(rows + (int64_t)p0 * width + k0);
+        const float4 v1 = *reinterpret_cast<const float4*>(rows + (int64_t)p1 * width + k0);
+        const float4 v2 = *reinterpret_cast<const float4*>(rows + (int64_t)p2 * width + k0);
+        const float4 v3 = *reinterpret_cast<const float4*>(rows + (int64_t)p3 * width + k0);
+        s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+        s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+        s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+        s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+      }
+    }
+    for (; i < end; i += 8) {
       const float* row = rows + (int64_t)perm[i] * width + k0;
       if ((width & 3) == 0) {  // rows 16-byte aligned
         const float4 v = *reinterpret_cast<const float4*>(row);
@@ -316,6 +367,11 @@ extern "C" int bess_scatter_sgd(void* table, int64_t table_pitch, int dtype, int
                                 int64_t dst_stride_rows, float lr, void* stream) {
   if (n == 0) return BESS_OK;
   BESS_CHECK_ARG(row_elems % 4 == 0, "row_elems must be a multiple of 4");
+  {  // the update is a 128-bit (fp32) / 64-bit (half) read-modify-write of 4 elements
+    const int es = dtype == BESS_F32 ? 4 : 2;
+    BESS_CHECK_ARG((reinterpret_cast<uintptr_t>(table) % (4 * es)) == 0 && (table_pitch % 4) == 0,
+                   "bess_scatter_sgd: table rows must be aligned to 4 elements");
+  }
   const GradSrc g = make_src(row_elems, n_local, per_dst, grad_local, grad_dst, dst_stride_rows);
   const int blocks = ceil_div((int64_t)n * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
