@@ -14,7 +14,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libbesskge_b200.so"
 
 F32, F16, BF16 = 0, 1, 2
-TRANSE, ROTATE, DISTMULT, COMPLEX, PAIRRE, BOXE = range(6)
+TRANSE, ROTATE, DISTMULT, COMPLEX, PAIRRE, BOXE, TRIPLERE = range(7)
 MODE_TAILS, MODE_HEADS = 0, 1
 LOSS_LOGSIGMOID, LOSS_MARGIN_RANKING, LOSS_SOFTMAX_CE = 0, 1, 2
 OPT_SGD, OPT_SGDM, OPT_ADAMW = 0, 1, 2
@@ -44,6 +44,7 @@ class ScoreCfg(C.Structure):
         ("apply_tanh", C.c_int32),
         ("per_dim", C.c_int32),
         ("eps", C.c_float),
+        ("rel_u", C.c_float),
     ]
 
 

@@ -434,7 +434,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                 raise NotImplementedError(
                     "augment_negative needs flat_negative_format=True and local_sampling=False"
                 )
-            if self.score_fn._family == L.PAIRRE and getattr(self.score_fn, "normalize", False):
+            if self.score_fn._family in (L.PAIRRE, L.TRIPLERE) and getattr(self.score_fn, "normalize", False):
                 raise NotImplementedError("augment_negative with normalised PairRE")
             # the micro-batch's own heads / tails come first (bess.py:369-394, 430-448)
             aug: List[_Pass] = []
@@ -570,7 +570,7 @@ class EmbeddingMovingBessKGE(BessKGE):
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         qv = ws.get("qv", (S, nvec, W), torch.float32)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
         aux = ws.get("aux", (R, S, N), torch.float32) if need_aux else None
 
         n_out = bps * R
@@ -589,7 +589,7 @@ class EmbeddingMovingBessKGE(BessKGE):
             d_pos = ws.get("d_pos", (R, S), torch.float32)
             d_neg = ws.get("d_neg", (R, S, N), torch.float32)
             ce_copy = lp["kind"] == L.LOSS_SOFTMAX_CE and train and cfg.norm_p == 2 and \
-                cfg.family in (L.TRANSE, L.ROTATE, L.PAIRRE, L.BOXE)
+                cfg.family in (L.TRANSE, L.ROTATE, L.PAIRRE, L.BOXE, L.TRIPLERE)
             neg_l = ws.get("neg_l", (S, N), torch.float32) if ce_copy else None
         if train:
             dH = ws.get("dH", (R, n_loc_rows, W), torch.float32)
@@ -1037,7 +1037,7 @@ class ScoreMovingBessKGE(BessKGE):
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         qv = ws.get("qv", (n * S, nvec, W), torch.float32)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
         # local mode: the score matrix of all replicas is written in place, column block r*X by
         # scoring shard r.  distributed: this rank scores all n*S queries against ITS candidates
         # ([n*S, X]) and the scores travel back to the shards that own the queries (AllToAll).
@@ -1400,7 +1400,7 @@ class TopKQueryBessKGE(torch.nn.Module):
         use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX) and (
             negative is None or flat)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
         Q = ws.get("tk_Q", (nS, W), tdt)
         rel_all = ws.get("tk_rel", (nS,), torch.int32)
         qv = ws.get("tk_qv", (nS, nvec, W), torch.float32)
@@ -1605,7 +1605,7 @@ class AllScoresBESS(torch.nn.Module):
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family == L.PAIRRE and cfg.normalize
+        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
         max_w = max(min(self.device_window, w) for _, w in windows)
         Q = ws.get("as_Q", (nS, W), tdt)
         rel_all = ws.get("as_rel", (nS,), torch.int32)

@@ -27,7 +27,8 @@
 
 namespace bess {
 
-enum Family { FAM_TRANSE = 0, FAM_ROTATE = 1, FAM_DISTMULT = 2, FAM_COMPLEX = 3, FAM_PAIRRE = 4, FAM_BOXE = 5 };
+enum Family { FAM_TRANSE = 0, FAM_ROTATE = 1, FAM_DISTMULT = 2, FAM_COMPLEX = 3, FAM_PAIRRE = 4, FAM_BOXE = 5,
+              FAM_TRIPLERE = 6 };
 enum PairOp { OP_DIST = 0, OP_DOT = 1, OP_PAIRRE = 2, OP_BOXE = 3 };
 enum Mode { MODE_TAILS = 0, MODE_HEADS = 1 };  // which side the candidates replace
 
@@ -39,7 +40,19 @@ struct FamCfg {
   int apply_tanh;  // BoxE
   int per_dim;     // BoxE dist_func_per_dim
   float eps;       // BoxE
+  float rel_u;     // TripleRE v2 offset added to both relation projections (0 = v1)
 };
+
+// PairRE and TripleRE share one code path: -|| h^ (r_h + u) - t^ (r_t + u) (+ r_m) ||_p with the
+// relation row laid out [r_h | r_t] (PairRE, scoring.py:465-593) or [r_h | r_m | r_t] (TripleRE,
+// scoring.py:596-743).  Offsets of the three parts inside a relation row; mid < 0 = no r_m.
+struct ProjLayout { int oh, ot, om; float u; };
+BESS_HD ProjLayout proj_layout(const FamCfg& c) {
+  ProjLayout l;
+  if (c.family == FAM_TRIPLERE) { l.oh = 0; l.om = c.d; l.ot = 2 * c.d; l.u = c.rel_u; }
+  else { l.oh = 0; l.ot = c.d; l.om = -1; l.u = 0.f; }
+  return l;
+}
 
 BESS_HD int ent_width(const FamCfg& c) {
   return (c.family == FAM_ROTATE || c.family == FAM_COMPLEX || c.family == FAM_BOXE) ? 2 * c.d : c.d;
@@ -47,6 +60,7 @@ BESS_HD int ent_width(const FamCfg& c) {
 BESS_HD int rel_width(const FamCfg& c) {
   switch (c.family) {
     case FAM_COMPLEX: case FAM_PAIRRE: return 2 * c.d;
+    case FAM_TRIPLERE: return 3 * c.d;
     case FAM_BOXE: return 4 * c.d + 2;
     default: return c.d;
   }
@@ -55,13 +69,13 @@ BESS_HD int pair_op(const FamCfg& c) {
   switch (c.family) {
     case FAM_TRANSE: case FAM_ROTATE: return OP_DIST;
     case FAM_DISTMULT: case FAM_COMPLEX: return OP_DOT;
-    case FAM_PAIRRE: return OP_PAIRRE;
+    case FAM_PAIRRE: case FAM_TRIPLERE: return OP_PAIRRE;
     default: return OP_BOXE;
   }
 }
 // number of query-side vectors of width ent_width() the pair kernels consume
 BESS_HD int pair_nvec(const FamCfg& c) {
-  return c.family == FAM_PAIRRE ? 2 : (c.family == FAM_BOXE ? 3 : 1);
+  return (c.family == FAM_PAIRRE || c.family == FAM_TRIPLERE) ? 2 : (c.family == FAM_BOXE ? 3 : 1);
 }
 
 // ---- p-norm pieces ---------------------------------------------------------
@@ -261,7 +275,7 @@ BESS_HD float triple_fwd(const FamCfg& c, const T* h, const T* r, const T* t) {
       }
       return Ctx::sum(acc);
     }
-    case FAM_PAIRRE: {
+    case FAM_PAIRRE: case FAM_TRIPLERE: {
       float ih = 1.f, it = 1.f;
       if (c.normalize) {
         float nh = 0.f, nt = 0.f;
@@ -272,8 +286,13 @@ BESS_HD float triple_fwd(const FamCfg& c, const T* h, const T* r, const T* t) {
         ih = 1.f / fmaxf(sqrtf(Ctx::sum(nh)), 1e-12f);
         it = 1.f / fmaxf(sqrtf(Ctx::sum(nt)), 1e-12f);
       }
-      for (int k = l0; k < d; k += ls)
-        acc += nacc(p, Ld<T>::f(h, k) * ih * Ld<T>::f(r, k) - Ld<T>::f(t, k) * it * Ld<T>::f(r, d + k));
+      const ProjLayout pl = proj_layout(c);
+      for (int k = l0; k < d; k += ls) {
+        float e = Ld<T>::f(h, k) * ih * (Ld<T>::f(r, pl.oh + k) + pl.u) -
+                  Ld<T>::f(t, k) * it * (Ld<T>::f(r, pl.ot + k) + pl.u);
+        if (pl.om >= 0) e += Ld<T>::f(r, pl.om + k);
+        acc += nacc(p, e);
+      }
       return -nfin(p, Ctx::sum(acc));
     }
     default: {  // FAM_BOXE
@@ -361,7 +380,7 @@ BESS_HD void triple_bwd(const FamCfg& c, const T* h, const T* r, const T* t, flo
       }
       return;
     }
-    case FAM_PAIRRE: {
+    case FAM_PAIRRE: case FAM_TRIPLERE: {
       const float nv = -score;
       float nh = 1.f, nt = 1.f, ih = 1.f, it = 1.f;
       if (c.normalize) {
@@ -374,19 +393,23 @@ BESS_HD void triple_bwd(const FamCfg& c, const T* h, const T* r, const T* t, flo
         ih = 1.f / fmaxf(nh, 1e-12f); it = 1.f / fmaxf(nt, 1e-12f);
       }
       // first pass: relation grads and the projections hh.dhh, tt.dtt
+      const ProjLayout pl = proj_layout(c);
       float ph = 0.f, pt = 0.f;
       for (int k = l0; k < d; k += ls) {
         const float hh = Ld<T>::f(h, k) * ih, tt = Ld<T>::f(t, k) * it;
-        const float rh = Ld<T>::f(r, k), rt = Ld<T>::f(r, d + k);
-        const float de = -g * ndiff(p, hh * rh - tt * rt, nv);
-        put(dr, k, de * hh, add_r); put(dr, d + k, -de * tt, add_r);
+        const float rh = Ld<T>::f(r, pl.oh + k) + pl.u, rt = Ld<T>::f(r, pl.ot + k) + pl.u;
+        const float rm = pl.om >= 0 ? Ld<T>::f(r, pl.om + k) : 0.f;
+        const float de = -g * ndiff(p, hh * rh - tt * rt + rm, nv);
+        put(dr, pl.oh + k, de * hh, add_r); put(dr, pl.ot + k, -de * tt, add_r);
+        if (pl.om >= 0) put(dr, pl.om + k, de, add_r);
         ph += hh * (de * rh); pt += tt * (-de * rt);
       }
       if (c.normalize) { ph = Ctx::sum(ph); pt = Ctx::sum(pt); }
       for (int k = l0; k < d; k += ls) {
         const float hh = Ld<T>::f(h, k) * ih, tt = Ld<T>::f(t, k) * it;
-        const float rh = Ld<T>::f(r, k), rt = Ld<T>::f(r, d + k);
-        const float de = -g * ndiff(p, hh * rh - tt * rt, nv);
+        const float rh = Ld<T>::f(r, pl.oh + k) + pl.u, rt = Ld<T>::f(r, pl.ot + k) + pl.u;
+        const float rm = pl.om >= 0 ? Ld<T>::f(r, pl.om + k) : 0.f;
+        const float de = -g * ndiff(p, hh * rh - tt * rt + rm, nv);
         float dhh = de * rh, dtt = -de * rt;
         if (c.normalize) {
           // d/dx of x/max(||x||,eps): (I - x^ x^T)/||x|| above eps, I/eps below
@@ -477,18 +500,23 @@ BESS_HD void prologue_fwd(const FamCfg& c, int mode, const T* x, const T* r, flo
         }
       }
       return;
-    case FAM_PAIRRE: {
+    case FAM_PAIRRE: case FAM_TRIPLERE: {
       float inv = 1.f;
       if (c.normalize) {
         float a2 = 0.f;
         for (int k = l0; k < d; k += ls) { const float a = Ld<T>::f(x, k); a2 += a * a; }
         inv = 1.f / fmaxf(sqrtf(Ctx::sum(a2)), 1e-12f);
       }
-      // tails: fixed = head -> qv0 = h^ r_h, qv1 = r_t ; heads: qv0 = t^ r_t, qv1 = r_h
-      const int own = mode == MODE_TAILS ? 0 : d, other = mode == MODE_TAILS ? d : 0;
+      // tails: fixed = head -> qv0 = h^ r_h (+ r_m), qv1 = r_t ; heads: qv0 = t^ r_t (- r_m), qv1 = r_h
+      // (score = -|| c^ qv1 - qv0 ||; TripleRE: scoring.py:699-743)
+      const ProjLayout pl = proj_layout(c);
+      const int own = mode == MODE_TAILS ? pl.oh : pl.ot, other = mode == MODE_TAILS ? pl.ot : pl.oh;
+      const float sm = mode == MODE_TAILS ? 1.f : -1.f;
       for (int k = l0; k < d; k += ls) {
-        qv[k] = Ld<T>::f(x, k) * inv * Ld<T>::f(r, own + k);
-        qv[W + k] = Ld<T>::f(r, other + k);
+        float q0 = Ld<T>::f(x, k) * inv * (Ld<T>::f(r, own + k) + pl.u);
+        if (pl.om >= 0) q0 += sm * Ld<T>::f(r, pl.om + k);
+        qv[k] = q0;
+        qv[W + k] = Ld<T>::f(r, other + k) + pl.u;
       }
       return;
     }
@@ -555,7 +583,7 @@ BESS_HD void prologue_bwd(const FamCfg& c, int mode, const T* x, const T* r, con
         }
       }
       return;
-    case FAM_PAIRRE: {
+    case FAM_PAIRRE: case FAM_TRIPLERE: {
       float nx = 1.f, inv = 1.f;
       if (c.normalize) {
         float a2 = 0.f;
@@ -563,18 +591,21 @@ BESS_HD void prologue_bwd(const FamCfg& c, int mode, const T* x, const T* r, con
         nx = sqrtf(Ctx::sum(a2));
         inv = 1.f / fmaxf(nx, 1e-12f);
       }
-      const int own = mode == MODE_TAILS ? 0 : d, other = mode == MODE_TAILS ? d : 0;
+      const ProjLayout pl = proj_layout(c);
+      const int own = mode == MODE_TAILS ? pl.oh : pl.ot, other = mode == MODE_TAILS ? pl.ot : pl.oh;
+      const float sm = mode == MODE_TAILS ? 1.f : -1.f;
       float proj = 0.f;
       for (int k = l0; k < d; k += ls) {
         const float xh = Ld<T>::f(x, k) * inv;
         put(dr, own + k, dqv[k] * xh, add_r);
         put(dr, other + k, dqv[W + k], add_r);
-        proj += xh * dqv[k] * Ld<T>::f(r, own + k);
+        if (pl.om >= 0) put(dr, pl.om + k, sm * dqv[k], add_r);
+        proj += xh * dqv[k] * (Ld<T>::f(r, own + k) + pl.u);
       }
       if (c.normalize) proj = Ctx::sum(proj);
       for (int k = l0; k < d; k += ls) {
         const float xh = Ld<T>::f(x, k) * inv;
-        float dxh = dqv[k] * Ld<T>::f(r, own + k);
+        float dxh = dqv[k] * (Ld<T>::f(r, own + k) + pl.u);
         if (c.normalize) dxh = nx > 1e-12f ? (dxh - xh * proj) * inv : dxh * inv;
         put(dx, k, dxh, add_x);
       }

@@ -33,7 +33,7 @@ struct Ld<__nv_bfloat16> {
 static inline FamCfg to_cfg(const bess_score_cfg_t* c) {
   FamCfg f;
   f.family = c->family; f.norm_p = c->norm_p; f.d = c->d; f.normalize = c->normalize;
-  f.apply_tanh = c->apply_tanh; f.per_dim = c->per_dim; f.eps = c->eps;
+  f.apply_tanh = c->apply_tanh; f.per_dim = c->per_dim; f.eps = c->eps; f.rel_u = c->rel_u;
   return f;
 }
 
@@ -1071,7 +1071,7 @@ static PerArgs make_per_args(const FamCfg& f, int dtype, int rot, const float* q
                              int col0) {
   PerArgs a;
   a.qv = qv; a.n_query = n_query; a.cand = cand; a.n_per = n_per; a.W = ent_width(f); a.rot = rot;
-  a.apply_tanh = f.apply_tanh; a.normalize = (f.family == FAM_PAIRRE) ? f.normalize : 0;
+  a.apply_tanh = f.apply_tanh; a.normalize = (f.family == FAM_PAIRRE || f.family == FAM_TRIPLERE) ? f.normalize : 0;
   a.vec_ok = cand_vec_ok(cand, dtype, a.W, 0) ? 1 : 0;
   a.score_map = score_map; a.ld = ld; a.col0 = col0;
   a.out = nullptr; a.aux = nullptr; a.score = nullptr; a.d_score = nullptr; a.d_qv = nullptr;

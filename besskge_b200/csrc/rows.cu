@@ -28,7 +28,7 @@ struct WarpCtx {
 static inline FamCfg to_cfg(const bess_score_cfg_t* c) {
   FamCfg f;
   f.family = c->family; f.norm_p = c->norm_p; f.d = c->d; f.normalize = c->normalize;
-  f.apply_tanh = c->apply_tanh; f.per_dim = c->per_dim; f.eps = c->eps;
+  f.apply_tanh = c->apply_tanh; f.per_dim = c->per_dim; f.eps = c->eps; f.rel_u = c->rel_u;
   return f;
 }
 
@@ -222,10 +222,10 @@ static inline int elem_size(int dtype) { return dtype == BESS_F32 ? 4 : 2; }
 
 static int check_cfg(const bess_score_cfg_t* cfg) {
   BESS_CHECK_ARG(cfg != nullptr, "null score config");
-  BESS_CHECK_ARG(cfg->family >= 0 && cfg->family <= BESS_BOXE, "unknown family %d", cfg->family);
+  BESS_CHECK_ARG(cfg->family >= 0 && cfg->family <= BESS_TRIPLERE, "unknown family %d", cfg->family);
   BESS_CHECK_ARG(cfg->d > 0, "embedding_size must be positive");
   if (cfg->family == BESS_TRANSE || cfg->family == BESS_ROTATE || cfg->family == BESS_PAIRRE ||
-      cfg->family == BESS_BOXE)
+      cfg->family == BESS_BOXE || cfg->family == BESS_TRIPLERE)
     BESS_CHECK_ARG(cfg->norm_p == 1 || cfg->norm_p == 2, "scoring_norm %d not supported (1 or 2)",
                    cfg->norm_p);
   return BESS_OK;

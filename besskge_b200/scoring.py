@@ -53,6 +53,7 @@ class BaseScoreFunction(torch.nn.Module, ABC):
             apply_tanh=int(getattr(self, "apply_tanh", False)),
             per_dim=int(getattr(self, "dist_func_per_dim", True)),
             eps=float(getattr(self, "eps", 0.0)),
+            rel_u=float(getattr(self, "u", 0.0)),
         )
 
     @property
@@ -111,7 +112,7 @@ class BaseScoreFunction(torch.nn.Module, ABC):
             out = torch.empty(nq, nc, dtype=torch.float32, device=x.device)
             aux = torch.empty_like(out) if need_aux else None
             scale = None
-            if self._family == L.PAIRRE and cfg.normalize:
+            if self._family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize:
                 scale = torch.empty(nc, dtype=torch.float32, device=x.device)
                 K.cand_inv_norm(dt, L.rows(flat), nc, W, scale)
             K.shared_fwd(cfg, dt, mode, qv, nq, L.rows(flat), scale, nc, out, L.IDENT, nc, 0, aux)
@@ -280,6 +281,48 @@ class PairRE(DistanceBasedScoreFunction):
             "and `2*embedding_size` embedding parameters for each relation"
         )
         self.embedding_size = embedding_size
+
+
+class TripleRE(DistanceBasedScoreFunction):
+    """-||h^ o (r_h + u) - t^ o (r_t + u) + r_m||_p (scoring.py:596-743); relation rows are
+    [r_h | r_m | r_t].  Runs on the PairRE kernels: the query prologue folds r_m into the
+    query vector, the pair function and the candidate normalisation are PairRE's."""
+
+    _family = L.TRIPLERE
+
+    def __init__(
+        self,
+        negative_sample_sharing: bool,
+        scoring_norm: int,
+        sharding: Sharding,
+        n_relation_type: int,
+        embedding_size: int,
+        entity_initializer: Initializer = [init_KGE_uniform],
+        relation_initializer: Initializer = [init_KGE_uniform],
+        normalize_entities: bool = True,
+        u: float = 0.0,
+        inverse_relations: bool = False,
+    ) -> None:
+        super().__init__(negative_sample_sharing, scoring_norm)
+        self.normalize = normalize_entities
+        if isinstance(relation_initializer, list):
+            relation_initializer = 3 * relation_initializer
+        self._build_tables(sharding, n_relation_type, inverse_relations, entity_initializer,
+                           relation_initializer, [embedding_size],
+                           [embedding_size, embedding_size, embedding_size])
+        assert (
+            3 * self.entity_embedding.shape[-1]
+            == self.relation_embedding.shape[-1]
+            == 3 * embedding_size
+        ), (
+            "TripleRE requires `embedding_size` embedding parameters for each entity"
+            "and `3*embedding_size` embedding parameters for each relation"
+        )
+        self.embedding_size = embedding_size
+        self.use_v2 = u > 0.0
+        # the reference adds rel_u only when u > 0 (scoring.py:692-694); u <= 0 means "no offset"
+        self.u = float(u) if self.use_v2 else 0.0
+        self.register_buffer("rel_u", torch.tensor([u], dtype=self.entity_embedding.dtype))
 
 
 class DistMult(MatrixDecompositionScoreFunction):

@@ -34,7 +34,8 @@ typedef enum { BESS_F32 = 0, BESS_F16 = 1, BESS_BF16 = 2 } bess_dtype;
 /* score-function families (scoring.py) */
 typedef enum {
   BESS_TRANSE = 0, BESS_ROTATE = 1, BESS_DISTMULT = 2,
-  BESS_COMPLEX = 3, BESS_PAIRRE = 4, BESS_BOXE = 5
+  BESS_COMPLEX = 3, BESS_PAIRRE = 4, BESS_BOXE = 5,
+  BESS_TRIPLERE = 6 /* scoring.py:596-743: PairRE kernels + a relation offset row */
 } bess_family;
 
 /* which entity the candidates replace: score_tails / score_heads */
@@ -75,6 +76,7 @@ typedef struct {
   int32_t apply_tanh;  /* BoxE */
   int32_t per_dim;     /* BoxE dist_func_per_dim */
   float eps;           /* BoxE */
+  float rel_u;         /* TripleRE v2 offset u added to both relation projections (0 = v1) */
 } bess_score_cfg_t;
 
 #define BESS_MAX_SHARD 16

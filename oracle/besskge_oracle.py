@@ -174,6 +174,14 @@ def score_triple(cfg: Dict[str, Any], h: torch.Tensor, rel_table: torch.Tensor, 
         if cfg.get("normalize", True):
             h, t = _normalize(h), _normalize(t)
         return -_norm(h * rh - t * rt, p)
+    if fam == "TripleRE":  # scoring.py:683-697
+        rh, rm, rt = re[..., :d], re[..., d:2 * d], re[..., 2 * d:]
+        u = cfg.get("rel_u", 0.0)
+        if u > 0.0:
+            rh, rt = rh + u, rt + u
+        if cfg.get("normalize", True):
+            h, t = _normalize(h), _normalize(t)
+        return -_norm(h * rh - t * rt + rm, p)
     if fam == "BoxE":  # scoring.py:1342-1363
         center, width, size = torch.split(re, 2 * d, dim=-1)
         bumped = h.view(-1, 2, d) + t.view(-1, 2, d)[:, [1, 0]]
@@ -210,6 +218,18 @@ def score_candidates(cfg: Dict[str, Any], mode: str, fixed: torch.Tensor, rel_ta
         if mode == "t":
             return -_norm(cand * rt.unsqueeze(1) - (fixed * rh).unsqueeze(1), p)
         return -_norm(cand * rh.unsqueeze(1) - (fixed * rt).unsqueeze(1), p)
+    if fam == "TripleRE":  # scoring.py:699-743
+        rh, rm, rt = re[..., :d], re[..., d:2 * d], re[..., 2 * d:]
+        u = cfg.get("rel_u", 0.0)
+        if u > 0.0:
+            rh, rt = rh + u, rt + u
+        if cfg.get("normalize", True):
+            fixed, cand = _normalize(fixed), _normalize(cand)
+        if shared:
+            cand = cand.reshape(1, -1, d)
+        if mode == "t":
+            return -_norm(cand * rt.unsqueeze(1) - (fixed * rh + rm).unsqueeze(1), p)
+        return -_norm(cand * rh.unsqueeze(1) - (fixed * rt - rm).unsqueeze(1), p)
     if fam == "BoxE":  # scoring.py:1366-1415
         center, width, size = torch.split(re, 2 * d, dim=-1)
         if shared:

@@ -8,9 +8,12 @@
 
 using namespace bess;
 
+// TripleRE's v2 offset u travels in a global set by hc_set_rel_u (keeps every signature unchanged)
+static float g_rel_u = 0.f;
+extern "C" void hc_set_rel_u(float u) { g_rel_u = u; }
 static FamCfg mk(int family, int p, int d, int normalize, int apply_tanh, int per_dim, float eps) {
   FamCfg c; c.family = family; c.norm_p = p; c.d = d; c.normalize = normalize;
-  c.apply_tanh = apply_tanh; c.per_dim = per_dim; c.eps = eps; return c;
+  c.apply_tanh = apply_tanh; c.per_dim = per_dim; c.eps = eps; c.rel_u = g_rel_u; return c;
 }
 
 extern "C" {

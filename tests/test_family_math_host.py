@@ -17,10 +17,12 @@ from torch.testing import assert_close
 from oracle import besskge_oracle as O
 
 ROOT = Path(__file__).resolve().parents[1]
-FAM_ID = {"TransE": 0, "RotatE": 1, "DistMult": 2, "ComplEx": 3, "PairRE": 4, "BoxE": 5}
-EW = {"TransE": 1, "RotatE": 2, "DistMult": 1, "ComplEx": 2, "PairRE": 1, "BoxE": 2}
+FAM_ID = {"TransE": 0, "RotatE": 1, "DistMult": 2, "ComplEx": 3, "PairRE": 4, "BoxE": 5,
+          "TripleRE": 6}
+EW = {"TransE": 1, "RotatE": 2, "DistMult": 1, "ComplEx": 2, "PairRE": 1, "BoxE": 2, "TripleRE": 1}
 RW = {"TransE": lambda d: d, "RotatE": lambda d: d, "DistMult": lambda d: d,
-      "ComplEx": lambda d: 2 * d, "PairRE": lambda d: 2 * d, "BoxE": lambda d: 4 * d + 2}
+      "ComplEx": lambda d: 2 * d, "PairRE": lambda d: 2 * d, "BoxE": lambda d: 4 * d + 2,
+      "TripleRE": lambda d: 3 * d}
 
 
 @pytest.fixture(scope="module")
@@ -40,12 +42,15 @@ VARIANTS = [
     ("DistMult", dict(p=2)), ("ComplEx", dict(p=2)),
     ("PairRE", dict(p=1)), ("PairRE", dict(p=2)), ("PairRE", dict(p=2, normalize=False)),
     ("BoxE", dict(p=1)), ("BoxE", dict(p=2)), ("BoxE", dict(p=2, apply_tanh=False)),
+    ("TripleRE", dict(p=1)), ("TripleRE", dict(p=2, rel_u=0.5)),
+    ("TripleRE", dict(p=1, normalize=False, rel_u=1.25)),
 ]
 
 
 def cfgs(fam, v, d):
     o = dict(family=fam, d=d, norm_p=v["p"], normalize=v.get("normalize", True),
-             apply_tanh=v.get("apply_tanh", True), per_dim=v.get("per_dim", True), eps=1e-6)
+             apply_tanh=v.get("apply_tanh", True), per_dim=v.get("per_dim", True), eps=1e-6,
+             rel_u=v.get("rel_u", 0.0))
     c_args = (FAM_ID[fam], v["p"], d, int(o["normalize"]), int(o["apply_tanh"]), int(o["per_dim"]),
               C.c_float(1e-6))
     return o, c_args
@@ -67,6 +72,7 @@ def data(fam, d, n, nc, seed=0):
 def test_triple_fwd_bwd(lib, fam, v):
     d, n = 16, 11
     o, ca = cfgs(fam, v, d)
+    lib.hc_set_rel_u(C.c_float(o["rel_u"]))
     h, t, rel, r, _, _ = data(fam, d, n, 3)
     out = torch.empty(n)
     lib.hc_triple_fwd(*ca, n, C.c_void_p(fp(h)), C.c_void_p(fp(rel)), C.c_void_p(fp(r)),
@@ -93,6 +99,7 @@ def test_triple_fwd_bwd(lib, fam, v):
 def test_candidates_fwd_bwd(lib, fam, v, mode, shared):
     d, n, nc = 16, 7, 5
     o, ca = cfgs(fam, v, d)
+    lib.hc_set_rel_u(C.c_float(o["rel_u"]))
     h, t, rel, r, cs, cp = data(fam, d, n, nc, seed=3)
     fixed = h if mode == "t" else t
     cand = cs if shared else cp
