@@ -267,7 +267,7 @@ def run_replicated(
             for s in range(batches_per_step):
                 i = s * n_shard + r
                 kwargs = {k: v[i : i + 1] for k, v in flat.items()}
-                if "triple_weight" not in kwargs and getattr(rep, "loss_fn", None) is not None:
+                if "triple_weight" not in kwargs and hasattr(rep, "loss_fn"):
                     kwargs["triple_weight"] = torch.tensor([1.0])
                 with torch.set_grad_enabled(grad):
                     res = rep(**kwargs)

@@ -153,6 +153,7 @@ FAMILIES = {
     "ComplEx": dict(cls="ComplEx", norm=False, ew=2, rw=lambda d: 2 * d),
     "PairRE": dict(cls="PairRE", norm=True, ew=1, rw=lambda d: 2 * d),
     "BoxE": dict(cls="BoxE", norm=True, ew=2, rw=lambda d: 4 * d + 2),
+    "TripleRE": dict(cls="TripleRE", norm=True, ew=1, rw=lambda d: 3 * d),
 }
 
 
@@ -174,15 +175,19 @@ def tables(fam, sh, n_rel, d, gen, scale=1.0):
     return ent, rel
 
 
-def golden_scores(ref) -> None:
+def golden_scores(ref, only=None) -> None:
     sh = ref.sharding.Sharding.create(60, 1, seed=SEED)
     n_rel, d, b, nn_ = 7, 16, 12, 9
     for fam in FAMILIES:
+        if only is not None and fam not in only:
+            continue
         gen = torch.Generator().manual_seed(SEED)
         arrays = {}
         variants = [dict(p=1), dict(p=2)] if FAMILIES[fam]["norm"] else [dict(p=0)]
         if fam == "PairRE":
             variants.append(dict(p=1, normalize_entities=False))
+        if fam == "TripleRE":
+            variants += [dict(p=1, u=0.5), dict(p=2, normalize_entities=False, u=1.25)]
         if fam == "BoxE":
             variants += [dict(p=2, apply_tanh=False), dict(p=1, dist_func_per_dim=False)]
         ent, rel = tables(fam, sh, n_rel, d, gen)
@@ -266,13 +271,15 @@ def golden_metric(ref) -> None:
 
 
 # --------------------------------------------------------------------- bess --
-def golden_bess(ref) -> None:
+def golden_bess(ref, only=None) -> None:
     n_entity, n_rel, n_shard, n_triple, bps, shard_bs, n_neg, d = 200, 6, 4, 400, 2, 16, 24, 16
     sh = ref.sharding.Sharding.create(n_entity, n_shard, seed=SEED)
     combos = [
         ("TransE", 1), ("TransE", 2), ("RotatE", 1), ("DistMult", 0), ("ComplEx", 0),
-        ("PairRE", 1), ("BoxE", 1), ("BoxE", 2),
+        ("PairRE", 1), ("BoxE", 1), ("BoxE", 2), ("TripleRE", 1),
     ]
+    if only is not None:
+        combos = [c for c in combos if c[0] in only]
     for model_name in ("EmbeddingMoving", "ScoreMoving"):
         for fam, p in combos:
             if model_name == "ScoreMoving" and fam in ("RotatE", "ComplEx", "BoxE") and p != 2:
@@ -311,7 +318,7 @@ def golden_bess(ref) -> None:
                          ranks=res["ranks"], metrics=res["metrics"])
 
 
-def golden_train(ref) -> None:
+def golden_train(ref, only=None) -> None:
     """reference forward -> torch.autograd -> dense torch.optim, n_shard 4 and 1."""
     n_entity, n_rel, n_triple, d, n_step = 200, 6, 600, 16, 3
     specs = [
@@ -340,8 +347,13 @@ def golden_train(ref) -> None:
         # NOTE: augment_negative cannot be generated from the unmodified reference on CPU
         # torch: bess.py:388 calls .view() on a non-contiguous split (works only when
         # traced by PopTorch).  That path is checked against the oracle only.
+        dict(fam="TripleRE", p=1, n_shard=4, scheme="t", flat=True, n_neg=6, shard_bs=16,
+             loss=("logsigmoid", dict(margin=3.0, negative_adversarial_sampling=True)),
+             opt=dict(kind="sgd", lr=0.05), kw=dict(u=0.5)),
     ]
     for si, sp in enumerate(specs):
+        if only is not None and sp["fam"] not in only:
+            continue
         n_shard = sp["n_shard"]
         sh = ref.sharding.Sharding.create(n_entity, n_shard, seed=SEED)
         rng = np.random.default_rng(SEED + 11)
@@ -350,7 +362,7 @@ def golden_train(ref) -> None:
         gen = torch.Generator().manual_seed(SEED + si)
         ent, rel = tables(sp["fam"], sh, n_rel, d, gen, scale=0.5)
         sf = build_score_fn(ref, sp["fam"], sp["flat"], sp["p"], sh, n_rel, d, ent.clone(),
-                            rel.clone())
+                            rel.clone(), **sp.get("kw", {}))
         ns = ref.negative_sampler.RandomShardedNegativeSampler(
             n_negative=sp["n_neg"], sharding=sh, seed=SEED, corruption_scheme=sp["scheme"],
             local_sampling=False, flat_negative_format=sp["flat"])

@@ -15,7 +15,8 @@ def T(a):
 
 def score_cfg(fam, d, p=2, **kw):
     return dict(family=fam, d=d, norm_p=p or 2, normalize=kw.get("normalize", True),
-                apply_tanh=kw.get("apply_tanh", True), per_dim=kw.get("per_dim", True), eps=1e-6)
+                apply_tanh=kw.get("apply_tanh", True), per_dim=kw.get("per_dim", True), eps=1e-6,
+                rel_u=kw.get("u", 0.0))
 
 
 def make_score_fn(fam, sharing, p, sh, n_rel, d, ent, rel, dtype=torch.float32, **kw):

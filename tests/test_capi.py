@@ -38,7 +38,7 @@ def test_struct_layout_matches_header():
     # bess_rowmap_t: 5 x int32; bess_rows_t: 2 pointers + rowmap + int64 pitch
     assert ctypes.sizeof(_lib.RowMap) == 20
     assert ctypes.sizeof(_lib.Rows) == 48
-    assert ctypes.sizeof(_lib.ScoreCfg) == 28
+    assert ctypes.sizeof(_lib.ScoreCfg) == 32  # 6 x int32 + eps + rel_u
 
 
 def test_widths_from_library():
@@ -48,6 +48,10 @@ def test_widths_from_library():
     assert lib.bess_entity_width(ctypes.byref(cfg)) == 16
     assert lib.bess_relation_width(ctypes.byref(cfg)) == 34
     assert lib.bess_query_nvec(ctypes.byref(cfg)) == 3
+    tri = _lib.ScoreCfg(family=_lib.TRIPLERE, norm_p=1, d=8, normalize=1, rel_u=0.5)
+    assert lib.bess_entity_width(ctypes.byref(tri)) == 8
+    assert lib.bess_relation_width(ctypes.byref(tri)) == 24
+    assert lib.bess_query_nvec(ctypes.byref(tri)) == 2
 
 
 def test_no_cpu_fallback():

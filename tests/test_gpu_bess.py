@@ -66,7 +66,7 @@ def test_training_vs_reference_golden(name):
     cfg, g = load_golden(name)
     sh = Sharding.create(cfg["n_entity"], cfg["n_shard"], seed=cfg["seed"])
     sf = H.make_score_fn(cfg["fam"], cfg["flat"], cfg["p"], sh, cfg["n_rel"], cfg["d"],
-                         H.T(g["ent0"]), H.T(g["rel0"]))
+                         H.T(g["ent0"]), H.T(g["rel0"]), **cfg.get("kw", {}))
     ns = H.fake_sampler(cfg["scheme"], cfg["flat"], triple_based=False)
     model = EmbeddingMovingBessKGE(ns, sf, loss_fn=H.make_loss(cfg["loss"]))
     o = cfg["opt"]

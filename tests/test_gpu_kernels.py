@@ -11,7 +11,7 @@ from .conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE"]
+FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE", "TripleRE"]
 
 
 def _imports():
@@ -91,6 +91,8 @@ def test_score_functions_vs_reference_golden(fam):
             kw["apply_tanh"] = v["apply_tanh"]
         if "dist_func_per_dim" in v:
             kw["dist_func_per_dim"] = v["dist_func_per_dim"]
+        if "u" in v:
+            kw["u"] = v["u"]
         for sharing in (True, False):
             sf = H.make_score_fn(fam, sharing, v["p"], sh, cfg["n_rel"], d, ent, rel, **kw)
             assert_close(sf.score_triple(h, r, t).cpu(), H.T(g[f"v{vi}_triple"]), rtol=1e-5,
@@ -105,7 +107,7 @@ def test_score_functions_vs_reference_golden(fam):
 
 
 @pytest.mark.parametrize("fam,p", [("TransE", 1), ("TransE", 2), ("RotatE", 1), ("DistMult", 2),
-                                   ("ComplEx", 2), ("PairRE", 2), ("BoxE", 1)])
+                                   ("ComplEx", 2), ("PairRE", 2), ("BoxE", 1), ("TripleRE", 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_score_shared_tiles_vs_oracle(fam, p, dtype):
     """multi-tile shapes (ragged edges) in every table dtype; 1e-5 (fp32) / 1e-2 (half)."""
@@ -116,7 +118,7 @@ def test_score_shared_tiles_vs_oracle(fam, p, dtype):
     g = torch.Generator().manual_seed(5)
     ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
     rw = {"TransE": d, "RotatE": d, "DistMult": d, "ComplEx": 2 * d, "PairRE": 2 * d,
-          "BoxE": 4 * d + 2}[fam]
+          "BoxE": 4 * d + 2, "TripleRE": 3 * d}[fam]
     ent = torch.randn(1, 64, ew * d, generator=g)
     rel = (torch.randn(n_rel, rw, generator=g)).to(dtype).float()
     h = torch.randn(nq, ew * d, generator=g).to(dtype)

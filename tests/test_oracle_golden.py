@@ -10,7 +10,7 @@ from oracle import besskge_oracle as O
 
 from .conftest import golden_names, load_golden
 
-FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE"]
+FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE", "TripleRE"]
 
 
 def T(a):
@@ -21,7 +21,7 @@ def score_cfg(fam, d, v):
     return dict(family=fam, d=d, norm_p=v.get("p", 2) or 2,
                 normalize=v.get("normalize_entities", True),
                 apply_tanh=v.get("apply_tanh", True), per_dim=v.get("dist_func_per_dim", True),
-                eps=1e-6)
+                eps=1e-6, rel_u=v.get("u", 0.0))
 
 
 def test_sharding_oracle():
@@ -131,7 +131,7 @@ def test_bess_forward_oracle(name):
 @pytest.mark.parametrize("name", golden_names("train_"))
 def test_training_oracle(name):
     cfg, g = load_golden(name)
-    c = score_cfg(cfg["fam"], cfg["d"], dict(p=cfg["p"]))
+    c = score_cfg(cfg["fam"], cfg["d"], dict(p=cfg["p"], **cfg.get("kw", {})))
     batches = []
     for s in range(cfg["n_step"]):
         b = {k[len(f"s{s}_in_"):]: T(v)[0] for k, v in g.items() if k.startswith(f"s{s}_in_")}
