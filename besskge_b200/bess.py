@@ -158,11 +158,19 @@ class _PeerExchange:
     def flags(self, channel: int) -> torch.Tensor:
         return self.view(channel * 64 * 4, (self.n,), torch.int32)
 
-    def handshake(self, channel: int) -> None:
-        """signal every rank, then wait for every rank, on one channel."""
+    def signal(self, channel: int) -> None:
+        """tell every rank that this rank's stores of the current phase are complete."""
         K.peer_signal(self.counters[channel:channel + 1],
                       [p + channel * 64 * 4 for p in self.ptrs], self.rank)
+
+    def wait(self, channel: int) -> None:
+        """wait until every rank has signalled the current phase (after `signal`)."""
         K.peer_wait(self.counters[channel:channel + 1], self.flags(channel), self.n)
+
+    def handshake(self, channel: int) -> None:
+        """signal every rank, then wait for every rank, on one channel."""
+        self.signal(channel)
+        self.wait(channel)
 
 
 class _Staged:
@@ -683,8 +691,21 @@ class EmbeddingMovingBessKGE(BessKGE):
                     dst = [TN[j].data_ptr() for j in range(n)]
                     slot = li
                 K.gather_route(table, gidx[row], n_loc_rows, per, H[li], dst, slot)
+            pre_done = False
             if px is not None:
-                px.handshake(0)
+                # Signal at once, wait as late as possible: the query prologue and its operand
+                # split read only LOCAL rows (own heads, replicated relation table), so they run
+                # while the peers' tail / negative rows are still arriving over NVLink.
+                px.signal(0)
+                if R == 1 and len(passes) == 1 and passes[0].fixed_from_head:
+                    ps0, row0 = passes[0], step_rows[0]
+                    K.prologue_fwd(cfg, dt, ps0.mode, L.rows(H[0], rmap=ps0.fixed_map), rel_table,
+                                   rel[row0], ps0.qmap, ps0.n_query, qv)
+                    if ps0.shared and use_tc:
+                        q0 = tc_q[0] = _TcOperand(ws, "q0", ps0.n_query, W, tdt, train)
+                        q0.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
+                    pre_done = True
+                px.wait(0)
             elif pl.distributed:
                 pl.all_to_all(TN[0], SEND)
 
@@ -702,13 +723,17 @@ class EmbeddingMovingBessKGE(BessKGE):
                 for pi, ps in enumerate(passes):
                     fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
                              else L.rows(TNl, rmap=ps.fixed_map))
-                    K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
-                                   ps.n_query, qv)
+                    if not pre_done:
+                        K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                       ps.n_query, qv)
                     cand = self._cand_rows(ps, Hl, TNl, local)
                     if ps.shared and use_tc:
                         # scores = Q C^T on the tensor cores (scoring.py:252)
-                        q_op = tc_q[pi] = _TcOperand(ws, f"q{pi}", ps.n_query, W, tdt, train)
-                        q_op.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
+                        if pre_done:
+                            q_op = tc_q[pi]
+                        else:
+                            q_op = tc_q[pi] = _TcOperand(ws, f"q{pi}", ps.n_query, W, tdt, train)
+                            q_op.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
                         c_op = tc_c[pi] = _TcOperand(ws, f"c{pi}", ps.n_cand, W, tdt, train)
                         c_op.fill(dt, cand, dt, None, dev)
                         K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
