@@ -82,6 +82,11 @@ SIGNATURES = {
     "bess_dot_gemm_workspace": [_I, _I, _I],
     "bess_dot_gemm": [_I, _P, _P, _L, _I, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P],
     "bess_split_operand": [_I, Rows, _I, _I, _P, _I, _P, _P, _L, _P, _P, _L, _P],
+    "bess_row_sqnorm": [_I, Rows, _I, _I, _P, _P],
+    "bess_l2_from_dot": [_P, RowMap, _L, _I, _I, _I, _P, _P, _P],
+    "bess_l2_coef_workspace": [_I, _I],
+    "bess_l2_coef": [_P, _P, RowMap, _L, _I, _I, _I, _P, _L, _P, _P, _P, _P],
+    "bess_rows_axpy": [_I, _P, _F, Rows, Rows, _I, _I, _P],
     "bess_table_operand_refresh": [_P, _L, _I, _L, _P, _P, _L, _P, _I, _P],
     "bess_score_pertriple_fwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, RowMap, _L, _I, _P, _P],
     "bess_score_pertriple_bwd": [_CFG, _I, _I, _P, _I, Rows, _L, _I, _P, _P, RowMap, _L, _I, _P, _P,
@@ -117,10 +122,12 @@ _RESTYPE = {
     "bess_shared_bwd_cand_workspace": C.c_int64,
     "bess_sort_workspace": C.c_int64,
     "bess_dot_gemm_workspace": C.c_int64,
+    "bess_l2_coef_workspace": C.c_int64,
     "bess_launch_count": C.c_int64,
 }
 _NO_STATUS = {"bess_version", "bess_launch_count", "bess_entity_width", "bess_relation_width", "bess_query_nvec",
-              "bess_shared_bwd_cand_workspace", "bess_sort_workspace", "bess_dot_gemm_workspace"}
+              "bess_shared_bwd_cand_workspace", "bess_sort_workspace", "bess_dot_gemm_workspace",
+              "bess_l2_coef_workspace"}
 
 _lib: Optional[C.CDLL] = None
 

@@ -26,6 +26,7 @@ Inputs keep the reference layout: a leading `batches_per_step * n_shard` axis
 from __future__ import annotations
 
 import dataclasses
+import os
 from abc import ABC, abstractmethod
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
@@ -207,6 +208,17 @@ class _Pass:
 # (csrc/gemm_tc.cu).  The exact-fp32 CUDA-core tile kernel (csrc/pair.cu)
 # computes the same thing and is kept selectable for A/B parity tests only.
 USE_TENSOR_CORES = True
+# TransE / RotatE with scoring_norm=2 against shared negatives: norm-expanded distance
+# ||q||^2 + ||c||^2 - 2 q.c with the q.c block (and both backward contractions) on the tcgen05
+# GEMM (csrc/l2.cu).  The expansion carries an absolute error of ~1e-6 (||q||^2 + ||c||^2) in the
+# squared distance — the same cancellation torch.cdist's own matmul path has — which only matters
+# for pairs closer than ~1e-2 of their norms; False selects the exact CUDA-core tile kernels.
+USE_L2_TENSOR_CORES = os.environ.get("BESS_L2_TC", "1") != "0"
+# ... and only where it pays: the expansion adds ~a dozen small kernels (operand split, norms,
+# coefficient sums, row scalings) around three GEMMs, which beats the three CUDA-core tile kernels
+# once a pass has about this many (query, candidate, coordinate) elements (measured: 8192 x 64 x
+# 128 = 6.7e7 is 17 % slower on the GEMM path, 0.202 vs 0.172 ms per step).
+L2_TC_MIN_WORK = int(os.environ.get("BESS_L2_TC_MIN_WORK", str(1 << 27)))
 
 
 def _pad8(x: int) -> int:
@@ -629,10 +641,16 @@ class EmbeddingMovingBessKGE(BessKGE):
             if need_scale else None
 
         use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX)
+        use_l2tc = (USE_TENSOR_CORES and USE_L2_TENSOR_CORES and cfg.norm_p == 2
+                    and cfg.family in (L.TRANSE, L.ROTATE))
+        # per pass: tensor cores only where the pass is large enough to amortise the extra kernels
+        l2tc = [bool(use_l2tc and ps.shared and ps.n_query * ps.n_cand * W >= L2_TC_MIN_WORK)
+                for ps in passes]
+        use_l2tc = any(l2tc)
         tc_q: Dict[int, _TcOperand] = {}
         tc_c: Dict[int, _TcOperand] = {}
         gemm_ws = None
-        if use_tc and any(ps.shared for ps in passes):
+        if (use_tc or use_l2tc) and any(ps.shared for ps in passes):
             nbytes = 0
             for ps in passes:
                 if ps.shared:
@@ -701,7 +719,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     ps0, row0 = passes[0], step_rows[0]
                     K.prologue_fwd(cfg, dt, ps0.mode, L.rows(H[0], rmap=ps0.fixed_map), rel_table,
                                    rel[row0], ps0.qmap, ps0.n_query, qv)
-                    if ps0.shared and use_tc:
+                    if ps0.shared and (use_tc or l2tc[0]):
                         q0 = tc_q[0] = _TcOperand(ws, "q0", ps0.n_query, W, tdt, train)
                         q0.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
                     pre_done = True
@@ -739,6 +757,26 @@ class EmbeddingMovingBessKGE(BessKGE):
                         K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
                                    ps.n_query, ps.n_cand, W, neg, ps.qmap, N, ps.col0, False,
                                    gemm_ws)
+                    elif l2tc[pi]:
+                        # -||q - c||_2 from ||q||^2 + ||c||^2 - 2 q.c, q.c on the tensor cores
+                        if pre_done:
+                            q_op = tc_q[pi]
+                        else:
+                            q_op = tc_q[pi] = _TcOperand(ws, f"q{pi}", ps.n_query, W, tdt, train)
+                            q_op.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
+                        c_op = tc_c[pi] = _TcOperand(ws, f"c{pi}", ps.n_cand, W, tdt, train)
+                        c_op.fill(dt, cand, dt, None, dev)
+                        K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
+                                   ps.n_query, ps.n_cand, W, neg, ps.qmap, N, ps.col0, False,
+                                   gemm_ws)
+                        qn = ws.get(f"l2_qn{pi}", (ps.n_query,), torch.float32)
+                        cn = ws.get(f"l2_cn{pi}", (ps.n_cand,), torch.float32)
+                        if tdt == torch.float32:  # 3xTF32 products are fp32-grade: norms of q itself
+                            K.row_sqnorm(L.F32, L.rows(qv.view(-1, W)), ps.n_query, W, qn)
+                        else:  # norms of the rounded operand the MMA multiplied
+                            K.row_sqnorm(dt, L.rows(q_op.hi), ps.n_query, W, qn)
+                        K.row_sqnorm(dt, cand, ps.n_cand, W, cn)
+                        K.l2_from_dot(neg, ps.qmap, N, ps.col0, ps.n_query, ps.n_cand, qn, cn)
                     elif ps.shared:
                         scale = None
                         if need_scale:
@@ -841,6 +879,31 @@ class EmbeddingMovingBessKGE(BessKGE):
                             continue
                         K.prologue_fwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                        ps.n_query, qv)
+                        if l2tc[pi]:
+                            # b = dL/dscore / dist; dQ = B C - rb * Q, dC = B^T Q - cb * C
+                            q_op, c_op = tc_q[pi], tc_c[pi]
+                            nq_, nc_ = ps.n_query, ps.n_cand
+                            ldc = _pad8(nc_)
+                            coef = ws.get("l2_coef", (nq_, ldc), torch.float32)
+                            rb = ws.get("l2_rb", (nq_,), torch.float32)
+                            cb = ws.get("l2_cb", (nc_,), torch.float32)
+                            cws = ws.get("l2_ws", (max(K.l2_coef_workspace(nq_, nc_) // 4, 1),),
+                                         torch.float32)
+                            K.l2_coef(d_neg[li], score_for_bwd, ps.qmap, N, ps.col0, nq_, nc_, coef,
+                                      ldc, rb, cb, cws)
+                            ds = _TcOperand(ws, "ds", nq_, nc_, tdt, True)
+                            ds.fill(L.F32, L.rows(coef), dt, None, dev)
+                            K.dot_gemm(dt, ds.hi, ds.lo, ds.ld, c_op.hit, c_op.lot, c_op.ldt, nq_, W,
+                                       nc_, d_qv, L.IDENT, W, 0, False, gemm_ws)
+                            K.rows_axpy(L.F32, rb, -1.0, L.rows(qv.view(-1, W)),
+                                        L.rows(d_qv.view(-1, W)), nq_, W)
+                            K.dot_gemm(dt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot, q_op.ldt, nc_,
+                                       W, nq_, d_qv, d_cand.map, d_cand.pitch, 0, ps.aug, gemm_ws,
+                                       out_ptr=d_cand.base)
+                            K.rows_axpy(dt, cb, -1.0, cand, d_cand, nc_, W)
+                            K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
+                                           nq_, d_qv, d_fixed, dRq[li], True, True)
+                            continue
                         if ps.shared:
                             scale = None
                             if need_scale:

@@ -149,6 +149,36 @@ def split_operand(src_dt: int, src: Rows, n_rows: int, width: int,
          ld, ptr(hi_t), ptr(lo_t), ld_t, torch.cuda.current_stream(device).cuda_stream)
 
 
+# ------------------------------------------ norm-expanded L2 (tensor cores) --
+def row_sqnorm(dt: int, rows_: Rows, n: int, width: int, out: torch.Tensor) -> None:
+    call("bess_row_sqnorm", dt, rows_, n, width, out.data_ptr(), _st(out))
+
+
+def l2_from_dot(score: torch.Tensor, score_map: RowMap, ld: int, col0: int, n_query: int,
+                n_cand: int, qn: torch.Tensor, cn: torch.Tensor) -> None:
+    """dots -> -sqrt(max(qn + cn - 2 dot, 0)) in place; see bess_l2_from_dot."""
+    call("bess_l2_from_dot", score.data_ptr(), score_map, ld, col0, n_query, n_cand, qn.data_ptr(),
+         cn.data_ptr(), _st(score))
+
+
+def l2_coef_workspace(n_query: int, n_cand: int) -> int:
+    return int(call("bess_l2_coef_workspace", n_query, n_cand))
+
+
+def l2_coef(d_score: torch.Tensor, score: torch.Tensor, score_map: RowMap, ld: int, col0: int,
+            n_query: int, n_cand: int, coef: torch.Tensor, ld_coef: int, row_sum: torch.Tensor,
+            col_sum: torch.Tensor, workspace: torch.Tensor) -> None:
+    call("bess_l2_coef", d_score.data_ptr(), score.data_ptr(), score_map, ld, col0, n_query, n_cand,
+         coef.data_ptr(), ld_coef, row_sum.data_ptr(), col_sum.data_ptr(), workspace.data_ptr(),
+         _st(score))
+
+
+def rows_axpy(dt: int, alpha: torch.Tensor, scale: float, src: Rows, out: Rows, n: int,
+              width: int) -> None:
+    """out_i += scale * alpha[i] * src_i; see bess_rows_axpy."""
+    call("bess_rows_axpy", dt, alpha.data_ptr(), float(scale), src, out, n, width, _st(alpha))
+
+
 def table_operand_refresh(table: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, ld: int,
                           state: torch.Tensor, force: bool) -> None:
     """fp32 table [rows, W] -> cached hi / lo operand arrays, rebuilt only when the table's

@@ -215,6 +215,26 @@ int bess_table_operand_refresh(const float* table, int64_t n_rows, int width, in
                                float* hi, float* lo, int64_t ld, uint64_t* state, int force,
                                void* stream);
 
+/* --------------------------- norm-expanded L2 distance on the tensor cores ---
+ * `pea.distance_matrix(v1, v2, p=2)` (scoring.py:195-197) for shared negatives as
+ * ||q - c||^2 = ||q||^2 + ||c||^2 - 2 q.c : the q.c block is one bess_dot_gemm, these are the
+ * kernels around it.  Backward with b = (dL/dscore) / dist: dQ = B C - rb * Q, dC = B^T Q - cb * C
+ * (two more bess_dot_gemm + row scalings).  All reductions run in a fixed order.
+ *   bess_row_sqnorm : out[i] = sum_k row_i[k]^2
+ *   bess_l2_from_dot: score[map(q), col0 + c] <- -sqrt(max(qn[q] + cn[c] - 2 score, 0)) in place
+ *   bess_l2_coef    : coef[q, c] = -d_score / score (0 where score == 0), row_sum[q], col_sum[c];
+ *                     workspace of bess_l2_coef_workspace(n_query, n_cand) bytes
+ *   bess_rows_axpy  : out_i[k] += scale * alpha[i] * src_i[k]  (out rows fp32) */
+int bess_row_sqnorm(int dtype, bess_rows_t rows, int n, int width, float* out, void* stream);
+int bess_l2_from_dot(float* score, bess_rowmap_t score_map, int64_t ld, int col0, int n_query,
+                     int n_cand, const float* q_sqnorm, const float* c_sqnorm, void* stream);
+int64_t bess_l2_coef_workspace(int n_query, int n_cand);
+int bess_l2_coef(const float* d_score, const float* score, bess_rowmap_t score_map, int64_t ld,
+                 int col0, int n_query, int n_cand, float* coef, int64_t ld_coef, float* row_sum,
+                 float* col_sum, void* workspace, void* stream);
+int bess_rows_axpy(int dtype, const float* alpha, float scale, bess_rows_t src, bess_rows_t out,
+                   int n, int width, void* stream);
+
 /* ------------------------------------------ per-triple negative scoring ---
  * negative_sample_sharing == False: reduce_embedding(v1.unsqueeze(1) - v2)
  * (scoring.py:199, 254): query q against its OWN n_per candidates; candidate

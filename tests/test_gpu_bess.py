@@ -239,3 +239,51 @@ def test_topk_query_given_candidates_vs_dense(fam, p, flat):
 
 
 K_BAD = -50000.0
+
+
+@pytest.mark.parametrize("fam,scheme", [("TransE", "t"), ("RotatE", "ht"), ("TransE", "h")])
+def test_l2_tensor_core_path_matches_tile_path_and_oracle(fam, scheme):
+    """norm-expanded L2 on the tcgen05 GEMM (csrc/l2.cu) == exact CUDA-core tile kernels == oracle
+    for one training step at a multi-tile shape (flat shared negatives, fp32)."""
+    B, H = _imports()
+    import besskge_b200.bess as bess_mod
+    from besskge_b200.bess import EmbeddingMovingBessKGE, training_model
+    from besskge_b200.optim import SGD
+    from besskge_b200.sharding import Sharding
+    n, p_part, Nn, d, n_rel, n_ent = 2, 80, 150, 24, 5, 900
+    sh = Sharding.create(n_ent, n, seed=3)
+    gen = torch.Generator().manual_seed(7)
+    ew = 2 if fam == "RotatE" else 1
+    ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen) * 0.5
+    rel = torch.randn(n_rel, d, generator=gen) * 0.5
+    Bn = 2 if scheme == "ht" else 1
+    lo = int(sh.shard_counts.min())
+    batch = dict(
+        head=torch.randint(lo, (n, n, p_part), generator=gen, dtype=torch.int32),
+        tail=torch.randint(lo, (n, n, p_part), generator=gen, dtype=torch.int32),
+        relation=torch.randint(n_rel, (n, n, p_part), generator=gen, dtype=torch.int32),
+        negative=torch.randint(lo, (n, n, Bn, Nn), generator=gen, dtype=torch.int32))
+    lcfg = dict(kind="logsigmoid", margin=6.0, negative_adversarial_sampling=True)
+    want = O.training_steps(H.score_cfg(fam, d, 2), H.oracle_loss_cfg(lcfg), dict(kind="sgd", lr=0.1),
+                            ent, rel, [batch], scheme, True, True, "mean")
+    got = {}
+    min_work = bess_mod.L2_TC_MIN_WORK
+    for flag in (True, False):
+        bess_mod.USE_L2_TENSOR_CORES = flag
+        bess_mod.L2_TC_MIN_WORK = 0  # the test shape is below the production threshold
+        try:
+            sf = H.make_score_fn(fam, True, 2, sh, n_rel, d, ent, rel)
+            model = EmbeddingMovingBessKGE(H.fake_sampler(scheme, True, triple_based=False), sf,
+                                           loss_fn=H.make_loss(lcfg), return_scores=True)
+            step = training_model(model, SGD(lr=0.1), cuda_graph=False)
+            res = step(**batch)
+            torch.cuda.synchronize()
+        finally:
+            bess_mod.USE_L2_TENSOR_CORES = True
+            bess_mod.L2_TC_MIN_WORK = min_work
+        got[flag] = (res["negative_score"].cpu(), res["loss"].cpu(),
+                     sf.entity_embedding.detach().cpu().clone(), sf.relation_embedding.detach().cpu().clone())
+        assert_close(got[flag][1], want["loss"][0], rtol=1e-5, atol=1e-3)
+        assert_close(got[flag][2], want["ent"], rtol=1e-5, atol=5e-6)
+        assert_close(got[flag][3], want["rel"], rtol=1e-5, atol=5e-6)
+    assert_close(got[True][0], got[False][0], rtol=1e-5, atol=2e-4)

@@ -392,3 +392,49 @@ def test_select_and_pairs_kernels():
     K.pairs_set(mat, None, pc.cuda(), vals.cuda())
     ref[torch.arange(50), pc.long()] = vals
     assert torch.equal(mat.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_l2_expansion_kernels(dtype):
+    """bess_row_sqnorm / bess_l2_from_dot / bess_l2_coef / bess_rows_axpy vs torch (fp64 reference)"""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(9)
+    nq, nc, W, ld, col0 = 70, 45, 40, 64, 8
+    q = torch.randn(nq, W, generator=g).to(dtype)
+    c = torch.randn(nc, W, generator=g).to(dtype)
+    dt = L.dtype_code(dtype)
+    qn = torch.empty(nq, device="cuda")
+    K.row_sqnorm(dt, L.rows(q.cuda()), nq, W, qn)
+    assert_close(qn.cpu().double(), (q.double() ** 2).sum(1), rtol=1e-6, atol=1e-6)
+    idx = torch.randperm(nc, generator=g).to(torch.int32)
+    cn = torch.empty(nc, device="cuda")
+    K.row_sqnorm(dt, L.rows(c.cuda(), idx=idx.cuda()), nc, W, cn)  # rows through an index list
+    assert_close(cn.cpu().double(), (c.double()[idx.long()] ** 2).sum(1), rtol=1e-6, atol=1e-6)
+    cs = c[idx.long()]
+    dots = (q.double() @ cs.double().T).float()
+    score = torch.full((nq, ld), 7.0)
+    score[:, col0:col0 + nc] = dots
+    score = score.cuda()
+    K.l2_from_dot(score, L.IDENT, ld, col0, nq, nc, qn, cn)
+    want = -torch.cdist(q.double(), cs.double())
+    assert_close(score.cpu()[:, col0:col0 + nc].double(), want, rtol=1e-5, atol=2e-4)
+    assert bool((score.cpu()[:, :col0] == 7.0).all())
+    # coefficient transform + sums
+    gs = torch.randn(nq, ld, generator=g)
+    sc = score.cpu().clone()
+    sc[3, col0 + 2] = 0.0  # zero distance -> coefficient 0
+    coef = torch.zeros(nq, 48, device="cuda")
+    rb, cb = torch.empty(nq, device="cuda"), torch.empty(nc, device="cuda")
+    ws = torch.empty(max(K.l2_coef_workspace(nq, nc) // 4, 1), device="cuda")
+    K.l2_coef(gs.cuda(), sc.cuda(), L.IDENT, ld, col0, nq, nc, coef, 48, rb, cb, ws)
+    s_blk, g_blk = sc[:, col0:col0 + nc], gs[:, col0:col0 + nc]
+    b = torch.where(s_blk != 0, -g_blk / s_blk, torch.zeros_like(g_blk))
+    assert_close(coef.cpu()[:, :nc], b, rtol=1e-6, atol=1e-7)
+    assert_close(rb.cpu(), b.sum(1), rtol=1e-5, atol=1e-5)
+    assert_close(cb.cpu(), b.sum(0), rtol=1e-5, atol=1e-5)
+    # out_i += scale * alpha_i * src_i
+    out = torch.randn(nc, W, generator=g)
+    alpha = torch.randn(nc, generator=g)
+    o = out.clone().cuda()
+    K.rows_axpy(dt, alpha.cuda(), -1.0, L.rows(c.cuda(), idx=idx.cuda()), L.rows(o), nc, W)
+    assert_close(o.cpu(), out - alpha[:, None] * cs.float(), rtol=1e-6, atol=1e-6)
