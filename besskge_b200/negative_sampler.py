@@ -95,7 +95,7 @@ class TypeBasedShardedNegativeSampler(RandomShardedNegativeSampler):
         n = sample_idx.shape[1]
         per_part = sample_idx.shape[-1]
         h_type, t_type = einops.rearrange(
-            self.triple_types[sample_idx], "... ht -> ht ..."
+            np.take(self.triple_types, sample_idx, axis=0), "... ht -> ht ..."
         )
         if self.corruption_scheme == "h":
             wanted = h_type
@@ -230,16 +230,18 @@ class TripleBasedShardedNegativeSampler(ShardedNegativeSampler):
             if self.flat_negative_format:
                 sample_idx = np.full(fill_value=0, shape=(*sample_idx.shape[:2], 1))
             ents = einops.rearrange(
-                self.padded_negatives[sample_idx], self.ent_rearrange_pattern
+                np.take(self.padded_negatives, sample_idx, axis=0), self.ent_rearrange_pattern
             )
-            mask = einops.rearrange(self.mask[sample_idx], self.mask_rearrange_pattern)
+            mask = einops.rearrange(
+                np.take(self.mask, sample_idx, axis=0), self.mask_rearrange_pattern
+            )
             if self.return_sort_idx:
                 pick = (
                     np.full(fill_value=0, shape=orig_shape)
                     if self.flat_negative_format
                     else sample_idx
                 )
-                sort_idx = self.sort_neg_idx[pick]
+                sort_idx = np.take(self.sort_neg_idx, pick, axis=0)
         else:  # "ht"
             cut = sample_idx.shape[-1] // 2
             if self.flat_negative_format:
@@ -266,18 +268,21 @@ class TripleBasedShardedNegativeSampler(ShardedNegativeSampler):
                 idx_t = sample_idx[..., cut:]
                 ents = einops.rearrange(
                     np.concatenate(
-                        [self.padded_negatives_h[idx_h], self.padded_negatives_t[idx_t]],
+                        [np.take(self.padded_negatives_h, idx_h, axis=0),
+                         np.take(self.padded_negatives_t, idx_t, axis=0)],
                         axis=-3,
                     ),
                     self.ent_rearrange_pattern,
                 )
                 mask = einops.rearrange(
-                    np.concatenate([self.mask_h[idx_h], self.mask_t[idx_t]], axis=-3),
+                    np.concatenate([np.take(self.mask_h, idx_h, axis=0),
+                                    np.take(self.mask_t, idx_t, axis=0)], axis=-3),
                     self.mask_rearrange_pattern,
                 )
             if self.return_sort_idx:
                 sort_idx = np.concatenate(
-                    [self.sort_neg_h_idx[idx_h], self.sort_neg_t_idx[idx_t]], axis=-2
+                    [np.take(self.sort_neg_h_idx, idx_h, axis=0),
+                     np.take(self.sort_neg_t_idx, idx_t, axis=0)], axis=-2
                 )
         out: SampleDict = dict(negative_entities=ents, negative_mask=mask)
         if self.return_sort_idx:
