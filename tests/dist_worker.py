@@ -50,6 +50,34 @@ def main() -> None:
     host = torch.arange(bps * n)
     mine = host[pl.rank::n]
     assert mine.tolist() == [s * n + rank for s in range(bps)]
+    # score-moving / all-scores exchange (bess.py:519-592, :1023-1060): queries are replicated
+    # with all_gather, every rank scores ALL n*S queries against ITS candidates, and
+    # all_to_all_single of the [n*S, X] local scores gives the owner of query (r, q) the block
+    # out[q, j, x] = score(query (r, q), candidate x of shard j)
+    S, X = 5, 3
+    q_mine = torch.arange(S, dtype=torch.float32) + 100.0 * rank  # this rank's queries
+    q_all = torch.empty(n * S)
+    dist.all_gather_into_tensor(q_all, q_mine)
+    assert torch.equal(q_all.view(n, S), torch.stack(
+        [torch.arange(S, dtype=torch.float32) + 100.0 * j for j in range(n)]))
+    cand_mine = torch.arange(X, dtype=torch.float32) * 0.25 + 10.0 * rank
+    sc_local = q_all.view(-1, 1) * 1000.0 + cand_mine.view(1, -1)  # [n*S, X]
+    sc_recv = torch.empty(n, S, X)
+    dist.all_to_all_single(sc_recv.view(-1), sc_local.contiguous().view(-1))
+    out = sc_recv.transpose(0, 1)  # [S, n, X]
+    for j in range(n):
+        want = q_mine.view(-1, 1) * 1000.0 + (torch.arange(X, dtype=torch.float32) * 0.25 + 10.0 * j)
+        assert torch.equal(out[:, j], want), f"rank {rank}: score block of shard {j} misrouted"
+    # AllScoresPipeline row selection in distributed mode: this rank keeps the valid rows of ITS
+    # shard, in (step, triple) order
+    tmask = (torch.arange(bps * n * 4).view(bps, n, 4) % 3) != 0
+    sel = tmask.clone()
+    own = torch.zeros_like(sel)
+    own[:, rank] = True
+    sel &= own
+    row_src = torch.nonzero(tmask[:, rank].reshape(-1)).reshape(-1)
+    flat_ids = torch.arange(bps * n * 4).view(bps, n, 4)
+    assert torch.equal(flat_ids[sel], flat_ids[:, rank].reshape(-1)[row_src])
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")
