@@ -19,6 +19,9 @@ MODE_TAILS, MODE_HEADS = 0, 1
 LOSS_LOGSIGMOID, LOSS_MARGIN_RANKING, LOSS_SOFTMAX_CE = 0, 1, 2
 OPT_SGD, OPT_SGDM, OPT_ADAMW = 0, 1, 2
 MAX_SHARD = 16
+(HYPER_LR, HYPER_MOMENTUM, HYPER_DAMPENING, HYPER_BETA1, HYPER_BETA2, HYPER_EPS, HYPER_WEIGHT_DECAY,
+ HYPER_BC1, HYPER_BC2, HYPER_FIRST_STEP) = range(10)
+HYPER_COUNT = 16
 
 
 class RowMap(C.Structure):
@@ -100,9 +103,12 @@ SIGNATURES = {
     "bess_rank_from_scores": [_P, _P, _I, _I, _L, _I, _I, _P, _P],
     "bess_sort_workspace": [_I],
     "bess_sort_keys": [_P, _I, _I, _P, _P, _P, _P],
-    "bess_scatter_sgd": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _P, _P, _L, _F, _P],
+    "bess_scatter_sgd": [_P, _L, _I, _I, _P, _P, _I, _I, _I, _P, _P, _L, _F, _P, _P],
     "bess_scatter_collect": [_I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P],
-    "bess_opt_dense": [_I, _P, _L, _I, _I, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P],
+    "bess_opt_dense": [_I, _P, _L, _I, _I, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _F, _I,
+                       _P],
+    "bess_scatter_accumulate": [_I, _P, _P, _I, _I, _I, _P, _P, _L, _P, _P],
+    "bess_set_hyper": [_P, _F, _F, _F, _F, _F, _F, _F, _I, _P],
     "bess_relation_grad_reduce": [_P, _I, _P, _P, _I, _I, _P, _P],
     "bess_topk_merge": [_P, _L, _I, _I, _P, _L, _I, _P, _P, _I, _P],
     "bess_topk_finalize": [_P, _P, _I, _I, _I, _P, _P, _I, _I, _F, _P, _P, _P],
@@ -110,9 +116,11 @@ SIGNATURES = {
     "bess_pairs_get": [_P, _L, _P, _P, _I, _P, _P],
     "bess_pairs_set": [_P, _L, _P, _P, _I, _P, _F, _P],
     "bess_peer_signal": [_P, C.POINTER(_P), _I, _I, _P],
-    "bess_peer_wait": [_P, _P, _I, _P],
+    "bess_peer_wait": [_P, _P, _I, _L, _P],
     "bess_peer_push": [_P, _L, C.POINTER(_P), _I, _L, _P],
     "bess_peer_reduce": [_P, _I, _L, _F, _P, _P],
+    "bess_take_along_rows": [_P, _I, _L, _I, _P, _I, _I, _P, _P],
+    "bess_complex_mul": [_I, _P, _P, _I, _I, _I, _P, _P],
     "bess_fill_f32": [_P, _L, _F, _P],
     "bess_fill_i32": [_P, _L, C.c_int32, _P],
     "bess_cast_from_f32": [_P, _P, _I, _L, _P],

@@ -16,9 +16,12 @@ Replica placement (the reference is single-controller with PopTorch replicas):
   * local mode      — all `n_shard` shards live on THIS process's GPU; the
     AllToAll is folded into the gather, which writes every row straight into
     the receive buffer of the replica that scores it;
-  * distributed mode — one process per GPU (`torch.distributed`, NCCL); this
-    process owns shard `rank`; the gather fills the send buffer and
-    `all_to_all_single` transposes the blocks over NVLink.
+  * distributed mode — one process per GPU (`torch.distributed` for rendezvous
+    and the symmetric-memory allocation); this process owns shard `rank`; the
+    gather kernel stores every tail / negative row straight into the
+    destination GPU's receive buffer over NVLink (peer-mapped pointers) and a
+    flag handshake replaces the collective (csrc/peer.cu).  NCCL
+    `all_to_all_single` remains selectable for A/B runs (`USE_PEER_EXCHANGE`).
 Inputs keep the reference layout: a leading `batches_per_step * n_shard` axis
 (step-major, shard-minor); outputs are concatenated in the same order
 (tests/test_bess.py:181-196 of the reference).
@@ -52,6 +55,10 @@ __all__ = [
     "EmbeddingMovingBessKGE",
     "ScoreMovingBessKGE",
     "TopKQueryBessKGE",
+    "AllScoresBESS",
+    "ScatterAllToAllBessKGE",
+    "AllScatterAllGatherBessKGE",
+    "TrainingModel",
     "training_model",
 ]
 
@@ -122,7 +129,11 @@ class _PeerExchange:
         self.sizes = (0, 0, 0)
         self.buf: Optional[torch.Tensor] = None
         self._keep: List[Any] = []
+        # sequence counters are monotonic for the life of the exchange: a re-allocation starts
+        # with zeroed flag rows, and every later signal carries a larger number than any earlier
+        # one, so graphs captured against an older (still mapped) buffer stay self-consistent
         self.counters = torch.zeros(3, dtype=torch.int32, device=device)
+        self.generation = 0  # moves on every re-allocation (captured graphs must be dropped)
 
     def ensure(self, tn_bytes: int, grad_bytes: int, rel_bytes: int) -> None:
         want = (_up(tn_bytes), _up(grad_bytes), _up(rel_bytes))
@@ -142,7 +153,7 @@ class _PeerExchange:
         buf = symm.empty(total, dtype=torch.uint8, device=self.device)
         hdl = symm.rendezvous(buf, group)
         buf.zero_()
-        self.counters.zero_()
+        self.generation += 1
         torch.cuda.synchronize(self.device)
         torch.distributed.barrier()  # nobody signals before every flag row is zero
         self._keep.append((self.buf, getattr(self, "hdl", None)))  # peers may still map it
@@ -300,6 +311,12 @@ class BessKGE(torch.nn.Module, ABC):
         self._placement: Optional[_Placement] = None
         self._px: Optional[_PeerExchange] = None
         self._opt_state: Dict[str, Any] = {}
+        # gradient accumulation over micro-batches (set by TrainingModel): an optimizer step is
+        # applied on every k-th micro-batch, `_accum_phase0` = position of the current call's
+        # first micro-batch in its cycle
+        self._accum_k = 1
+        self._accum_scale = 1.0
+        self._accum_phase0 = 0
 
     # ------------------------------------------------------------------ misc
     @property
@@ -329,6 +346,29 @@ class BessKGE(torch.nn.Module, ABC):
         if self._placement is None:
             self._placement = _Placement(self.sharding.n_shard)
         return self._ws, self._placement
+
+    def _hyper(self, bps: int) -> torch.Tensor:
+        """[bps, HYPER_COUNT] fp32 on the device: optimizer hyper-parameters of each
+        micro-batch of the current call (csrc/scatter.cu reads them, so they are not frozen
+        into a captured graph)."""
+        return self._ws.get("opt_hyper", (bps, L.HYPER_COUNT), torch.float32)
+
+    def _begin_steps(self, opt, bps: int) -> None:
+        """Advance the step counter by `bps` optimizer steps and write their
+        hyper-parameters (current lr / momentum / ..., Adam bias corrections of each step)
+        to the device array on the current stream — OUTSIDE any captured graph."""
+        self._setup()
+        hyper = self._hyper(bps)
+        b1, b2 = getattr(opt, "betas", (0.0, 0.0))
+        k = self._accum_k
+        self._accum_phase0 = self._opt_state.get("micro", 0) % k
+        for s in range(bps):
+            if (self._accum_phase0 + s) % k != k - 1:
+                continue  # gradients of this micro-batch are only accumulated
+            self._opt_state["step"] = self._opt_state.get("step", 0) + 1
+            K.set_hyper(hyper[s], opt.lr, opt.momentum, opt.dampening, b1, b2,
+                        getattr(opt, "eps", 0.0), opt.weight_decay, self._opt_state["step"])
+        self._opt_state["micro"] = self._opt_state.get("micro", 0) + bps
 
     def _side_stream(self, dev: torch.device) -> "torch.cuda.Stream":
         if getattr(self, "_side", None) is None or self._side.device != dev:
@@ -936,9 +976,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     px.handshake(1)
                 elif pl.distributed and px is None:
                     pl.all_to_all(dBACK, dTN[0])
-                self._opt_state.setdefault("step", 0)
-                self._opt_state["step"] += 1
-                step_no = self._opt_state["step"]
+                hyper = self._hyper(bps)[s]  # filled by TrainingModel before this call / replay
                 main = torch.cuda.current_stream(dev)
                 main.wait_stream(side)  # join: permutations ready (and the early gradient push)
                 # relation table (replicated): reduce per-query rows of all local replicas; its
@@ -962,17 +1000,37 @@ class EmbeddingMovingBessKGE(BessKGE):
                         torch.distributed.all_reduce(d_rel_table)
                     if mean and n > 1:
                         d_rel_table.mul_(1.0 / n)
+                acc_k = self._accum_k
+                acc_phase = (self._accum_phase0 + s) % acc_k
                 for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                     if pl.distributed:
                         g_dst, stride_rows = dBACK.data_ptr(), per
                     else:
                         g_dst = dTN.data_ptr() + li * per * W * 4
                         stride_rows = n * per
-                    self._update_entity(optimizer, ent[shard], shard, sk[li], sp[li], G, n_loc_rows, per,
-                                        dH[li], g_dst, stride_rows, step_no, ws)
+                    if acc_k > 1:
+                        self._accumulate_entity(optimizer, ent[shard], shard, sk[li], sp[li], G,
+                                                n_loc_rows, per, dH[li], g_dst, stride_rows, hyper,
+                                                acc_phase == acc_k - 1)
+                    else:
+                        self._update_entity(optimizer, ent[shard], shard, sk[li], sp[li], G,
+                                            n_loc_rows, per, dH[li], g_dst, stride_rows, hyper, ws)
                 if px is not None:
                     main.wait_stream(side)  # relation all-reduce done
-                self._update_relation(optimizer, rel_table, d_rel_table, step_no, ws)
+                if acc_k > 1:
+                    # relation table: one slot per micro-batch of the cycle, summed in slot
+                    # order on the last one (deterministic), then one optimizer step
+                    cnt = d_rel_table.numel()
+                    slots = self._opt_state.get("rel_acc")
+                    if slots is None or slots.shape != (acc_k, cnt):
+                        slots = self._opt_state["rel_acc"] = torch.zeros(
+                            acc_k, cnt, dtype=torch.float32, device=dev)
+                    slots[acc_phase].copy_(d_rel_table.view(-1))
+                    if acc_phase == acc_k - 1:
+                        K.peer_reduce(slots, acc_k, cnt, self._accum_scale, d_rel_table)
+                        self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
+                else:
+                    self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
 
         out: Dict[str, Any] = {}
         if want_scores:
@@ -1025,11 +1083,11 @@ class EmbeddingMovingBessKGE(BessKGE):
             K.mask_add(neg, S, width, N, m, width, m.shape[0], False, BAD_NEGATIVE_SCORE, col_off)
 
     def _update_entity(self, opt, table: torch.Tensor, shard: int, sk, sp, G: int, n_local: int,
-                       per: int, dH_l: torch.Tensor, g_dst: int, stride_rows: int, step_no: int,
-                       ws: K.Workspace) -> None:
+                       per: int, dH_l: torch.Tensor, g_dst: int, stride_rows: int,
+                       hyper: torch.Tensor, ws: K.Workspace) -> None:
         W = table.shape[1]
         if opt.sparse_exact:
-            K.scatter_sgd(table, sk, sp, G, n_local, per, dH_l, g_dst, stride_rows, opt.lr)
+            K.scatter_sgd(table, sk, sp, G, n_local, per, dH_l, g_dst, stride_rows, opt.lr, hyper)
             return
         seg = ws.get("seg_grad", (G, W), torch.float32)
         r2s = ws.get(f"row_to_seg", (table.shape[0],), torch.int32)
@@ -1039,23 +1097,47 @@ class EmbeddingMovingBessKGE(BessKGE):
         key0, key1 = f"ent_s0_{shard}", f"ent_s1_{shard}"
         if key0 not in st:
             st[key0] = torch.zeros(table.shape[0], W, dtype=torch.float32, device=table.device)
-            if opt.kind == L.OPT_ADAMW:
-                st[key1] = torch.zeros_like(st[key0])
+        if opt.kind == L.OPT_ADAMW and key1 not in st:
+            st[key1] = torch.zeros_like(st[key0])
         b1, b2 = getattr(opt, "betas", (0.0, 0.0))
         K.opt_dense(opt.kind, table, seg, r2s, st[key0], st.get(key1), opt.lr, opt.momentum,
-                    opt.dampening, b1, b2, getattr(opt, "eps", 0.0), opt.weight_decay, step_no)
+                    opt.dampening, b1, b2, getattr(opt, "eps", 0.0), opt.weight_decay, 1, hyper)
 
-    def _update_relation(self, opt, rel_table: torch.Tensor, d_rel: torch.Tensor, step_no: int,
-                         ws: K.Workspace) -> None:
+    def _accumulate_entity(self, opt, table: torch.Tensor, shard: int, sk, sp, G: int,
+                           n_local: int, per: int, dH_l: torch.Tensor, g_dst: int,
+                           stride_rows: int, hyper: torch.Tensor, apply: bool) -> None:
+        """Gradient accumulation: add this micro-batch's segment sums to the dense fp32
+        accumulator of the shard; on the last micro-batch of the cycle one dense optimizer pass
+        consumes (and clears) it.  Rows without gradient see g = 0, so plain SGD stays exact."""
+        W = table.shape[1]
+        st = self._opt_state
+        key = f"ent_acc_{shard}"
+        if key not in st:
+            st[key] = torch.zeros(table.shape[0], W, dtype=torch.float32, device=table.device)
+        K.scatter_accumulate(W, sk, sp, G, n_local, per, dH_l, g_dst, stride_rows, st[key])
+        if not apply:
+            return
+        key0, key1 = f"ent_s0_{shard}", f"ent_s1_{shard}"
+        if opt.kind != L.OPT_SGD and key0 not in st:
+            st[key0] = torch.zeros_like(st[key])
+        if opt.kind == L.OPT_ADAMW and key1 not in st:
+            st[key1] = torch.zeros_like(st[key])
+        b1, b2 = getattr(opt, "betas", (0.0, 0.0))
+        K.opt_dense(opt.kind, table, st[key], None, st.get(key0), st.get(key1), opt.lr,
+                    opt.momentum, opt.dampening, b1, b2, getattr(opt, "eps", 0.0),
+                    opt.weight_decay, 1, hyper, grad_scale=self._accum_scale, zero_grad=True)
+
+    def _update_relation(self, opt, rel_table: torch.Tensor, d_rel: torch.Tensor,
+                         hyper: torch.Tensor, ws: K.Workspace) -> None:
         st = self._opt_state
         if opt.kind != L.OPT_SGD and "rel_s0" not in st:
             st["rel_s0"] = torch.zeros_like(d_rel)
-            if opt.kind == L.OPT_ADAMW:
-                st["rel_s1"] = torch.zeros_like(d_rel)
+        if opt.kind == L.OPT_ADAMW and "rel_s1" not in st:
+            st["rel_s1"] = torch.zeros_like(d_rel)
         b1, b2 = getattr(opt, "betas", (0.0, 0.0))
         K.opt_dense(opt.kind, rel_table, d_rel, None, st.get("rel_s0"), st.get("rel_s1"), opt.lr,
                     opt.momentum, opt.dampening, b1, b2, getattr(opt, "eps", 0.0),
-                    opt.weight_decay, step_no)
+                    opt.weight_decay, 1, hyper)
 
 
 # ---------------------------------------------------------------------------
@@ -1255,26 +1337,45 @@ class TrainingModel:
     """Callable returned by `training_model`: one call = `batches_per_step`
     fused forward + backward + optimizer steps; returns the forward dict.
 
-    With `cuda_graph=True` (default for SGD / SGD-momentum) the whole device
-    sequence of a call — gather, exchange, scoring, loss, backward, sort,
-    scatter + update — is captured once per input signature into a CUDA graph
-    and replayed: the B200 counterpart of PopTorch's `deviceIterations` loop
-    (one host launch per call instead of ~40 kernel launches).  The first call
-    with a new signature runs eagerly (it sizes the persistent workspaces), the
-    second is captured.  The returned tensors are then STATIC buffers that the
-    next call overwrites."""
+    With `cuda_graph=True` (the default) the whole device sequence of a call —
+    gather, exchange, scoring, loss, backward, sort, scatter + update — is
+    captured once per input signature into a CUDA graph and replayed: the B200
+    counterpart of PopTorch's `deviceIterations` loop (one host launch per call
+    instead of ~40 kernel launches).  The first call with a new signature runs
+    eagerly (it sizes the persistent workspaces), the second is captured.  The
+    returned tensors are then STATIC buffers that the next call overwrites.
+
+    What a captured graph does NOT freeze:
+      * optimizer hyper-parameters — `optimizer.lr` (and momentum, weight decay, betas, eps)
+        are re-read on every call and handed to the kernels through a small device array, as
+        is the step count of AdamW's bias correction, so learning-rate schedules work;
+      * buffer addresses — whenever a persistent workspace buffer or the symmetric-memory
+        exchange buffer is re-allocated (a larger batch, another dtype, a validation
+        `model.forward()` on the same module) every captured graph is dropped and re-captured
+        on its next use; replaced buffers stay allocated until then.
+
+    Optimizer state (step count, momentum / Adam moments of the local shards and of the
+    relation table) is exposed through `state_dict()` / `load_state_dict()`."""
 
     def __init__(self, model: BessKGE, optimizer: Union[SGD, AdamW],
-                 relation_grad_reduction: str = "mean", cuda_graph: Optional[bool] = None) -> None:
+                 relation_grad_reduction: str = "mean", cuda_graph: Optional[bool] = None,
+                 gradient_accumulation: int = 1, accumulation_reduction: str = "mean") -> None:
         if relation_grad_reduction not in ("mean", "sum"):
             raise ValueError("relation_grad_reduction must be 'mean' or 'sum'")
+        if accumulation_reduction not in ("mean", "sum"):
+            raise ValueError("accumulation_reduction must be 'mean' or 'sum'")
+        if gradient_accumulation < 1:
+            raise ValueError("gradient_accumulation must be >= 1")
+        model._accum_k = int(gradient_accumulation)
+        model._accum_scale = (1.0 / gradient_accumulation if accumulation_reduction == "mean"
+                              else 1.0)
         self.model = model
         self.optimizer = optimizer
         self.optimizer.relation_grad_reduction = relation_grad_reduction
-        # AdamW's bias correction takes the step count by value: not replayable
-        graph_ok = optimizer.kind != L.OPT_ADAMW and isinstance(model, EmbeddingMovingBessKGE)
+        graph_ok = isinstance(model, EmbeddingMovingBessKGE)
         self.cuda_graph = graph_ok if cuda_graph is None else (bool(cuda_graph) and graph_ok)
         self._graphs: Dict[Any, Any] = {}
+        self._graph_gen: Optional[Tuple[int, int, int]] = None
 
     def _use_graph(self) -> bool:
         # NCCL collectives inside a captured step hung on 2 x B200 (NCCL 2.28.9, torch 2.11);
@@ -1283,12 +1384,9 @@ class TrainingModel:
 
     def __call__(self, head, relation, tail, negative, triple_mask=None, triple_weight=None,
                  negative_mask=None) -> Dict[str, Any]:
-        if not self._use_graph():
-            return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
-                                   negative_mask, optimizer=self.optimizer)
         staged = self.model.stage(head, relation, tail, negative, triple_mask, triple_weight,
                                   negative_mask)  # H2D into the persistent input buffers
-        return self._run_graphed(staged)
+        return self._run(staged)
 
     def stage(self, **batch) -> _Staged:
         """Copy a batch to the device once; see `run_staged`."""
@@ -1297,38 +1395,86 @@ class TrainingModel:
     def run_staged(self, staged: _Staged) -> Dict[str, Any]:
         """Training step(s) on inputs that are already resident in HBM."""
         if not self._use_graph():
-            return self.model._run(None, None, None, None, None, None, None,
-                                   optimizer=self.optimizer, staged=staged)
-        return self._run_graphed(self.model._restage(staged))
+            return self._run(staged)
+        return self._run(self.model._restage(staged))
 
-    def _run_graphed(self, staged: _Staged) -> Dict[str, Any]:
+    def _eager(self, staged: _Staged) -> Dict[str, Any]:
+        return self.model._run(None, None, None, None, None, None, None,
+                               optimizer=self.optimizer, staged=staged)
+
+    def _generation(self) -> Tuple[int, int, int]:
+        m = self.model
+        return (id(m._ws), m._ws.generation, m._px.generation if m._px is not None else 0)
+
+    def _run(self, staged: _Staged) -> Dict[str, Any]:
+        bps = staged.dims[0] // staged.dims[1]
+        self.model._begin_steps(self.optimizer, bps)
+        if not self._use_graph():
+            return self._eager(staged)
+        o = self.optimizer
         key = (staged.dims, staged.tw is not None, staged.nmask is not None,
-               staged.tmask is not None, self.model.score_fn.entity_embedding.dtype)
+               staged.tmask is not None, self.model.score_fn.entity_embedding.dtype,
+               o.kind, bool(o.sparse_exact), self.model._accum_phase0)
+        if self._graph_gen != self._generation():
+            # a buffer some captured graph points into was replaced: drop every graph (their
+            # old buffers were kept alive until now) and start over
+            self._graphs.clear()
+            self.model._ws.release_retired()
+            self._graph_gen = self._generation()
         entry = self._graphs.get(key)
-        if entry is None or entry == "warm":
-            if entry is None:
-                self._graphs[key] = "warm"
-                return self.model._run(None, None, None, None, None, None, None,
-                                       optimizer=self.optimizer, staged=staged)
+        if entry is None:
+            self._graphs[key] = "warm"
+            return self._eager(staged)
+        if entry == "warm":
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(graph):
-                out = self.model._run(None, None, None, None, None, None, None,
-                                      optimizer=self.optimizer, staged=staged)
-            entry = self._graphs[key] = (graph, out)
+                out = self._eager(staged)
+            if self._graph_gen != self._generation():  # sized differently than the warm run
+                self._graphs.clear()
+                self._graph_gen = None
+                return out
+            self._graphs[key] = (graph, out)
+            return out
         graph, out = entry
         graph.replay()
         return out
 
+    # ---- optimizer state -------------------------------------------------------
+    def state_dict(self) -> Dict[str, Any]:
+        """Optimizer state of THIS process: `step` and fp32 tensors `ent_s0_<shard>` /
+        `ent_s1_<shard>` (momentum buffer or Adam m / v of each local shard) and `rel_s0` /
+        `rel_s1` (relation table), cloned."""
+        return {k: (v.clone() if isinstance(v, torch.Tensor) else v)
+                for k, v in self.model._opt_state.items()}
+
+    def load_state_dict(self, state: Dict[str, Any]) -> None:
+        st = self.model._opt_state
+        dev = self.model._device()
+        for k, v in state.items():
+            if isinstance(v, torch.Tensor):
+                if k in st and st[k].shape == v.shape:
+                    st[k].copy_(v)  # in place: captured graphs keep pointing at it
+                else:
+                    st[k] = v.to(device=dev, dtype=torch.float32).clone()
+                    self._graphs.clear()
+            else:
+                st[k] = v
+
 
 def training_model(model: BessKGE, optimizer: Union[SGD, AdamW],
                    relation_grad_reduction: str = "mean",
-                   cuda_graph: Optional[bool] = None) -> TrainingModel:
+                   cuda_graph: Optional[bool] = None, gradient_accumulation: int = 1,
+                   accumulation_reduction: str = "mean") -> TrainingModel:
     """Counterpart of `poptorch.trainingModel(model, options, optimizer)`
     (reference notebooks, e.g. 1_biokg cell 28).  `relation_grad_reduction`:
     how the replicated relation table's gradient is combined over replicas
-    ("mean" = PopTorch default, "sum")."""
-    return TrainingModel(model, optimizer, relation_grad_reduction, cuda_graph)
+    ("mean" = PopTorch default, "sum").  `gradient_accumulation = k`
+    (`options.Training.gradientAccumulation(k)`, notebook 1 cell 26): gradients of k
+    consecutive micro-batches — all computed from the same weights — are accumulated and
+    combined by `accumulation_reduction` before one optimizer step."""
+    return TrainingModel(model, optimizer, relation_grad_reduction, cuda_graph,
+                         gradient_accumulation, accumulation_reduction)
 
 
 class TopKQueryBessKGE(torch.nn.Module):
@@ -1807,3 +1953,18 @@ class AllScoresBESS(torch.nn.Module):
         fixed, rel, L_rows, S = self._queries(relation, head, tail)
         Es = self.sharding.max_entity_per_shard
         return self._score(rel, fixed, L_rows, S, [(0, Es)], clamp_to=0)
+
+
+# ---------------------------------------------------------------------------
+# Names used by BASELINE.json's north_star.  The reference has no classes called
+# `ScatterAllToAllBessKGE` / `AllScatterAllGatherBessKGE` (its distribution schemes are
+# EmbeddingMovingBessKGE, bess.py:308, and ScoreMovingBessKGE, bess.py:471 — SURVEY.md §0);
+# the names describe those two schemes by their collectives and are exported as plain aliases,
+# with no semantics of their own:
+#   * ScatterAllToAll       — gathered tail / negative rows are scattered to the shard that
+#                             scores them with one balanced AllToAll  = EmbeddingMovingBessKGE;
+#   * AllScatterAllGather   — queries are AllGathered, negatives are scored where they are
+#                             stored and the scores travel back       = ScoreMovingBessKGE.
+# ---------------------------------------------------------------------------
+ScatterAllToAllBessKGE = EmbeddingMovingBessKGE
+AllScatterAllGatherBessKGE = ScoreMovingBessKGE

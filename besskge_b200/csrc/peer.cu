@@ -15,7 +15,8 @@
 // memory) and a local int32 sequence counter.  signal: seq = ++counter, then
 // flag[my_rank] on every peer := seq with release semantics at system scope.
 // wait: spin (acquire, system scope) until all n local flags >= counter.
-// Waits are bounded: a missing peer traps the launch instead of hanging the GPU.
+// Waits are bounded in wall-clock time (caller-chosen, minutes by default): a peer that never
+// arrives traps the launch instead of hanging the GPU for ever.
 #include <cstdio>
 
 #include "common.cuh"
@@ -48,14 +49,27 @@ __global__ void peer_signal_kernel(int32_t* counter, PeerPtrs peer_flags, int my
   }
 }
 
-__global__ void peer_wait_kernel(const int32_t* counter, const int32_t* my_flags, int n) {
+BESS_D uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Bounded spin on wall-clock time (%globaltimer, nanoseconds: independent of the SM clock).
+// timeout_ns <= 0 waits for ever.  On expiry the launch reports which peer is missing and
+// traps: continuing would score / update with rows that never arrived.
+__global__ void peer_wait_kernel(const int32_t* counter, const int32_t* my_flags, int n,
+                                 int64_t timeout_ns) {
   const int32_t expected = *counter;
   if ((int)threadIdx.x < n) {
-    const long long t0 = clock64();
+    const uint64_t t0 = globaltimer_ns();
+    unsigned spins = 0;
     while (ld_acquire_sys(my_flags + threadIdx.x) < expected) {
-      if (clock64() - t0 > 20000000000LL) {  // ~10 s
-        printf("besskge_b200 peer_wait: rank flag %d stuck at %d, expected %d\n", (int)threadIdx.x,
-               ld_acquire_sys(my_flags + threadIdx.x), expected);
+      if (timeout_ns > 0 && (++spins & 1023u) == 0 &&
+          globaltimer_ns() - t0 > (uint64_t)timeout_ns) {
+        printf("besskge_b200 peer_wait: flag of rank %d stuck at %d, expected %d after %lld ms "
+               "(BESS_PEER_TIMEOUT_S)\n", (int)threadIdx.x, ld_acquire_sys(my_flags + threadIdx.x),
+               expected, (long long)(timeout_ns / 1000000));
         __trap();
       }
     }
@@ -109,9 +123,11 @@ extern "C" int bess_peer_signal(int32_t* counter, void* const* peer_flags, int m
   return BESS_OK;
 }
 
-extern "C" int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n, void* stream) {
+extern "C" int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n,
+                              int64_t timeout_ms, void* stream) {
   BESS_CHECK_ARG(n >= 1 && n <= 32, "bess_peer_wait: n=%d out of range", n);
-  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, my_flags, n);
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, my_flags, n,
+                                                      timeout_ms * 1000000LL);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

@@ -86,6 +86,53 @@ __global__ void __launch_bounds__(256) gather_route_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// Python-surface helpers of the reference's utils.py.
+// take_along_rows: out[i, j] = x[i or 0, index[i or 0, j]] (utils.py:10-33, a 2-D
+// take-along-dim written there as a flat index_select).  Elements are opaque 1/2/4/8-byte words.
+// complex_mul: rows hold [re | im] halves; out = v1 * v2 (utils.py:72-89) or, with
+// rotate, v1 * (cos r + i sin r) for a row of e angles (utils.py:92-112, full-precision
+// sin / cos: the fp16 shortcut there applies to IPU devices only).
+// ---------------------------------------------------------------------------
+template <typename U>
+__global__ void __launch_bounds__(256) take_along_rows_kernel(const U* __restrict__ x, int a,
+                                                               int64_t e,
+                                                               const int32_t* __restrict__ index,
+                                                               int b, int k, int n_out,
+                                                               U* __restrict__ out) {
+  const int64_t total = (int64_t)n_out * k;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / k), j = (int)(t - (int64_t)i * k);
+    const int col = __ldg(index + (int64_t)(b == 1 ? 0 : i) * k + j);
+    out[t] = x[(int64_t)(a == 1 ? 0 : i) * e + col];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) complex_mul_kernel(const T* __restrict__ v1,
+                                                           const T* __restrict__ v2, int n, int e,
+                                                           int rotate, T* __restrict__ out) {
+  const int64_t total = (int64_t)n * e;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / e), j = (int)(t - (int64_t)i * e);
+    const float a_re = ldf(v1 + (int64_t)i * 2 * e + j), a_im = ldf(v1 + (int64_t)i * 2 * e + e + j);
+    float b_re, b_im;
+    if (rotate) {
+      sincosf(ldf(v2 + (int64_t)i * e + j), &b_im, &b_re);
+      // the reference rounds cos / sin to the tensor dtype before the product
+      b_re = Elem<T>::to_f(Elem<T>::from_f(b_re));
+      b_im = Elem<T>::to_f(Elem<T>::from_f(b_im));
+    } else {
+      b_re = ldf(v2 + (int64_t)i * 2 * e + j);
+      b_im = ldf(v2 + (int64_t)i * 2 * e + e + j);
+    }
+    out[(int64_t)i * 2 * e + j] = Elem<T>::from_f(a_re * b_re - a_im * b_im);
+    out[(int64_t)i * 2 * e + e + j] = Elem<T>::from_f(a_re * b_im + a_im * b_re);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // score_triple
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -263,6 +310,31 @@ extern "C" int bess_gather_rows(const void* table, int64_t table_pitch, int dtyp
                            stream);
 }
 
+static inline int stream_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > (int64_t)kNumSM * 8) b = (int64_t)kNumSM * 8;
+  return b < 1 ? 1 : (int)b;
+}
+
+extern "C" int bess_take_along_rows(const void* x, int a, int64_t e, int elem_bytes,
+                                    const int32_t* index, int b, int k, void* out, void* stream) {
+  BESS_CHECK_ARG(a >= 1 && b >= 1 && (a == 1 || b == 1 || a == b),
+                 "bess_take_along_rows: x has %d rows, index %d (need equal, or one of them 1)", a, b);
+  const int n_out = a > b ? a : b;
+  if (k == 0) return BESS_OK;
+  const int blocks = stream_blocks((int64_t)n_out * k);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (elem_bytes) {
+    case 1: take_along_rows_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)x, a, e, index, b, k, n_out, (uint8_t*)out); break;
+    case 2: take_along_rows_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t*)x, a, e, index, b, k, n_out, (uint16_t*)out); break;
+    case 4: take_along_rows_kernel<uint32_t><<<blocks, 256, 0, st>>>((const uint32_t*)x, a, e, index, b, k, n_out, (uint32_t*)out); break;
+    case 8: take_along_rows_kernel<uint64_t><<<blocks, 256, 0, st>>>((const uint64_t*)x, a, e, index, b, k, n_out, (uint64_t*)out); break;
+    default: bess_set_error("bess_take_along_rows: element size %d", elem_bytes); return BESS_ERR_INVALID_ARG;
+  }
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
 #define DISPATCH_DTYPE(dtype, ...)                                   \
   switch (dtype) {                                                   \
     case BESS_F32: { using T = float; __VA_ARGS__; break; }          \
@@ -272,6 +344,17 @@ extern "C" int bess_gather_rows(const void* table, int64_t table_pitch, int dtyp
   }
 
 static inline dim3 warp_grid(int n_rows) { return dim3(ceil_div((int64_t)n_rows * 32, 256)); }
+
+extern "C" int bess_complex_mul(int dtype, const void* v1, const void* v2, int n, int e, int rotate,
+                                void* out, void* stream) {
+  if (n == 0 || e == 0) return BESS_OK;
+  const int blocks = stream_blocks((int64_t)n * e);
+  DISPATCH_DTYPE(dtype, complex_mul_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                            static_cast<const T*>(v1), static_cast<const T*>(v2), n, e, rotate,
+                            static_cast<T*>(out)));
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
 
 extern "C" int bess_score_triple_fwd(const bess_score_cfg_t* cfg, int dtype, bess_rows_t head,
                                      bess_rows_t tail, const void* rel_table,

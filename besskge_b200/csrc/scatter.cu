@@ -177,15 +177,18 @@ BESS_D void segment_apply_sgd<__nv_bfloat16>(__nv_bfloat16* row, const float4& s
   *reinterpret_cast<uint2*>(row) = raw;
 }
 
-// MODE 0: SGD update of the table row; MODE 1: store the segment sum
+// MODE 0: SGD update of the table row; MODE 1: store the segment sum; MODE 2: add the segment
+// sum to row `key` of a dense fp32 accumulator (gradient accumulation over micro-batches: one
+// warp owns a key, so the += needs no atomics and the result is bit-reproducible)
 template <int MODE, typename T>
 __global__ void __launch_bounds__(256) segment_kernel(T* table, int64_t pitch,
                                                        const int32_t* sorted_keys,
                                                        const int32_t* perm, int n, GradSrc g,
-                                                       float lr, float* seg_grad,
-                                                       int32_t* row_to_seg) {
+                                                       float lr, const float* hyper,
+                                                       float* seg_grad, int32_t* row_to_seg) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= n) return;
+  if (MODE == 0 && hyper != nullptr) lr = __ldg(hyper + BESS_HYPER_LR);
   const int lane = threadIdx.x & 31;
   const int key = sorted_keys[wid];
   if (wid > 0 && sorted_keys[wid - 1] == key) return;  // not a run head
@@ -210,6 +213,17 @@ __global__ void __launch_bounds__(256) segment_kernel(T* table, int64_t pitch,
     if (MODE == 0) {
       segment_apply_sgd<T>(table + (int64_t)key * pitch + k0, s, lr);
       if (two) segment_apply_sgd<T>(table + (int64_t)key * pitch + k1, t, lr);
+    } else if (MODE == 2) {
+      float4* a0 = reinterpret_cast<float4*>(seg_grad + (int64_t)key * W + k0);
+      float4 c = *a0;
+      c.x += s.x; c.y += s.y; c.z += s.z; c.w += s.w;
+      *a0 = c;
+      if (two) {
+        float4* a1 = reinterpret_cast<float4*>(seg_grad + (int64_t)key * W + k1);
+        float4 e = *a1;
+        e.x += t.x; e.y += t.y; e.z += t.z; e.w += t.w;
+        *a1 = e;
+      }
     } else {
       *reinterpret_cast<float4*>(seg_grad + (int64_t)wid * W + k0) = s;
       if (two) *reinterpret_cast<float4*>(seg_grad + (int64_t)wid * W + k1) = t;
@@ -218,40 +232,152 @@ __global__ void __launch_bounds__(256) segment_kernel(T* table, int64_t pitch,
 }
 
 // Dense optimizer pass (torch.optim.SGD with momentum / AdamW semantics).
+// Hyper-parameters come by value or, when `hyper` is non-null, from a small device array
+// (BESS_HYPER_* slots) that the host rewrites before every replay of a captured step, so a
+// learning-rate schedule and Adam's bias correction survive CUDA-graph capture.
+struct OptHyper {
+  float lr, momentum, dampening, beta1, beta2, eps, wd, bc1, bc2;
+  int first_step;
+};
+BESS_D OptHyper load_hyper(OptHyper h, const float* hyper) {
+  if (hyper != nullptr) {
+    h.lr = __ldg(hyper + BESS_HYPER_LR); h.momentum = __ldg(hyper + BESS_HYPER_MOMENTUM);
+    h.dampening = __ldg(hyper + BESS_HYPER_DAMPENING); h.beta1 = __ldg(hyper + BESS_HYPER_BETA1);
+    h.beta2 = __ldg(hyper + BESS_HYPER_BETA2); h.eps = __ldg(hyper + BESS_HYPER_EPS);
+    h.wd = __ldg(hyper + BESS_HYPER_WEIGHT_DECAY); h.bc1 = __ldg(hyper + BESS_HYPER_BC1);
+    h.bc2 = __ldg(hyper + BESS_HYPER_BC2);
+    h.first_step = __ldg(hyper + BESS_HYPER_FIRST_STEP) != 0.f;
+  }
+  return h;
+}
+BESS_D float opt_update(int kind, const OptHyper& h, float wv, float gval, float& s0, float& s1) {
+  if (kind == BESS_OPT_SGD) {
+    gval += h.wd * wv;
+    wv -= h.lr * gval;
+  } else if (kind == BESS_OPT_SGDM) {
+    gval += h.wd * wv;
+    const float b = h.first_step ? gval : h.momentum * s0 + (1.f - h.dampening) * gval;
+    s0 = b;
+    wv -= h.lr * b;
+  } else {  // AdamW (decoupled weight decay), torch.optim.AdamW
+    wv *= 1.f - h.lr * h.wd;
+    const float m = h.beta1 * s0 + (1.f - h.beta1) * gval;
+    const float v = h.beta2 * s1 + (1.f - h.beta2) * gval * gval;
+    s0 = m; s1 = v;
+    const float denom = sqrtf(v) / sqrtf(h.bc2) + h.eps;
+    wv -= (h.lr / h.bc1) * (m / denom);
+  }
+  return wv;
+}
+
 template <typename T>
+struct Vec4;  // 4 table elements as one 128-bit (fp32) / 64-bit (half) access
+template <>
+struct Vec4<float> {
+  static BESS_D void load(const float* p, float (&w)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  }
+  static BESS_D void store(float* p, const float (&w)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct Vec4<__half> {
+  static BESS_D void load(const __half* p, float (&w)[4]) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+  }
+  static BESS_D void store(__half* p, const float (&w)[4]) {
+    uint2 raw;
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+    h[0] = __halves2half2(__float2half_rn(w[0]), __float2half_rn(w[1]));
+    h[1] = __halves2half2(__float2half_rn(w[2]), __float2half_rn(w[3]));
+    *reinterpret_cast<uint2*>(p) = raw;
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static BESS_D void load(const __nv_bfloat16* p, float (&w)[4]) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+  }
+  static BESS_D void store(__nv_bfloat16* p, const float (&w)[4]) {
+    uint2 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+    h[0] = __halves2bfloat162(__float2bfloat16_rn(w[0]), __float2bfloat16_rn(w[1]));
+    h[1] = __halves2bfloat162(__float2bfloat16_rn(w[2]), __float2bfloat16_rn(w[3]));
+    *reinterpret_cast<uint2*>(p) = raw;
+  }
+};
+
+// VEC: 4 elements per thread with 128-bit state / gradient accesses (rows a multiple of 4
+// elements, 16-byte aligned); otherwise one element per thread.  Warp-coalesced along the
+// row: a pure HBM stream of table (s) + state (4 / 8) bytes per element, read + write.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) opt_dense_kernel(int kind, T* table, int64_t pitch,
                                                          int n_rows, int W, const float* seg_grad,
                                                          const int32_t* row_to_seg, float* state0,
-                                                         float* state1, float lr, float momentum,
-                                                         float dampening, float beta1, float beta2,
-                                                         float eps, float wd, float bc1, float bc2,
-                                                         int first_step) {
-  const int64_t total = (int64_t)n_rows * W;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int row = (int)(t / W), k = (int)(t - (int64_t)row * W);
-    const int seg = row_to_seg != nullptr ? row_to_seg[row] : row;
-    float gval = seg >= 0 ? seg_grad[(int64_t)seg * W + k] : 0.f;
-    T* pw = table + (int64_t)row * pitch + k;
-    float wv = Elem<T>::to_f(*pw);
-    if (kind == BESS_OPT_SGD) {
-      gval += wd * wv;
-      wv -= lr * gval;
-    } else if (kind == BESS_OPT_SGDM) {
-      gval += wd * wv;
-      float b = first_step ? gval : momentum * state0[t] + (1.f - dampening) * gval;
-      state0[t] = b;
-      wv -= lr * b;
-    } else {  // AdamW (decoupled weight decay), torch.optim.AdamW
-      wv *= 1.f - lr * wd;
-      const float m = beta1 * state0[t] + (1.f - beta1) * gval;
-      const float v = beta2 * state1[t] + (1.f - beta2) * gval * gval;
-      state0[t] = m; state1[t] = v;
-      const float denom = sqrtf(v) / sqrtf(bc2) + eps;
-      wv -= (lr / bc1) * (m / denom);
+                                                         float* state1, OptHyper hv,
+                                                         const float* hyper, float grad_scale,
+                                                         float* zero_grad) {
+  const OptHyper h = load_hyper(hv, hyper);
+  if (VEC) {
+    const int W4 = W >> 2;
+    const int64_t total = (int64_t)n_rows * W4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+      const int row = (int)(t / W4), k = (int)(t - (int64_t)row * W4) << 2;
+      const int seg = row_to_seg != nullptr ? __ldg(row_to_seg + row) : row;
+      float g[4] = {0.f, 0.f, 0.f, 0.f}, w[4], s0[4] = {0.f, 0.f, 0.f, 0.f},
+            s1[4] = {0.f, 0.f, 0.f, 0.f};
+      if (seg >= 0) Vec4<float>::load(seg_grad + (int64_t)seg * W + k, g);
+      if (zero_grad != nullptr) {  // dense accumulator: consumed, cleared for the next cycle
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        Vec4<float>::store(zero_grad + (int64_t)seg * W + k, z);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] *= grad_scale;
+      T* pw = table + (int64_t)row * pitch + k;
+      Vec4<T>::load(pw, w);
+      const int64_t so = (int64_t)row * W + k;
+      if (kind != BESS_OPT_SGD && !(kind == BESS_OPT_SGDM && h.first_step))
+        Vec4<float>::load(state0 + so, s0);
+      if (kind == BESS_OPT_ADAMW) Vec4<float>::load(state1 + so, s1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = opt_update(kind, h, w[i], g[i], s0[i], s1[i]);
+      Vec4<T>::store(pw, w);
+      if (kind != BESS_OPT_SGD) Vec4<float>::store(state0 + so, s0);
+      if (kind == BESS_OPT_ADAMW) Vec4<float>::store(state1 + so, s1);
     }
-    *pw = Elem<T>::from_f(wv);
+  } else {
+    const int64_t total = (int64_t)n_rows * W;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+      const int row = (int)(t / W), k = (int)(t - (int64_t)row * W);
+      const int seg = row_to_seg != nullptr ? row_to_seg[row] : row;
+      const float gval = (seg >= 0 ? seg_grad[(int64_t)seg * W + k] : 0.f) * grad_scale;
+      if (zero_grad != nullptr) zero_grad[(int64_t)seg * W + k] = 0.f;
+      T* pw = table + (int64_t)row * pitch + k;
+      float s0 = kind != BESS_OPT_SGD ? state0[t] : 0.f;
+      float s1 = kind == BESS_OPT_ADAMW ? state1[t] : 0.f;
+      const float wv = opt_update(kind, h, Elem<T>::to_f(*pw), gval, s0, s1);
+      *pw = Elem<T>::from_f(wv);
+      if (kind != BESS_OPT_SGD) state0[t] = s0;
+      if (kind == BESS_OPT_ADAMW) state1[t] = s1;
+    }
   }
+}
+
+struct HyperVals {
+  float v[BESS_HYPER_COUNT];
+};
+__global__ void set_hyper_kernel(float* hyper, HyperVals h) {
+  if (threadIdx.x < BESS_HYPER_COUNT) hyper[threadIdx.x] = h.v[threadIdx.x];
 }
 
 // Relation-table gradient: CTA (relation r, 128-column block) reduces the sorted
@@ -364,7 +490,8 @@ static GradSrc make_src(int row_elems, int n_local, int per_dst, const float* gr
 extern "C" int bess_scatter_sgd(void* table, int64_t table_pitch, int dtype, int row_elems,
                                 const int32_t* sorted_keys, const int32_t* perm, int n, int n_local,
                                 int per_dst, const float* grad_local, const float* grad_dst,
-                                int64_t dst_stride_rows, float lr, void* stream) {
+                                int64_t dst_stride_rows, float lr, const float* hyper,
+                                void* stream) {
   if (n == 0) return BESS_OK;
   BESS_CHECK_ARG(row_elems % 4 == 0, "row_elems must be a multiple of 4");
   {  // the update is a 128-bit (fp32) / 64-bit (half) read-modify-write of 4 elements
@@ -376,9 +503,9 @@ extern "C" int bess_scatter_sgd(void* table, int64_t table_pitch, int dtype, int
   const int blocks = ceil_div((int64_t)n * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case BESS_F32: segment_kernel<0, float><<<blocks, 256, 0, st>>>((float*)table, table_pitch, sorted_keys, perm, n, g, lr, nullptr, nullptr); break;
-    case BESS_F16: segment_kernel<0, __half><<<blocks, 256, 0, st>>>((__half*)table, table_pitch, sorted_keys, perm, n, g, lr, nullptr, nullptr); break;
-    case BESS_BF16: segment_kernel<0, __nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)table, table_pitch, sorted_keys, perm, n, g, lr, nullptr, nullptr); break;
+    case BESS_F32: segment_kernel<0, float><<<blocks, 256, 0, st>>>((float*)table, table_pitch, sorted_keys, perm, n, g, lr, hyper, nullptr, nullptr); break;
+    case BESS_F16: segment_kernel<0, __half><<<blocks, 256, 0, st>>>((__half*)table, table_pitch, sorted_keys, perm, n, g, lr, hyper, nullptr, nullptr); break;
+    case BESS_BF16: segment_kernel<0, __nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)table, table_pitch, sorted_keys, perm, n, g, lr, hyper, nullptr, nullptr); break;
     default: bess_set_error("unknown dtype %d", dtype); return BESS_ERR_INVALID_ARG;
   }
   BESS_CHECK_LAUNCH();
@@ -394,7 +521,22 @@ extern "C" int bess_scatter_collect(int row_elems, const int32_t* sorted_keys, c
   const GradSrc g = make_src(row_elems, n_local, per_dst, grad_local, grad_dst, dst_stride_rows);
   const int blocks = ceil_div((int64_t)n * 32, 256);
   segment_kernel<1, float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      nullptr, 0, sorted_keys, perm, n, g, 0.f, seg_grad, row_to_seg);
+      nullptr, 0, sorted_keys, perm, n, g, 0.f, nullptr, seg_grad, row_to_seg);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_scatter_accumulate(int row_elems, const int32_t* sorted_keys,
+                                       const int32_t* perm, int n, int n_local, int per_dst,
+                                       const float* grad_local, const float* grad_dst,
+                                       int64_t dst_stride_rows, float* acc, void* stream) {
+  if (n == 0) return BESS_OK;
+  BESS_CHECK_ARG(row_elems % 4 == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0,
+                 "bess_scatter_accumulate: rows must be 16-byte aligned multiples of 4 elements");
+  const GradSrc g = make_src(row_elems, n_local, per_dst, grad_local, grad_dst, dst_stride_rows);
+  const int blocks = ceil_div((int64_t)n * 32, 256);
+  segment_kernel<2, float><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      nullptr, 0, sorted_keys, perm, n, g, 0.f, nullptr, acc, nullptr);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }
@@ -403,23 +545,60 @@ extern "C" int bess_opt_dense(int kind, void* table, int64_t table_pitch, int dt
                               int row_elems, const float* seg_grad, const int32_t* row_to_seg,
                               float* state0, float* state1, float lr, float momentum,
                               float dampening, float beta1, float beta2, float eps,
-                              float weight_decay, int step, void* stream) {
+                              float weight_decay, int step, const float* hyper, float grad_scale,
+                              int zero_grad, void* stream) {
   if (n_rows == 0) return BESS_OK;
+  BESS_CHECK_ARG(!zero_grad || row_to_seg == nullptr,
+                 "bess_opt_dense: zero_grad needs a dense gradient (row_to_seg == NULL)");
+  float* zg = zero_grad ? const_cast<float*>(seg_grad) : nullptr;
   BESS_CHECK_ARG(kind >= BESS_OPT_SGD && kind <= BESS_OPT_ADAMW, "optimizer kind %d", kind);
   if (kind != BESS_OPT_SGD) BESS_CHECK_ARG(state0 != nullptr, "optimizer state missing");
   if (kind == BESS_OPT_ADAMW) BESS_CHECK_ARG(state1 != nullptr, "optimizer state missing");
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  const int64_t total = (int64_t)n_rows * row_elems;
+  OptHyper h;
+  h.lr = lr; h.momentum = momentum; h.dampening = dampening; h.beta1 = beta1; h.beta2 = beta2;
+  h.eps = eps; h.wd = weight_decay;
+  h.bc1 = 1.f - powf(beta1, (float)step); h.bc2 = 1.f - powf(beta2, (float)step);
+  h.first_step = step <= 1 ? 1 : 0;
+  const int es = dtype == BESS_F32 ? 4 : 2;
+  const bool vec = row_elems % 4 == 0 && table_pitch % 4 == 0 &&
+                   reinterpret_cast<uintptr_t>(table) % (4 * es) == 0 &&
+                   reinterpret_cast<uintptr_t>(seg_grad) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(state0) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(state1) % 16 == 0;
+  const int64_t total = (int64_t)n_rows * (vec ? row_elems / 4 : row_elems);
   int blocks = ceil_div(total, 256);
-  if (blocks > kNumSM * 16) blocks = kNumSM * 16;
+  if (blocks > kNumSM * 8) blocks = kNumSM * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  const int first = step <= 1 ? 1 : 0;
+#define BESS_OPT_LAUNCH(T, V)                                                                     \
+  opt_dense_kernel<T, V><<<blocks, 256, 0, st>>>(kind, (T*)table, table_pitch, n_rows, row_elems, \
+                                                 seg_grad, row_to_seg, state0, state1, h, hyper, \
+                                                 grad_scale, zg)
   switch (dtype) {
-    case BESS_F32: opt_dense_kernel<float><<<blocks, 256, 0, st>>>(kind, (float*)table, table_pitch, n_rows, row_elems, seg_grad, row_to_seg, state0, state1, lr, momentum, dampening, beta1, beta2, eps, weight_decay, bc1, bc2, first); break;
-    case BESS_F16: opt_dense_kernel<__half><<<blocks, 256, 0, st>>>(kind, (__half*)table, table_pitch, n_rows, row_elems, seg_grad, row_to_seg, state0, state1, lr, momentum, dampening, beta1, beta2, eps, weight_decay, bc1, bc2, first); break;
-    case BESS_BF16: opt_dense_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(kind, (__nv_bfloat16*)table, table_pitch, n_rows, row_elems, seg_grad, row_to_seg, state0, state1, lr, momentum, dampening, beta1, beta2, eps, weight_decay, bc1, bc2, first); break;
+    case BESS_F32: if (vec) BESS_OPT_LAUNCH(float, true); else BESS_OPT_LAUNCH(float, false); break;
+    case BESS_F16: if (vec) BESS_OPT_LAUNCH(__half, true); else BESS_OPT_LAUNCH(__half, false); break;
+    case BESS_BF16:
+      if (vec) BESS_OPT_LAUNCH(__nv_bfloat16, true); else BESS_OPT_LAUNCH(__nv_bfloat16, false);
+      break;
     default: bess_set_error("unknown dtype %d", dtype); return BESS_ERR_INVALID_ARG;
   }
+#undef BESS_OPT_LAUNCH
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_set_hyper(float* hyper, float lr, float momentum, float dampening, float beta1,
+                              float beta2, float eps, float weight_decay, int step, void* stream) {
+  BESS_CHECK_ARG(hyper != nullptr && step >= 1, "bess_set_hyper: hyper array and step >= 1 required");
+  HyperVals h;
+  for (int i = 0; i < BESS_HYPER_COUNT; ++i) h.v[i] = 0.f;
+  h.v[BESS_HYPER_LR] = lr; h.v[BESS_HYPER_MOMENTUM] = momentum;
+  h.v[BESS_HYPER_DAMPENING] = dampening; h.v[BESS_HYPER_BETA1] = beta1;
+  h.v[BESS_HYPER_BETA2] = beta2; h.v[BESS_HYPER_EPS] = eps;
+  h.v[BESS_HYPER_WEIGHT_DECAY] = weight_decay;
+  h.v[BESS_HYPER_BC1] = 1.f - powf(beta1, (float)step);
+  h.v[BESS_HYPER_BC2] = 1.f - powf(beta2, (float)step);
+  h.v[BESS_HYPER_FIRST_STEP] = step <= 1 ? 1.f : 0.f;
+  set_hyper_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hyper, h);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

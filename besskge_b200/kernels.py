@@ -27,14 +27,27 @@ class Workspace:
     def __init__(self, device: torch.device) -> None:
         self.device = device
         self._buf: Dict[str, torch.Tensor] = {}
+        # `generation` moves whenever an existing buffer is REPLACED (grown or re-typed): raw
+        # pointers baked into a captured CUDA graph then refer to the old buffer.  Replaced
+        # buffers are parked in `_retired` (still allocated, so a stale replay cannot touch
+        # freed memory) until the owner of the graphs has dropped them (`release_retired`).
+        self.generation = 0
+        self._retired: List[torch.Tensor] = []
 
     def get(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
         n = int(math.prod(shape)) if len(shape) else 1
         cur = self._buf.get(name)
         if cur is None or cur.dtype != dtype or cur.numel() < n:
+            if cur is not None:
+                self._retired.append(cur)
+                self.generation += 1
             cur = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._buf[name] = cur
         return cur[:n].view(*shape)
+
+    def release_retired(self) -> None:
+        """Free replaced buffers; call only when no captured graph refers to them."""
+        self._retired.clear()
 
     def bytes(self) -> int:
         return sum(b.numel() * b.element_size() for b in self._buf.values())
@@ -278,10 +291,10 @@ def sort_keys(keys: torch.Tensor, n: int, key_bits: int, keys_out: torch.Tensor,
 
 def scatter_sgd(table: torch.Tensor, sorted_keys: torch.Tensor, perm: torch.Tensor, n: int,
                 n_local: int, per_dst: int, grad_local: torch.Tensor, grad_dst_ptr: int,
-                dst_stride_rows: int, lr: float) -> None:
+                dst_stride_rows: int, lr: float, hyper: Optional[torch.Tensor] = None) -> None:
     call("bess_scatter_sgd", table.data_ptr(), table.stride(0), dtype_code(table.dtype),
          table.shape[1], sorted_keys.data_ptr(), perm.data_ptr(), n, n_local, per_dst,
-         grad_local.data_ptr(), grad_dst_ptr, dst_stride_rows, float(lr), _st(table))
+         grad_local.data_ptr(), grad_dst_ptr, dst_stride_rows, float(lr), ptr(hyper), _st(table))
 
 
 def scatter_collect(row_elems: int, sorted_keys: torch.Tensor, perm: torch.Tensor, n: int,
@@ -295,11 +308,29 @@ def scatter_collect(row_elems: int, sorted_keys: torch.Tensor, perm: torch.Tenso
 def opt_dense(kind: int, table: torch.Tensor, seg_grad: torch.Tensor,
               row_to_seg: Optional[torch.Tensor], state0: Optional[torch.Tensor],
               state1: Optional[torch.Tensor], lr: float, momentum: float, dampening: float,
-              beta1: float, beta2: float, eps: float, weight_decay: float, step: int) -> None:
+              beta1: float, beta2: float, eps: float, weight_decay: float, step: int,
+              hyper: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+              zero_grad: bool = False) -> None:
     call("bess_opt_dense", kind, table.data_ptr(), table.stride(0), dtype_code(table.dtype),
          table.shape[0], table.shape[1], seg_grad.data_ptr(), ptr(row_to_seg), ptr(state0),
          ptr(state1), float(lr), float(momentum), float(dampening), float(beta1), float(beta2),
-         float(eps), float(weight_decay), int(step), _st(table))
+         float(eps), float(weight_decay), int(step), ptr(hyper), float(grad_scale),
+         int(zero_grad), _st(table))
+
+
+def scatter_accumulate(row_elems: int, sorted_keys: torch.Tensor, perm: torch.Tensor, n: int,
+                       n_local: int, per_dst: int, grad_local: torch.Tensor, grad_dst_ptr: int,
+                       dst_stride_rows: int, acc: torch.Tensor) -> None:
+    call("bess_scatter_accumulate", row_elems, sorted_keys.data_ptr(), perm.data_ptr(), n, n_local,
+         per_dst, grad_local.data_ptr(), grad_dst_ptr, dst_stride_rows, acc.data_ptr(), _st(acc))
+
+
+def set_hyper(hyper: torch.Tensor, lr: float, momentum: float, dampening: float, beta1: float,
+              beta2: float, eps: float, weight_decay: float, step: int) -> None:
+    """Write one optimizer step's hyper-parameters (and Adam bias corrections of `step`) into
+    the device array the update kernels read; stream-ordered, safe to call every step."""
+    call("bess_set_hyper", hyper.data_ptr(), float(lr), float(momentum), float(dampening),
+         float(beta1), float(beta2), float(eps), float(weight_decay), int(step), _st(hyper))
 
 
 def relation_grad_reduce(rows_: torch.Tensor, width: int, sorted_rel: torch.Tensor,
@@ -362,8 +393,18 @@ def peer_signal(counter: torch.Tensor, peer_flag_ptrs: Sequence[int], my_rank: i
          len(peer_flag_ptrs), _st(counter))
 
 
-def peer_wait(counter: torch.Tensor, my_flags: torch.Tensor, n: int) -> None:
-    call("bess_peer_wait", counter.data_ptr(), my_flags.data_ptr(), n, _st(counter))
+def peer_timeout_ms() -> int:
+    """Wall-clock bound of a peer wait: BESS_PEER_TIMEOUT_S seconds (default 600; 0 = none).
+    Long enough for a checkpoint save or a slow batch on one rank, short enough that a dead
+    peer ends in a CUDA error rather than a hung GPU."""
+    import os
+    return int(float(os.environ.get("BESS_PEER_TIMEOUT_S", "600")) * 1000)
+
+
+def peer_wait(counter: torch.Tensor, my_flags: torch.Tensor, n: int,
+              timeout_ms: Optional[int] = None) -> None:
+    call("bess_peer_wait", counter.data_ptr(), my_flags.data_ptr(), n,
+         peer_timeout_ms() if timeout_ms is None else int(timeout_ms), _st(counter))
 
 
 def peer_push(src: torch.Tensor, src_stride_bytes: int, dst_ptrs: Sequence[int],

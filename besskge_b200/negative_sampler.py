@@ -117,10 +117,13 @@ class TypeBasedShardedNegativeSampler(RandomShardedNegativeSampler):
         wanted = einops.repeat(wanted, pattern, r=n)
         raw = self._draw(sample_idx)
         src = np.arange(n)[None, :, None, None]
-        rows = (
-            raw % self.type_counts[src, wanted, np.newaxis]
-            + self.type_offsets[src, wanted, np.newaxis]
-        )
+        # a shard without entities of the wanted type gives x % 0: numpy defines it as 0 (the
+        # reference computes the same value, with a RuntimeWarning that carries no information)
+        with np.errstate(divide="ignore"):
+            rows = (
+                raw % self.type_counts[src, wanted, np.newaxis]
+                + self.type_offsets[src, wanted, np.newaxis]
+            )
         return dict(negative_entities=rows)
 
 
@@ -316,9 +319,10 @@ class TripleBasedShardedNegativeSampler(ShardedNegativeSampler):
         slot = np.arange(padded_shard_length)[None, None, :]
         mask = slot < shard_counts[..., None]
         starts = np.c_[[0] * self.N, np.cumsum(shard_counts, axis=-1)[:, :-1]]
-        src = np.minimum(
-            slot % shard_counts[..., None] + starts[..., None], self.n_negative - 1
-        )
+        with np.errstate(divide="ignore"):  # a shard that holds no candidate: x % 0 := 0, masked
+            src = np.minimum(
+                slot % shard_counts[..., None] + starts[..., None], self.n_negative - 1
+            )
         return negatives[np.arange(self.N)[:, None, None], src], mask
 
 

@@ -83,16 +83,26 @@ class Sharding:
 
     def save(self, out_file: Path) -> None:
         """.npz checkpoint (reference: sharding.py:139-147)."""
-        np.savez(out_file, **dataclasses.asdict(self))
+        fields = {k: v for k, v in dataclasses.asdict(self).items() if v is not None}
+        np.savez(out_file, **fields)  # None fields are simply absent: no object arrays
 
     @classmethod
     def load(cls, path: Path) -> "Sharding":
-        data = dict(np.load(path, allow_pickle=True))
-        n_shard = int(data.pop("n_shard"))
-        for k in ("entity_type_counts", "entity_type_offsets"):
-            if k in data and data[k].dtype == object:
-                data[k] = None
-        return cls(n_shard=n_shard, **data)
+        """Reference: sharding.py:149-160.  Never unpickles: the optional per-type fields are
+        None when absent (or when a file written by the reference stored None as an object
+        array, which numpy refuses to load without pickle)."""
+        data = {}
+        with np.load(path, allow_pickle=False) as f:
+            for k in f.files:
+                try:
+                    data[k] = f[k]
+                except ValueError:
+                    if k not in ("entity_type_counts", "entity_type_offsets"):
+                        raise
+                    data[k] = None
+        data.setdefault("entity_type_counts", None)
+        data.setdefault("entity_type_offsets", None)
+        return cls(n_shard=int(data.pop("n_shard")), **data)
 
 
 def _partition(

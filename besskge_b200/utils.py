@@ -1,4 +1,7 @@
-"""Host utilities of the evaluation pipeline (reference: besskge/utils.py:36-69)."""
+"""General-purpose utilities (reference: besskge/utils.py): the device helpers
+`gather_indices`, `complex_multiplication`, `complex_rotation` (CUDA kernels through the
+C-ABI; CUDA tensors only, like every device entry point of this package) and the host-side
+entity filter of the evaluation pipeline."""
 from __future__ import annotations
 
 from typing import Union
@@ -6,6 +9,53 @@ from typing import Union
 import numpy as np
 import torch
 from numpy.typing import NDArray
+
+from . import _lib as L
+
+
+def gather_indices(x: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """2-D take-along-dim (reference: utils.py:10-33): `x` (a, e), `index` (b, k) ->
+    (max(a, b), k) with out[i, j] = x[i, index[i, j]]; b == 1 takes the same columns from
+    every row of `x`, a == 1 makes every index row read `x[0]`, otherwise a == b."""
+    L.require_cuda(x, index)
+    if x.dim() != 2 or index.dim() != 2:
+        raise ValueError("gather_indices expects 2-dimensional x and index")
+    x = x.contiguous()
+    idx = index.to(torch.int32).contiguous()
+    a, e = x.shape
+    b, k = idx.shape
+    out = torch.empty(max(a, b), k, dtype=x.dtype, device=x.device)
+    L.call("bess_take_along_rows", x.data_ptr(), a, e, x.element_size(), idx.data_ptr(), b, k,
+           out.data_ptr(), L.stream_ptr(x.device))
+    return out
+
+
+def _complex(v1: torch.Tensor, v2: torch.Tensor, rotate: bool) -> torch.Tensor:
+    L.require_cuda(v1, v2)
+    if v1.dtype != v2.dtype:
+        raise TypeError("operands must share one dtype")
+    lead = v1.shape[:-1]
+    a = v1.reshape(-1, v1.shape[-1]).contiguous()
+    e = a.shape[-1] // 2
+    b = v2.expand(*lead, v2.shape[-1]).reshape(-1, v2.shape[-1]).contiguous()
+    if a.shape[-1] != 2 * e or b.shape[-1] != (e if rotate else 2 * e) or b.shape[0] != a.shape[0]:
+        raise ValueError(f"incompatible shapes {tuple(v1.shape)} and {tuple(v2.shape)}")
+    out = torch.empty_like(a)
+    L.call("bess_complex_mul", L.dtype_code(a.dtype), a.data_ptr(), b.data_ptr(), a.shape[0], e,
+           int(rotate), out.data_ptr(), L.stream_ptr(a.device))
+    return out.view(*lead, 2 * e)
+
+
+def complex_multiplication(v1: torch.Tensor, v2: torch.Tensor) -> torch.Tensor:
+    """Row-wise complex product of (a, 2e) tensors, `[:, :e]` real and `[:, e:]` imaginary
+    parts (reference: utils.py:72-89)."""
+    return _complex(v1, v2, False)
+
+
+def complex_rotation(v: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+    """Rotate `v` (a, 2e) by the unit complex numbers `cos r + i sin r`, `r` (a, e)
+    (reference: utils.py:92-112; full-precision sin / cos as the reference does off-IPU)."""
+    return _complex(v, r, True)
 
 
 class EntityFilterIndex:

@@ -305,20 +305,50 @@ int bess_sort_keys(const int32_t* keys, int n, int key_bits, int32_t* keys_out,
  *   torch.optim semantics: rows without gradient still decay / coast).
  * grad rows: position x < n_local -> grad_local row x; else y = x - n_local ->
  * grad_dst row (y / per_dst) * dst_stride_rows + y % per_dst  (mirror of
- * bess_gather_route's routing). */
+ * bess_gather_route's routing).
+ *
+ * `hyper` (device pointer, may be NULL): when given, the optimizer hyper-parameters are
+ * read from this fp32 array on the device (slots BESS_HYPER_*) instead of the by-value
+ * arguments, so a captured CUDA graph follows a learning-rate schedule and AdamW's bias
+ * correction: the host rewrites the array before each replay. */
+enum {
+  BESS_HYPER_LR = 0, BESS_HYPER_MOMENTUM = 1, BESS_HYPER_DAMPENING = 2, BESS_HYPER_BETA1 = 3,
+  BESS_HYPER_BETA2 = 4, BESS_HYPER_EPS = 5, BESS_HYPER_WEIGHT_DECAY = 6,
+  BESS_HYPER_BC1 = 7 /* 1 - beta1^step */, BESS_HYPER_BC2 = 8 /* 1 - beta2^step */,
+  BESS_HYPER_FIRST_STEP = 9 /* 1.0 on the first step (momentum buffer := grad) */,
+  BESS_HYPER_COUNT = 16
+};
 int bess_scatter_sgd(void* table, int64_t table_pitch, int dtype, int row_elems,
                      const int32_t* sorted_keys, const int32_t* perm, int n, int n_local,
                      int per_dst, const float* grad_local, const float* grad_dst,
-                     int64_t dst_stride_rows, float lr, void* stream);
+                     int64_t dst_stride_rows, float lr, const float* hyper, void* stream);
 int bess_scatter_collect(int row_elems, const int32_t* sorted_keys, const int32_t* perm, int n,
                          int n_local, int per_dst, const float* grad_local,
                          const float* grad_dst, int64_t dst_stride_rows, float* seg_grad,
                          int32_t* row_to_seg, void* stream);
-/* dense optimizer pass over [n_rows, row_elems]; row_to_seg[row] < 0: zero grad.
- * state0: momentum buffer / Adam m; state1: Adam v (fp32).  step: 1-based. */
+/* gradient accumulation over micro-batches (the reference's runtime option
+ * `options.Training.gradientAccumulation(k)`, notebooks 1 cell 26 / 2 cell 14): add the
+ * segment sums of one micro-batch to a dense fp32 accumulator acc [Es, row_elems]
+ * (deterministic: one warp owns a key). */
+int bess_scatter_accumulate(int row_elems, const int32_t* sorted_keys, const int32_t* perm, int n,
+                            int n_local, int per_dst, const float* grad_local,
+                            const float* grad_dst, int64_t dst_stride_rows, float* acc,
+                            void* stream);
+/* dense optimizer pass over [n_rows, row_elems]; row_to_seg[row] < 0: zero grad;
+ * row_to_seg == NULL: seg_grad is a dense [n_rows, row_elems] gradient.
+ * state0: momentum buffer / Adam m; state1: Adam v (fp32).  step: 1-based.
+ * The gradient is multiplied by grad_scale (1/k for a mean over k accumulated
+ * micro-batches); zero_grad != 0 (dense gradient only) clears seg_grad after reading it. */
 int bess_opt_dense(int kind, void* table, int64_t table_pitch, int dtype, int n_rows,
                    int row_elems, const float* seg_grad, const int32_t* row_to_seg, float* state0,
                    float* state1, float lr, float momentum, float dampening, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* hyper,
+                   float grad_scale, int zero_grad, void* stream);
+/* fill one BESS_HYPER_COUNT-float device array for optimizer step `step` (1-based):
+ * the by-value hyper-parameters plus bc1 = 1 - beta1^step, bc2 = 1 - beta2^step and the
+ * first-step flag.  Kernel arguments are captured at launch, so the host may call this
+ * every step without synchronising. */
+int bess_set_hyper(float* hyper, float lr, float momentum, float dampening, float beta1,
                    float beta2, float eps, float weight_decay, int step, void* stream);
 /* relation table: deterministic reduce of per-query gradient rows by relation
  * id -> d_table [n_rel, width] fp32 (overwritten).  sorted_rel/perm from
@@ -373,15 +403,30 @@ int bess_pairs_set(float* mat, int64_t ld, const int32_t* rows, const int32_t* c
  * rank j's flag row (n int32, symmetric memory) of one channel, `counter` is a
  * local int32 sequence counter of the same channel.
  *   signal: seq = ++*counter; flag row of every rank [my_rank] := seq (release.sys)
- *   wait  : until all n local flags >= *counter (acquire.sys; traps after ~10 s)
+ *   wait  : until all n local flags >= *counter (acquire.sys).  timeout_ms > 0 bounds the
+ *           spin in wall-clock time (%globaltimer): on expiry the launch prints the
+ *           missing rank and traps; timeout_ms <= 0 waits for ever
  *   push  : dst[j] <- src + j * src_stride_bytes, bytes_each bytes, for j < n
  *   reduce: out[i] = scale * sum_j slots[j * count + i], j ascending */
 int bess_peer_signal(int32_t* counter, void* const* peer_flags /* host array [n] */, int my_rank,
                      int n, void* stream);
-int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n, void* stream);
+int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n, int64_t timeout_ms,
+                   void* stream);
 int bess_peer_push(const void* src, int64_t src_stride_bytes, void* const* dst /* host array [n] */,
                    int n, int64_t bytes_each, void* stream);
 int bess_peer_reduce(const float* slots, int n, int64_t count, float scale, float* out, void* stream);
+
+/* Python-surface helpers of the reference's utils.py.
+ * take_along_rows (utils.py:10-33 `gather_indices`): out[i, j] = x[i or 0, index[i or 0, j]];
+ *   x [a, e] of elem_bytes-wide words (1/2/4/8), index int32 [b, k], a == b or one of them 1,
+ *   out [max(a, b), k].
+ * complex_mul (utils.py:72-112): rows are [re | im] halves of e elements each;
+ *   rotate == 0: out = v1 * v2 (both [n, 2e]); rotate != 0: v2 is [n, e] angles and
+ *   out = v1 * (cos v2 + i sin v2). */
+int bess_take_along_rows(const void* x, int a, int64_t e, int elem_bytes, const int32_t* index,
+                         int b, int k, void* out, void* stream);
+int bess_complex_mul(int dtype, const void* v1, const void* v2, int n, int e, int rotate, void* out,
+                     void* stream);
 
 /* utility */
 int bess_fill_f32(float* p, int64_t n, float v, void* stream);

@@ -523,11 +523,17 @@ def training_steps(
     rel_table: torch.Tensor, batches: List[Dict[str, torch.Tensor]], scheme: str, flat: bool,
     shared: bool, relation_grad_reduction: str = "mean", augment: bool = False,
     weights: Optional[List[Optional[torch.Tensor]]] = None,
+    lr_schedule: Optional[List[float]] = None, accumulate: int = 1,
+    accumulation_reduction: str = "mean",
 ) -> Dict[str, Any]:
     """Runs len(batches) micro-batch steps (each: n replicas, summed losses, one
     optimizer step).  Entity-table gradients are the plain sum over replicas
     (no all-reduce on the sharded table, custom_ops/remove_all_reduce_pattern.cpp);
-    the replicated relation table's gradient is reduced by `relation_grad_reduction`."""
+    the replicated relation table's gradient is reduced by `relation_grad_reduction`.
+    `lr_schedule[i]`: learning rate of optimizer step i.  `accumulate = k`: gradients of k
+    consecutive micro-batches are accumulated (all from the same weights) and reduced by
+    `accumulation_reduction` before ONE optimizer step — PopTorch's
+    `options.Training.gradientAccumulation(k)` (notebook 1 cell 26: 6, notebook 2 cell 14: 2)."""
     ent = ent.clone().requires_grad_(True)
     rel_table = rel_table.clone().requires_grad_(True)
     n = ent.shape[0]
@@ -542,8 +548,10 @@ def training_steps(
     opt_e, opt_r = mk([ent]), mk([rel_table])
     losses, grads_e, grads_r = [], [], []
     for bi, b in enumerate(batches):
-        opt_e.zero_grad(set_to_none=True)
-        opt_r.zero_grad(set_to_none=True)
+        if bi % accumulate == 0:
+            opt_e.zero_grad(set_to_none=True)
+            opt_r.zero_grad(set_to_none=True)
+            rel_acc = None
         pos, neg = embedding_moving_forward(cfg, ent, rel_table, b["head"], b["relation"], b["tail"],
                                             b["negative"], scheme, flat, shared,
                                             b.get("negative_mask"), augment)
@@ -551,12 +559,23 @@ def training_steps(
         for r in range(n):
             w = torch.tensor([1.0]) if weights is None or weights[bi] is None else weights[bi][r]
             step_losses.append(loss_value(loss_cfg, pos[r].float(), neg[r].float(), w))
+        before = None if rel_table.grad is None else rel_table.grad.detach().clone()
         torch.stack(step_losses).sum().backward()
-        if relation_grad_reduction == "mean":
-            rel_table.grad.div_(n)
+        if relation_grad_reduction == "mean":  # only this micro-batch's contribution
+            cur = rel_table.grad if before is None else rel_table.grad - before
+            rel_table.grad = (cur / n) if before is None else before + cur / n
         losses.append(torch.stack(step_losses).detach())
+        if (bi + 1) % accumulate != 0:
+            continue
+        if accumulate > 1 and accumulation_reduction == "mean":
+            ent.grad.div_(accumulate)
+            rel_table.grad.div_(accumulate)
         grads_e.append(ent.grad.detach().clone())
         grads_r.append(rel_table.grad.detach().clone())
+        if lr_schedule is not None:
+            for o in (opt_e, opt_r):
+                for gp in o.param_groups:
+                    gp["lr"] = lr_schedule[len(grads_e) - 1]
         opt_e.step()
         opt_r.step()
     return dict(loss=torch.stack(losses), ent=ent.detach(), rel=rel_table.detach(),

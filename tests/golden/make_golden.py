@@ -507,17 +507,57 @@ def golden_pipeline(ref) -> None:
                          **{f"in_{kk}": v for kk, v in batch.items()}, block_last_sub=block[::4, ::7])
 
 
+def dataset_frames():
+    """Labelled triples used by golden_dataset and tests/test_host_golden.py (seeded)."""
+    import pandas as pd
+    rng = np.random.default_rng(SEED)
+    ents = [f"e{i:03d}" for i in range(60)]
+    types = {e: f"type{rng.integers(4)}" for e in ents}
+    rels = [f"r{i}" for i in range(7)]
+    n = 400
+    df = pd.DataFrame(dict(h=rng.choice(ents, n), r=rng.choice(rels, n), t=rng.choice(ents, n)))
+    return df, types
+
+
+def golden_dataset(ref) -> None:
+    """KGDataset.from_triples / from_dataframe of the reference (dataset.py:83-239)."""
+    df, types = dataset_frames()
+    arrays = {}
+    for tag, kw in (("typed", dict(entity_types=types)), ("plain", dict())):
+        ds = ref.dataset.KGDataset.from_dataframe(df, "h", "r", "t", seed=SEED, **kw)
+        for part in ("train", "valid", "test"):
+            arrays[f"{tag}_{part}"] = ds.triples[part]
+            arrays[f"{tag}_ids_{part}"] = ds.original_triple_ids[part]
+        arrays[f"{tag}_entity_dict"] = np.array(ds.entity_dict)
+        arrays[f"{tag}_relation_dict"] = np.array(ds.relation_dict)
+        if ds.type_offsets is not None:
+            arrays[f"{tag}_type_names"] = np.array(list(ds.type_offsets.keys()))
+            arrays[f"{tag}_type_offsets"] = np.array(list(ds.type_offsets.values()))
+    parts = {"train": df.iloc[:300], "valid": df.iloc[300:]}
+    ds = ref.dataset.KGDataset.from_dataframe(parts, "h", "r", "t", entity_types=types)
+    arrays.update(split_train=ds.triples["train"], split_valid=ds.triples["valid"],
+                  split_entity_dict=np.array(ds.entity_dict))
+    rng = np.random.default_rng(SEED + 1)
+    raw = np.stack([rng.integers(50, size=333), rng.integers(5, size=333),
+                    rng.integers(50, size=333)], axis=1).astype(np.int32)
+    ds = ref.dataset.KGDataset.from_triples(raw, split=(0.6, 0.3, 0.1), seed=7)
+    arrays.update(raw=raw, raw_train=ds.triples["train"], raw_valid=ds.triples["valid"],
+                  raw_test=ds.triples["test"], raw_ids_test=ds.original_triple_ids["test"])
+    save("host_dataset", dict(seed=SEED, n_entity=int(ds.n_entity), n_rel=int(ds.n_relation_type)),
+         **arrays)
+
+
+GENERATORS = dict(host=golden_host, dataset=golden_dataset, scores=golden_scores, loss=golden_loss,
+                  metric=golden_metric, bess=golden_bess, train=golden_train, topk=golden_topk,
+                  pipeline=golden_pipeline)
+
+
 def main() -> None:
+    """`python tests/golden/make_golden.py [name ...]` — all generators, or the named ones."""
     ref = ref_loader.load_reference()
-    torch.manual_seed(SEED)
-    golden_host(ref)
-    golden_scores(ref)
-    golden_loss(ref)
-    golden_metric(ref)
-    golden_bess(ref)
-    golden_train(ref)
-    golden_topk(ref)
-    golden_pipeline(ref)
+    for name in (sys.argv[1:] or list(GENERATORS)):
+        torch.manual_seed(SEED)
+        GENERATORS[name](ref)
 
 
 if __name__ == "__main__":

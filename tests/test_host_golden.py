@@ -58,6 +58,66 @@ def test_sharding_save_load(tmp_path):
     assert sh2.entity_type_counts is None
 
 
+def test_sharding_load_never_unpickles(tmp_path):
+    """None fields are absent from the file; a reference-style file that stores None as an
+    object array loads with the field None instead of demanding allow_pickle."""
+    sh = Sharding.create(101, 3, seed=7, type_offsets=np.array([0, 40, 70]))
+    sh.save(tmp_path / "typed.npz")
+    with np.load(tmp_path / "typed.npz", allow_pickle=False) as f:
+        assert all(f[k].dtype != object for k in f.files)
+    sh2 = Sharding.load(tmp_path / "typed.npz")
+    assert_array_equal(sh.entity_type_counts, sh2.entity_type_counts)
+    assert_array_equal(sh.entity_type_offsets, sh2.entity_type_offsets)
+    plain = Sharding.create(101, 3, seed=7)
+    import dataclasses
+    np.savez(tmp_path / "ref_style.npz", **dataclasses.asdict(plain))  # what the reference writes
+    sh3 = Sharding.load(tmp_path / "ref_style.npz")
+    assert sh3.entity_type_counts is None and sh3.entity_type_offsets is None
+    assert_array_equal(plain.entity_to_idx, sh3.entity_to_idx)
+
+
+def test_dataset_constructors_vs_reference_golden(tmp_path):
+    """KGDataset.from_dataframe / from_triples (dataset.py:83-239): ids, type offsets and
+    the random split equal the reference's on the same labelled triples."""
+    from besskge_b200.dataset import KGDataset
+    from .golden.make_golden import dataset_frames
+    cfg, g = load_golden("host_dataset")
+    df, types = dataset_frames()
+    for tag, kw in (("typed", dict(entity_types=types)), ("plain", dict())):
+        ds = KGDataset.from_dataframe(df, "h", "r", "t", seed=cfg["seed"], **kw)
+        for part in ("train", "valid", "test"):
+            assert_array_equal(ds.triples[part], g[f"{tag}_{part}"])
+            assert_array_equal(ds.original_triple_ids[part], g[f"{tag}_ids_{part}"])
+        assert ds.entity_dict == g[f"{tag}_entity_dict"].tolist()
+        assert ds.relation_dict == g[f"{tag}_relation_dict"].tolist()
+        if tag == "typed":
+            assert list(ds.type_offsets.keys()) == g["typed_type_names"].tolist()
+            assert list(ds.type_offsets.values()) == g["typed_type_offsets"].tolist()
+            assert ds.ht_types["train"].shape == (ds.triples["train"].shape[0], 2)
+        else:
+            assert ds.type_offsets is None
+    parts = {"train": df.iloc[:300], "valid": df.iloc[300:]}
+    ds = KGDataset.from_dataframe(parts, "h", "r", "t", entity_types=types)
+    assert_array_equal(ds.triples["train"], g["split_train"])
+    assert_array_equal(ds.triples["valid"], g["split_valid"])
+    assert ds.entity_dict == g["split_entity_dict"].tolist()
+    raw = KGDataset.from_triples(g["raw"], split=(0.6, 0.3, 0.1), seed=7)
+    for part in ("train", "valid", "test"):
+        assert_array_equal(raw.triples[part], g[f"raw_{part}"])
+    assert_array_equal(raw.original_triple_ids["test"], g["raw_ids_test"])
+    assert (raw.n_entity, raw.n_relation_type) == (cfg["n_entity"], cfg["n_rel"])
+    # save / load round trip (data-only container, no pickle)
+    ds.save(tmp_path / "ds.npz")
+    back = KGDataset.load(tmp_path / "ds.npz")
+    assert back.entity_dict == ds.entity_dict and back.type_offsets == ds.type_offsets
+    assert back.neg_heads is None
+    for part in ds.triples:
+        assert_array_equal(back.triples[part], ds.triples[part])
+    with pytest.raises(ValueError):
+        np.savez(tmp_path / "other.npz", a=np.zeros(3))
+        KGDataset.load(tmp_path / "other.npz")
+
+
 @pytest.mark.parametrize("mode", ["h_shard", "t_shard", "ht_shardpair"])
 @pytest.mark.parametrize("inv", [False, True])
 def test_partition_bit_exact(mode, inv):
