@@ -111,6 +111,9 @@ SIGNATURES = {
     "bess_set_hyper": [_P, _F, _F, _F, _F, _F, _F, _F, _I, _P],
     "bess_relation_grad_reduce": [_P, _I, _P, _P, _I, _I, _P, _P],
     "bess_topk_merge": [_P, _L, _I, _I, _P, _L, _I, _P, _P, _I, _P],
+    "bess_topk_exact_supported": [_I],
+    "bess_topk_exact_rescore": [_CFG, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P, _P, _I, _I, _I, _P,
+                                _P, _P],
     "bess_topk_finalize": [_P, _P, _I, _I, _I, _P, _P, _I, _I, _F, _P, _P, _P],
     "bess_select_scores": [_P, _L, _P, _I, _P, _I, _F, _P, _L, _P],
     "bess_pairs_get": [_P, _L, _P, _P, _I, _P, _P],
@@ -133,7 +136,7 @@ _RESTYPE = {
     "bess_l2_coef_workspace": C.c_int64,
     "bess_launch_count": C.c_int64,
 }
-_NO_STATUS = {"bess_version", "bess_launch_count", "bess_entity_width", "bess_relation_width", "bess_query_nvec",
+_NO_STATUS = {"bess_version", "bess_topk_exact_supported", "bess_launch_count", "bess_entity_width", "bess_relation_width", "bess_query_nvec",
               "bess_shared_bwd_cand_workspace", "bess_sort_workspace", "bess_dot_gemm_workspace",
               "bess_l2_coef_workspace"}
 

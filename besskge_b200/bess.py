@@ -1493,6 +1493,14 @@ class TopKQueryBessKGE(torch.nn.Module):
     `window_size` is kept for API compatibility.  Inference only."""
 
     device_window = 4096
+    #: Exact ranking (SURVEY.md 7.2 item 3): against ALL entities the window scorers keep the
+    #: top-(k + 1 + exact_margin) local candidates per (query, shard), which are then re-scored
+    #: in one fixed fp32 summation order and re-sorted (csrc/exact.cu) — ids, scores, ranks and
+    #: MRR are then bit-identical to the oracle's restatement of that arithmetic, with no
+    #: near-tie tolerance.  Applies to TransE / DistMult / ComplEx (reproducible arithmetic)
+    #: when k + 1 + exact_margin <= 32; other cases keep the scorers' own fp32 scores.
+    exact_rerank = True
+    exact_margin = 6
 
     def __init__(
         self,
@@ -1641,8 +1649,17 @@ class TopKQueryBessKGE(torch.nn.Module):
         scores = ws.get("tk_scores", (nS, win), torch.float32)
         aux = ws.get("tk_aux", (nS, win), torch.float32) if need_aux else None
         scale = ws.get("tk_scale", (win,), torch.float32) if need_scale else None
-        best_s = ws.get("tk_best_s", (R, nS, kb), torch.float32)
-        best_i = ws.get("tk_best_i", (R, nS, kb), torch.int32)
+        # running best lists: kb entries, or kb + margin when they are re-ranked exactly
+        exact = bool(self.exact_rerank and negative is None and kb + self.exact_margin <= 32
+                     and K.topk_exact_supported(cfg.family))
+        kbm = kb + self.exact_margin if exact else kb
+        best_s = ws.get("tk_best_s", (R, nS, kbm), torch.float32)
+        best_i = ws.get("tk_best_i", (R, nS, kbm), torch.int32)
+        if exact:
+            send_s = ws.get("tk_send_s", (R, nS, kb), torch.float32)
+            send_i = ws.get("tk_send_i", (R, nS, kb), torch.int32)
+        else:
+            send_s, send_i = best_s, best_i
         recv_s = ws.get("tk_recv_s", (R, n, S, kb), torch.float32)
         recv_i = ws.get("tk_recv_i", (R, n, S, kb), torch.int32)
         gemm_ws = None
@@ -1723,14 +1740,17 @@ class TopKQueryBessKGE(torch.nn.Module):
                              else cand_mask[row, :, c0:c0 + nc]).contiguous()  # [1 or n*S, nc]
                         K.mask_add(scores, nS, nc, win, m, nc, m.shape[0], False,
                                    BAD_NEGATIVE_SCORE)
-                    K.topk_merge(scores, win, nS, nc, ids, ld_ids, id0, best_s[li], best_i[li], kb)
+                    K.topk_merge(scores, win, nS, nc, ids, ld_ids, id0, best_s[li], best_i[li], kbm)
+                if exact:
+                    K.topk_exact_rescore(cfg, dt, mode, Q, rel_table, rel_all, table, best_i[li],
+                                         best_s[li], nS, kbm, kb, send_s[li], send_i[li])
             # ---- best lists back to the shard that owns the queries (bess.py:856-863)
             if pl.distributed:
-                torch.distributed.all_to_all_single(recv_s.view(-1), best_s.view(-1))
-                torch.distributed.all_to_all_single(recv_i.view(-1), best_i.view(-1))
+                torch.distributed.all_to_all_single(recv_s.view(-1), send_s.view(-1))
+                torch.distributed.all_to_all_single(recv_i.view(-1), send_i.view(-1))
             else:
-                recv_s.copy_(best_s.view(R, n, S, kb).transpose(0, 1))
-                recv_i.copy_(best_i.view(R, n, S, kb).transpose(0, 1))
+                recv_s.copy_(send_s.view(R, n, S, kb).transpose(0, 1))
+                recv_i.copy_(send_i.view(R, n, S, kb).transpose(0, 1))
             for li in range(R):
                 o = s * R + li
                 K.topk_finalize(recv_s[li], recv_i[li], n, S, kb, counts_dev, s2e_dev, Es, self.k,

@@ -346,6 +346,22 @@ def topk_merge(win_score: torch.Tensor, ld: int, n_query: int, n_win: int,
          win_id0, best_score.data_ptr(), best_id.data_ptr(), k, _st(win_score))
 
 
+def topk_exact_supported(family: int) -> bool:
+    return bool(call("bess_topk_exact_supported", int(family)))
+
+
+def topk_exact_rescore(cfg: ScoreCfg, dt: int, mode: int, fixed: torch.Tensor,
+                       rel_table: torch.Tensor, rel_id: torch.Tensor, table: torch.Tensor,
+                       ids_in: torch.Tensor, score_in: torch.Tensor, n_query: int, k_in: int,
+                       k_out: int, score_out: torch.Tensor, ids_out: torch.Tensor) -> None:
+    """Fixed-order fp32 re-score + re-sort of the best lists; see bess_topk_exact_rescore."""
+    require_cuda(fixed, rel_table, rel_id, table, ids_in, score_in, score_out, ids_out)
+    call("bess_topk_exact_rescore", C.byref(cfg), dt, mode, fixed.data_ptr(), fixed.stride(0),
+         rel_table.data_ptr(), rel_table.stride(0), rel_id.data_ptr(), table.data_ptr(),
+         table.stride(0), table.shape[0], table.shape[1], ids_in.data_ptr(), score_in.data_ptr(),
+         n_query, k_in, k_out, score_out.data_ptr(), ids_out.data_ptr(), _st(table))
+
+
 def topk_finalize(score: torch.Tensor, idx: torch.Tensor, n_shard: int, n_query: int, kb: int,
                   shard_counts: torch.Tensor, shard_idx_to_entity: torch.Tensor, es: int, k: int,
                   bad: float, out_score: torch.Tensor, out_id: torch.Tensor) -> None:

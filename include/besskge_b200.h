@@ -366,6 +366,24 @@ int bess_topk_merge(const float* win_score, int64_t ld, int n_query, int n_win,
                     const int32_t* win_ids, int64_t ld_ids, int win_id0, float* best_score,
                     int32_t* best_id, int k, void* stream);
 
+/* Exact re-rank of the running best lists (csrc/exact.cu).  The
+ * window scorers only select candidates; this call re-scores the k_in (<= 32) entries of
+ * every query's list — local row ids ids_in [n_query, k_in] into `table` — in ONE fixed fp32
+ * summation order (coordinate 0..row_elems-1, each product / sum rounded separately, no FMA)
+ * and writes the k_out best, ordered by (score descending, id ascending), to score_out /
+ * ids_out [n_query, k_out].  `fixed` [n_query, row_elems]: the known entity row of each query
+ * (head for BESS_MODE_TAILS, tail for BESS_MODE_HEADS); rel_id [n_query].  Entries with
+ * id >= n_table_rows (empty slots) keep score_in.  TransE / DistMult / ComplEx only
+ * (bess_topk_exact_supported): their arithmetic is + - x sqrt, reproducible bit for bit by
+ * the CPU oracle, so ranks and MRR can be asserted equal with no near-tie tolerance. */
+int bess_topk_exact_supported(int family);
+int bess_topk_exact_rescore(const bess_score_cfg_t* cfg, int dtype, int mode, const void* fixed,
+                            int64_t fixed_pitch, const void* rel_table, int64_t rel_pitch,
+                            const int32_t* rel_id, const void* table, int64_t table_pitch,
+                            int n_table_rows, int row_elems, const int32_t* ids_in,
+                            const float* score_in, int n_query, int k_in, int k_out,
+                            float* score_out, int32_t* ids_out, void* stream);
+
 /* Final step of TopKQueryBessKGE (bess.py:866-891) on the shard that owns the
  * queries: score / idx [n_shard, n_query, kb] are the best lists received from
  * every scoring shard.  Adds bad_score to entries whose local id is a padding

@@ -307,7 +307,7 @@ def ranks_from_indices(truth: torch.Tensor, ids: torch.Tensor,
     """metric.py:185-220."""
     n = ids.shape[1]
     worst = torch.inf if worst_rank_infty else float(n + 1)
-    pos = torch.arange(1, n + 1, dtype=torch.float32)
+    pos = torch.arange(1, n + 1, dtype=torch.float32, device=ids.device)
     return torch.where(truth.reshape(-1, 1) == ids, pos, worst).min(dim=-1)[0]
 
 
@@ -391,7 +391,8 @@ def apply_masks(neg: torch.Tensor, relation_r: torch.Tensor, neg_shape, scheme: 
                                nmask[1:2].expand(n, p - cut, -1)], dim=1).flatten(end_dim=1)
     if augment:
         step = 1 if flat else 1 + neg_shape[0] * neg_shape[-1]
-        aug = (torch.arange(neg.shape[1])[None, :] == step * torch.arange(neg.shape[0])[:, None])
+        aug = (torch.arange(neg.shape[1], device=neg.device)[None, :]
+               == step * torch.arange(neg.shape[0], device=neg.device)[:, None])
         if scheme == "ht":
             aug = aug[: aug.shape[0] // 2].reshape(n, p // 2, -1).repeat(1, 2, 1).flatten(end_dim=1)
         if nmask is not None:
@@ -480,6 +481,71 @@ def topk_forward(cfg: Dict[str, Any], ent: torch.Tensor, rel_table: torch.Tensor
         top = torch.topk(sc, k=k, dim=1)
         sc_out.append(top.values)
         ids_out.append(gi[top.indices])
+    return torch.stack(ids_out), torch.stack(sc_out)
+
+
+def exact_scores(cfg: Dict[str, Any], mode: str, fixed: torch.Tensor, rel_rows: torch.Tensor,
+                 cand: torch.Tensor) -> torch.Tensor:
+    """Scores of queries (fixed [Q, W] entity rows + rel_rows [Q, Wr]) against cand [C, W] in
+    the ONE fixed fp32 arithmetic that defines exact ranking (csrc/exact.cu, SURVEY.md 7.2
+    item 3): the score_tails / score_heads expressions of scoring.py:335-356 (TransE),
+    :815-840 (DistMult), :918-946 (ComplEx) evaluated coordinate by coordinate, k = 0..W-1,
+    every product and every sum a separate fp32 rounding (each torch op below rounds once;
+    nothing is fused), IEEE sqrt.  Pure torch: runs on whatever device the inputs live on."""
+    fam, p = cfg["family"], cfg.get("norm_p", 2)
+    tails = mode == "t"
+    f, r, c = fixed.float(), rel_rows.float(), cand.float()
+    W = c.shape[1]
+    if fam == "DistMult":
+        q = f * r
+    elif fam == "ComplEx":
+        e = W // 2
+        f_re, f_im, r_re, r_im = f[:, :e], f[:, e:], r[:, :e], r[:, e:]
+        if tails:
+            q = torch.cat([f_re * r_re - f_im * r_im, f_re * r_im + f_im * r_re], dim=1)
+        else:
+            n_im = -r_im
+            q = torch.cat([r_re * f_re - n_im * f_im, r_re * f_im + n_im * f_re], dim=1)
+    elif fam == "TransE":
+        q = f + r if tails else f - r
+    else:
+        raise ValueError(f"no bit-reproducible arithmetic for {fam}")
+    acc = torch.zeros(q.shape[0], c.shape[0], dtype=torch.float32, device=c.device)
+    ct = c.t().contiguous()
+    for k in range(W):
+        if fam == "TransE":
+            d = q[:, k:k + 1] - ct[k][None, :]
+            term = d.abs() if p == 1 else d * d
+        else:
+            term = q[:, k:k + 1] * ct[k][None, :]
+        acc = acc + term
+    if fam == "TransE":
+        return -(acc if p == 1 else torch.sqrt(acc))
+    return acc
+
+
+def topk_exact(cfg: Dict[str, Any], ent: torch.Tensor, rel_table: torch.Tensor,
+               sh: Dict[str, Any], relation: torch.Tensor, fixed_idx: torch.Tensor, scheme: str,
+               k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`topk_forward` under the exact-ranking arithmetic: `exact_scores` against every real
+    entity, ordered by (score descending, shard ascending, local id ascending) — the order
+    the product's per-shard lists and final merge produce.  Returns (global ids, scores)
+    [n, S, k]; the product must reproduce both BIT FOR BIT."""
+    n, S = relation.shape
+    dev = ent.device
+    ids_out, sc_out = [], []
+    for r in range(n):
+        fixed = ent[r][fixed_idx[r].long()]
+        rel_rows = rel_table[relation[r].long()]
+        scores, gids = [], []
+        for j in range(n):
+            cnt = int(sh["shard_counts"][j])
+            scores.append(exact_scores(cfg, scheme, fixed, rel_rows, ent[j][:cnt]))
+            gids.append(torch.from_numpy(sh["shard_and_idx_to_entity"][j][:cnt].astype(np.int64)))
+        sc = torch.cat(scores, dim=1)
+        order = torch.sort(sc, dim=1, descending=True, stable=True)
+        sc_out.append(order.values[:, :k])
+        ids_out.append(torch.cat(gids).to(dev)[order.indices[:, :k]])
     return torch.stack(ids_out), torch.stack(sc_out)
 
 

@@ -1,6 +1,15 @@
-"""Multi-GPU parity worker (launch with torchrun, one rank per GPU, NCCL):
-distributed EmbeddingMoving training steps vs the CPU oracle.  Run by
-scripts/gpu_multi.sh on an N-GPU box; not collected by pytest."""
+"""Multi-rank parity worker (launched with torchrun by tests/test_gpu_distributed.py, or by
+hand on an N-GPU box): distributed EmbeddingMoving training steps — the NVLink peer-memory
+exchange: routed remote gather, flag handshakes, gradient push, relation all-reduce, all
+inside one captured CUDA graph per rank — vs the CPU oracle, then the distributed inference
+modules vs their local-mode results.
+
+    one rank per GPU (NCCL):   torchrun --nproc-per-node N tests/dist_gpu_worker.py
+    BESS_TEST_SAME_DEVICE=1:   every rank on cuda:0 (a 1-GPU box), rendezvous over gloo; the
+                               symmetric-memory mapping and the kernels are the same, peers are
+                               other processes time-sliced on the same GPU.  NCCL cannot put two
+                               ranks on one device, so the inference modules (which use NCCL
+                               collectives) are skipped in this mode."""
 import os
 import sys
 from pathlib import Path
@@ -18,9 +27,13 @@ from tests import gpu_helpers as H  # noqa: E402
 
 
 def main() -> None:
-    local = int(os.environ["LOCAL_RANK"])
+    same_device = os.environ.get("BESS_TEST_SAME_DEVICE", "0") == "1"
+    local = 0 if same_device else int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if same_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, n = dist.get_rank(), dist.get_world_size()
     for fam, p, scheme, flat, shared, lkind in [
         ("TransE", 1, "t", True, True, "logsigmoid"),
@@ -61,9 +74,12 @@ def main() -> None:
                                    rtol=1e-5, atol=2e-6)
         torch.testing.assert_close(sf.relation_embedding.detach().cpu(), want["rel"], rtol=1e-5,
                                    atol=2e-6)
+        assert step.cuda_graph and len([g for g in step._graphs.values() if g != "warm"]) == 1, \
+            "the distributed step was not captured / replayed"
         if rank == 0:
-            print(f"distributed parity ok: {fam} {scheme} flat={flat} n={n}")
-    inference_parity(rank, n)
+            print(f"distributed parity ok: {fam} {scheme} flat={flat} n={n}", flush=True)
+    if not same_device:
+        inference_parity(rank, n)
     dist.barrier()
     dist.destroy_process_group()
 

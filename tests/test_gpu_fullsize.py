@@ -8,7 +8,21 @@
 * bf16 / fp16 tables (configs[3]: TransE-L1 bf16/fp16; DistMult / ComplEx through
   the kind::f16 tensor-core path): product vs the oracle in fp32 started from
   the same rounded tables, tolerance 1e-2 (north_star).
+* BASELINE.json configs[2] at full size (YAGO3-10-shaped, 123 182 entities, ComplEx d=256 =
+  512-wide fp32 rows, 2048 queries, top-10 against ALL entities): ids, scores, ranks and MRR /
+  Hits@10 BIT-IDENTICAL to the oracle's fixed-order arithmetic (no near-tie tolerance), plus
+  the count of queries on which a plain fp32 matmul ordering disagrees.
+* configs[3] at full size (wikikg2-shaped 2.5 M-entity shard, TransE-L1 d=256, bf16 and fp16,
+  shard_bs 8192, 256 shared negatives): one SGD step vs the fp32 oracle, 1e-2.
+* configs[4] at full size (wikikg2-shaped shards, RotatE / PairRE d=512, ScoreMoving, 500
+  triple-specific candidate tails per query from the real TripleBased sampler): scores, ranks
+  and MRR vs the oracle.
 """
+import json
+import os
+from pathlib import Path
+
+import numpy as np
 import pytest
 import torch
 from torch.testing import assert_close
@@ -128,3 +142,198 @@ def test_training_half_tables_vs_fp32_oracle(dtype, fam, p, scheme):
     assert_close(res["loss"].cpu(), want["loss"][0], rtol=1e-2, atol=1e-2)
     assert_close(sf.entity_embedding.detach().float().cpu(), want["ent"], rtol=1e-2, atol=2e-3)
     assert_close(sf.relation_embedding.detach().float().cpu(), want["rel"], rtol=1e-2, atol=2e-3)
+
+
+def _report(name, **kv):
+    """Counts that are reported rather than asserted (gpurun_out/parity_report.jsonl)."""
+    out = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parents[1])) / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        with open(out / "parity_report.jsonl", "a") as f:
+            f.write(json.dumps(dict(test=name, **kv)) + "\n")
+    except OSError:
+        pass
+    print(name, kv)
+
+
+@pytest.mark.parametrize("n_shard,S,fam,d,scheme,dtype", [
+    (1, 2048, "ComplEx", 256, "t", torch.float32),   # configs[2] as stated
+    (4, 512, "ComplEx", 256, "h", torch.float32),    # same graph on 4 shards (merge of lists)
+    (2, 1024, "DistMult", 256, "t", torch.bfloat16),
+    (1, 1024, "TransE", 256, "t", torch.float32),
+])
+def test_full_size_cfg3_topk_exact_ids_and_mrr(n_shard, S, fam, d, scheme, dtype):
+    B, H = _imports()
+    from besskge_b200.bess import TopKQueryBessKGE
+    from besskge_b200.metric import Evaluation
+    from besskge_b200.negative_sampler import PlaceholderNegativeSampler
+    from besskge_b200.sharding import Sharding
+    E, R, k = 123182, 37, 10
+    sh = Sharding.create(E, n_shard, seed=1234)
+    g = torch.Generator().manual_seed(7)
+    W = 2 * d if fam == "ComplEx" else d
+    Wr = 2 * d if fam == "ComplEx" else d
+    ent = torch.randn(n_shard, sh.max_entity_per_shard, W, generator=g).to(dtype).float()
+    rel = torch.randn(R, Wr, generator=g).to(dtype).float()
+    p = 1 if fam == "TransE" else 2
+    sf = H.make_score_fn(fam, True, p, sh, R, d, ent, rel, dtype=dtype)
+    ev = Evaluation(["mrr", "hits@10"], worst_rank_infty=True, reduction="sum", return_ranks=True)
+    model = TopKQueryBessKGE(k=k, candidate_sampler=PlaceholderNegativeSampler(scheme), score_fn=sf,
+                             evaluation=ev, return_scores=True, window_size=500)
+    lo = int(sh.shard_counts.min())
+    relation = torch.randint(R, (n_shard, S), generator=g, dtype=torch.int32)
+    fixed = torch.randint(lo, (n_shard, S), generator=g, dtype=torch.int32)
+    # ground truth: half of the queries ask for an entity that IS in their exact top-10 (filled in
+    # below from the oracle's own list), half for a random one
+    sh_d = dict(shard_counts=sh.shard_counts, shard_and_idx_to_entity=sh.shard_and_idx_to_entity)
+    cfg = H.score_cfg(fam, d, p)
+    want_ids, want_sc = O.topk_exact(cfg, ent.cuda(), rel.cuda(), sh_d, relation.cuda(),
+                                     fixed.cuda(), scheme, k)
+    want_ids, want_sc = want_ids.flatten(end_dim=1), want_sc.flatten(end_dim=1)
+    truth = torch.randint(E, (n_shard * S,), generator=g)
+    pick = torch.randint(k, (n_shard * S,), generator=g)
+    in_list = torch.rand(n_shard * S, generator=g) < 0.5
+    truth = torch.where(in_list, want_ids.cpu()[torch.arange(n_shard * S), pick], truth)
+    kw = dict(relation=relation, triple_mask=None)
+    kw["head" if scheme == "t" else "tail"] = fixed
+    kw["tail" if scheme == "t" else "head"] = truth.view(n_shard, S).to(torch.int32)
+    res = model(**kw)
+    torch.cuda.synchronize()
+    ids, sc = res["topk_global_id"], res["topk_scores"].float()
+    # --- exact: no tolerance, no near-tie carve-out
+    assert torch.equal(ids.long(), want_ids)
+    if dtype == torch.float32:
+        assert torch.equal(sc, want_sc)
+    want_rank = O.ranks_from_indices(truth.cuda(), want_ids, True)
+    assert torch.equal(res["ranks"], want_rank)
+    mrr = (1.0 / want_rank).view(n_shard, S).sum(-1)
+    hits = (want_rank <= 10).float().view(n_shard, S).sum(-1)
+    names = list(ev.metrics.keys())
+    # ranks are bit-equal (above); Hits@10 is an integer count, exact in any summation order;
+    # the MRR sum of 1/rank is compared to the last few ulp (its reduction order is free)
+    assert torch.equal(res["metrics"][:, names.index("hits@10")], hits)
+    assert_close(res["metrics"][:, names.index("mrr")], mrr, rtol=2e-6, atol=0)
+    # --- reported: how often does another fp32 summation order (one torch matmul / cdist over
+    # the un-sharded table, the reference's own arithmetic on a GPU) pick a different list?
+    n_diff = n_close = 0
+    for r in range(n_shard):
+        q = ent[r][fixed[r].long()].cuda()
+        cand = torch.cat([ent[j][:int(sh.shard_counts[j])] for j in range(n_shard)]).cuda()
+        gid = torch.cat([torch.from_numpy(sh.shard_and_idx_to_entity[j][:int(sh.shard_counts[j])])
+                         for j in range(n_shard)]).cuda()
+        plain = O.score_candidates(cfg, scheme, q, rel.cuda(), relation[r].cuda(),
+                                   cand.unsqueeze(0), True)
+        top = torch.topk(plain, k + 1, dim=1)
+        n_diff += int((gid[top.indices[:, :k]] != want_ids[r * S:(r + 1) * S]).any(-1).sum())
+        gaps = (top.values[:, :-1] - top.values[:, 1:]) / top.values[:, :-1].abs().clamp_min(1e-30)
+        n_close += int((gaps < 1e-6).any(-1).sum())
+    _report("cfg3_topk_exact", n_shard=n_shard, family=fam, dtype=str(dtype), queries=n_shard * S,
+            lists_differing_from_plain_fp32_order=n_diff,
+            queries_with_gap_below_1e_6_relative=n_close)
+    assert n_diff <= n_close + 2  # disagreements only where the decisive gap is rounding noise
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_full_size_cfg4_wikikg2_transe_l1_half_training_step(dtype):
+    B, H = _imports()
+    from besskge_b200.bess import EmbeddingMovingBessKGE, training_model
+    from besskge_b200.optim import SGD
+    from besskge_b200.sharding import Sharding
+    E, R, d, S, N, lr = 2_500_604, 535, 256, 8192, 256, 0.5
+    sh = Sharding.create(E, 1, seed=1234)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ent = (torch.randn(1, E, d, generator=g, device="cuda") * 0.3).to(dtype)
+    rel = (torch.randn(R, d, generator=g, device="cuda") * 0.3).to(dtype)
+    gc = torch.Generator().manual_seed(4)
+    batch = dict(head=torch.randint(E, (1, 1, S), generator=gc, dtype=torch.int32),
+                 tail=torch.randint(E, (1, 1, S), generator=gc, dtype=torch.int32),
+                 relation=torch.randint(R, (1, 1, S), generator=gc, dtype=torch.int32),
+                 negative=torch.randint(E, (1, 1, 1, N), generator=gc, dtype=torch.int32))
+    lcfg = dict(kind="logsigmoid", margin=12.0, negative_adversarial_sampling=True)
+    sf = H.make_score_fn("TransE", True, 1, sh, R, d, ent, rel, dtype=dtype)
+    model = EmbeddingMovingBessKGE(H.fake_sampler("t", True, triple_based=False), sf,
+                                   loss_fn=H.make_loss(lcfg), return_scores=True)
+    step = training_model(model, SGD(lr=lr), cuda_graph=False)
+    res = step(**batch)
+    torch.cuda.synchronize()
+    # fp32 oracle from the same rounded tables, on the rows the step touches (the dense
+    # [2.5 M, 256] autograd gradient would only add zeros)
+    touched = torch.unique(torch.cat([batch[k].flatten().long() for k in ("head", "tail", "negative")]))
+    remap = torch.full((E,), -1, dtype=torch.long)
+    remap[touched] = torch.arange(touched.numel())
+    small = ent[0][touched.cuda()].float().unsqueeze(0).requires_grad_(True)
+    rel32 = rel.float().requires_grad_(True)
+    sb = {k: remap[v.long()].to(torch.int32).cuda() for k, v in batch.items() if k != "relation"}
+    pos, neg = O.embedding_moving_forward(H.score_cfg("TransE", d, 1), small, rel32, sb["head"],
+                                          batch["relation"].cuda(), sb["tail"], sb["negative"],
+                                          "t", True, True)
+    loss = O.loss_value(H.oracle_loss_cfg(lcfg), pos[0], neg[0], torch.ones(1, device="cuda"))
+    loss.backward()
+    assert_close(res["positive_score"].float(), pos[0].detach(), rtol=1e-2, atol=1e-2)
+    assert_close(res["negative_score"].float(), neg[0].detach(), rtol=1e-2, atol=1e-2)
+    assert_close(res["loss"][0], loss.detach(), rtol=1e-2, atol=0)
+    new_small = (small - lr * small.grad).detach()[0]
+    new_rel = (rel32 - lr * rel32.grad).detach()
+    got = sf.entity_embedding.detach()[0]
+    assert_close(got[touched.cuda()].float(), new_small, rtol=1e-2, atol=4e-3)
+    assert_close(sf.relation_embedding.detach().float(), new_rel, rtol=1e-2, atol=4e-3)
+    # the gradient itself (not hidden behind table rounding): step / lr on the touched rows
+    upd = (ent[0][touched.cuda()].float() - got[touched.cuda()].float()) / lr
+    ref = small.grad[0]
+    big = ref.abs() > 0.05
+    assert_close(upd[big], ref[big], rtol=0.1, atol=0.02)
+    untouched = torch.ones(E, dtype=torch.bool, device="cuda")
+    untouched[touched.cuda()] = False
+    assert torch.equal(got[untouched], ent[0][untouched])
+
+
+@pytest.mark.parametrize("fam", ["RotatE", "PairRE"])
+def test_full_size_cfg5_scoremoving_500_candidates(fam):
+    """wikikg2-shaped shards, d=512 fp32 (RotatE rows 4 KiB, PairRE 2 KiB), 500 candidate tails
+    per query split by owning shard by the real TripleBasedShardedNegativeSampler."""
+    B, H = _imports()
+    from besskge_b200.batch_sampler import RigidShardedBatchSampler
+    from besskge_b200.bess import ScoreMovingBessKGE
+    from besskge_b200.dataset import synthetic_kg
+    from besskge_b200.metric import Evaluation
+    from besskge_b200.negative_sampler import TripleBasedShardedNegativeSampler
+    from besskge_b200.sharding import PartitionedTripleSet, Sharding
+    n, S, d, n_cand = 2, 512, 512, 500
+    ds = synthetic_kg("ogbl-wikikg2", seed=1234, n_triple=n * S)
+    ds.neg_tails = {"train": np.random.default_rng(4321).integers(
+        ds.n_entity, size=(n * S, n_cand), dtype=np.int32)}
+    sh = Sharding.create(ds.n_entity, n, seed=1234)
+    pts = PartitionedTripleSet.create_from_dataset(ds, "train", sh)
+    ns = TripleBasedShardedNegativeSampler(pts.neg_heads, pts.neg_tails, sh, "t", 1234)
+    bs = RigidShardedBatchSampler(pts, ns, shard_bs=S, batches_per_step=1, seed=1234)
+    batch = bs[list(range(bs.partition_sample_size))]
+    g = torch.Generator(device="cuda").manual_seed(9)
+    W = 2 * d if fam == "RotatE" else d
+    Wr = 2 * d if fam == "PairRE" else d
+    ent = torch.randn(n, sh.max_entity_per_shard, W, generator=g, device="cuda") * 0.3
+    rel = torch.randn(ds.n_relation_type, Wr, generator=g, device="cuda") * 0.3
+    sf = H.make_score_fn(fam, False, 1, sh, ds.n_relation_type, d, ent, rel)
+    ev = Evaluation(["mrr", "hits@10"], reduction="sum", return_ranks=True)
+    model = ScoreMovingBessKGE(ns, sf, evaluation=ev, return_scores=True)
+    res = model(**{k: v.flatten(end_dim=1) for k, v in batch.items()})
+    torch.cuda.synchronize()
+    dev = {k: v[0].cuda() for k, v in batch.items()}
+    pos, neg = O.score_moving_forward(H.score_cfg(fam, d, 1), ent, rel, dev["head"], dev["relation"],
+                                      dev["tail"], dev["negative"], "t", False, False, True,
+                                      negative_mask=dev["negative_mask"])
+    pos, neg = pos.flatten(), neg.flatten(end_dim=1)
+    assert_close(res["positive_score"], pos, rtol=1e-5, atol=2e-4)
+    assert_close(res["negative_score"], neg, rtol=1e-5, atol=2e-4)
+    want_rank = O.ranks_from_scores(pos.clone(), neg, "average", False)
+    # a rank can only differ where a candidate lies within twice the observed score error
+    err = max(float((res["negative_score"] - neg).abs().max()),
+              float((res["positive_score"] - pos).abs().max()))
+    decisive = ((neg - pos[:, None]).abs() <= 2 * err).any(-1)
+    assert torch.equal(res["ranks"][~decisive], want_rank[~decisive])
+    _report("cfg5_scoremoving", family=fam, queries=int(pos.numel()),
+            max_abs_score_error=err, queries_with_candidate_within_2x_error=int(decisive.sum()),
+            ranks_equal=int((res["ranks"] == want_rank).sum()))
+    m = dev["triple_mask"].flatten()
+    names = list(ev.metrics.keys())
+    got_mrr = res["metrics"][:, names.index("mrr")].sum()
+    assert_close(got_mrr, (1.0 / want_rank)[m].sum(), rtol=1e-5, atol=1e-4)

@@ -166,6 +166,29 @@ def test_topk_oracle(name):
     assert_array_equal(torch.cat(ids)[mask].numpy(), g["topk_global_id"][mask.numpy()])
 
 
+@pytest.mark.parametrize("name", golden_names("topk_"))
+def test_topk_exact_arithmetic_vs_reference(name):
+    """The fixed-order fp32 arithmetic that defines exact ranking (O.exact_scores /
+    O.topk_exact, csrc/exact.cu) against the reference's own TopKQueryBessKGE output: scores
+    within 1e-5, ids IDENTICAL on every fixture (none of them holds a pair of candidates
+    closer than the rounding noise, which is the only place two fp32 orders can disagree)."""
+    cfg, g = load_golden(name)
+    n, bps = cfg["n_shard"], cfg["bps"]
+    c = score_cfg(cfg["family"], cfg["d"], dict(p=cfg["p"]))
+    sh = O.sharding_create(cfg["n_entity"], n, cfg["seed"])
+    ent, rel = T(g["ent"]), T(g["rel"])
+    fixed_key = "in_head" if cfg["scheme"] == "t" else "in_tail"
+    ids, scs = [], []
+    for s in range(bps):
+        i, sc = O.topk_exact(c, ent, rel, sh, T(g["in_relation"])[s], T(g[fixed_key])[s],
+                             cfg["scheme"], cfg["k"])
+        ids.append(i.flatten(end_dim=1))
+        scs.append(sc.flatten(end_dim=1))
+    mask = T(g["triple_mask"]).flatten()
+    assert_close(torch.cat(scs)[mask], T(g["topk_scores"])[mask], rtol=1e-5, atol=1e-5)
+    assert_array_equal(torch.cat(ids)[mask].numpy(), g["topk_global_id"][mask.numpy()])
+
+
 @pytest.mark.parametrize("name", golden_names("pipeline_"))
 def test_all_scores_pipeline_oracle(name):
     """oracle dense restatement of AllScoresPipeline == the reference pipeline's outputs"""
