@@ -55,11 +55,15 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--workload", default="biokg-distmult-d256-fp32", choices=list(WORKLOADS))
     ap.add_argument("--shard-bs", type=int, default=0)
     ap.add_argument("--negatives", type=int, default=0)
+    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "sgdm", "adamw"],
+                    help="sgd: SGD(1e-3) (sparse-exact update); sgdm: SGD(1e-3, momentum 0.95) "
+                         "(nb3 cell 18); adamw: AdamW(1e-3) (nb1 cell 28) - both dense passes")
     ap.add_argument("--n-triple", type=int, default=1 << 21,
                     help="synthetic training triples (sampled with replacement)")
-    ap.add_argument("--ref-shard-bs", type=int, default=4096,
-                    help="micro-batch of the reference CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the wikikg2 secondary workload and the shard_bs 65536 points")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -118,39 +122,77 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-def build_problem(args, n_shard: int):
+def build_problem(workload: str, n_shard: int, shard_bs: int = 0, negatives: int = 0,
+                  n_triple: int = 1 << 21):
     """Synthetic graph of the named shape + sharding + samplers (host side)."""
     from besskge_b200.batch_sampler import RandomShardedBatchSampler
     from besskge_b200.dataset import synthetic_kg
     from besskge_b200.negative_sampler import RandomShardedNegativeSampler
     from besskge_b200.sharding import PartitionedTripleSet, Sharding
 
-    shape, fam, d, p, dt, sbs, nneg = WORKLOADS[args.workload]
-    shard_bs = args.shard_bs or sbs
-    negatives = args.negatives or nneg
-    ds = synthetic_kg(shape, seed=1234, n_triple=args.n_triple)
+    shape, fam, d, p, dt, sbs, nneg = WORKLOADS[workload]
+    shard_bs = shard_bs or sbs
+    negatives = negatives or nneg
+    ds = synthetic_kg(shape, seed=1234, n_triple=n_triple)
     sh = Sharding.create(ds.n_entity, n_shard, seed=1234)
     pts = PartitionedTripleSet.create_from_dataset(ds, "train", sh)
     ns = RandomShardedNegativeSampler(max(negatives // n_shard, 1), sh, 1234, "t", False, True)
     bs = RandomShardedBatchSampler(pts, ns, shard_bs=shard_bs, batches_per_step=1, seed=1234)
-    return dict(ds=ds, sh=sh, ns=ns, bs=bs, fam=fam, d=d, p=p, dtype=dt, shard_bs=shard_bs,
-                negatives=max(negatives // n_shard, 1) * n_shard, shape=shape)
+    return dict(workload=workload, ds=ds, sh=sh, ns=ns, bs=bs, fam=fam, d=d, p=p, dtype=dt,
+                shard_bs=shard_bs, negatives=max(negatives // n_shard, 1) * n_shard, shape=shape)
 
 
-def make_model(prob, device, rank_tables_only=False):
+OPTIMIZERS = {"sgd": "SGD(1e-3)", "sgdm": "SGD(1e-3, momentum=0.95)", "adamw": "AdamW(1e-3)"}
+
+
+def make_optimizer(name: str):
+    from besskge_b200.optim import SGD, AdamW
+    if name == "sgd":
+        return SGD(lr=1e-3)
+    if name == "sgdm":
+        return SGD(lr=1e-3, momentum=0.95)
+    return AdamW(lr=1e-3)
+
+
+def workload_config(prob, n_shard: int, optimizer: str) -> dict:
+    """The `config` object: names the workload; identical for the B200 arm and the reference arm
+    at the same N (everything arm-specific is reported outside `config`)."""
+    return {"workload": prob["workload"], "dataset_shape": prob["shape"],
+            "n_entity": prob["ds"].n_entity, "n_shard": n_shard, "shard_bs": prob["shard_bs"],
+            "negatives_per_triple": prob["negatives"], "loss": "LogSigmoid(12, adversarial)",
+            "optimizer": OPTIMIZERS[optimizer], "score_fn": prob["fam"],
+            "embedding_size": prob["d"],
+            "l2": "no flush: the per-step working set (index lists, gathered rows, the "
+                  "[shard_bs, negatives] score matrix and its gradient) exceeds the 126 MB L2, and "
+                  "every step draws a new batch"}
+
+
+def make_model(prob, device, randn_scale: float = 0.0):
+    """Default initialisers of the score function (training runs), or — for the
+    parity check — randn tables so that scores are O(sqrt(D)) and well separated."""
     from besskge_b200 import scoring
     from besskge_b200.bess import EmbeddingMovingBessKGE
     from besskge_b200.loss import LogSigmoidLoss
 
     torch.manual_seed(1234)
     cls = getattr(scoring, prob["fam"])
+    kw = {}
+    if randn_scale:
+        n, Es = prob["sh"].n_shard, prob["sh"].max_entity_per_shard
+        W = prob["d"] * (2 if prob["fam"] in ("RotatE", "ComplEx", "BoxE") else 1)
+        Wr = {"ComplEx": 2 * prob["d"], "PairRE": 2 * prob["d"]}.get(prob["fam"], prob["d"])
+        g = torch.Generator().manual_seed(4321)
+        dt = DTYPES[prob["dtype"]]
+        kw["entity_initializer"] = (torch.randn(n, Es, W, generator=g) * randn_scale).to(dt).float()
+        kw["relation_initializer"] = (torch.randn(prob["ds"].n_relation_type, Wr, generator=g)
+                                      * randn_scale).to(dt).float()
     if prob["fam"] in ("DistMult", "ComplEx"):
-        sf = cls(True, prob["sh"], prob["ds"].n_relation_type, prob["d"])
+        sf = cls(True, prob["sh"], prob["ds"].n_relation_type, prob["d"], **kw)
     else:
-        sf = cls(True, prob["p"], prob["sh"], prob["ds"].n_relation_type, prob["d"])
+        sf = cls(True, prob["p"], prob["sh"], prob["ds"].n_relation_type, prob["d"], **kw)
     sf = sf.to(device=device, dtype=DTYPES[prob["dtype"]])
     model = EmbeddingMovingBessKGE(prob["ns"], sf, loss_fn=LogSigmoidLoss(12.0, True))
-    return model, sf
+    return model, sf, kw
 
 
 def flat_batch(batch):
@@ -170,10 +212,15 @@ def time_kernel(fn, iters=20, warm=3):
     return st.elapsed_time(en) / iters * 1e-3  # seconds per launch
 
 
-def kernel_rooflines(model, sf, prob, pk):
-    """Stand-alone timing of the dominant negative-scoring kernel and of the gather
-    (CUDA events on the launching stream); algorithmic flops/bytes per launch are
-    those of SURVEY.md §8(d)."""
+L2_BYTES = 126e6
+WIKIKG2_ROWS = 2_500_604
+
+
+def kernel_rooflines(sf, prob, pk, optimizer: str):
+    """Stand-alone timings (CUDA events on the launching stream) of the dominant
+    negative-scoring kernel, of the row gather and the scatter-add COLD (a wikikg2-sized table
+    far larger than L2, 8 distinct index lists in rotation), and of the dense optimizer pass.
+    Algorithmic flops / bytes per launch are those of SURVEY.md 8(d)."""
     from besskge_b200 import _lib as L, kernels as K
 
     dev = sf.entity_embedding.device
@@ -184,22 +231,112 @@ def kernel_rooflines(model, sf, prob, pk):
     cfg = sf.kernel_cfg()
     dt = L.dtype_code(ent.dtype)
     g = torch.Generator(device="cpu").manual_seed(0)
-    idx = torch.randint(ent.shape[0], (2 * S + N,), generator=g, dtype=torch.int32).to(dev)
-    out = torch.empty(2 * S + N, W, dtype=ent.dtype, device=dev)
-    t_gather = time_kernel(lambda: K.gather_rows(ent, idx, out))
-    rows = 2 * S + N
-    gather_bytes = rows * (W * es + 4) + rows * W * es
+
+    # ---- gather / scatter on a table that cannot live in L2 -------------------------------
+    big_rows = max(ent.shape[0], WIKIKG2_ROWS)
+    own_table = ent.shape[0] * W * es > 4 * L2_BYTES
+    big = ent if own_table else torch.randn(big_rows, W, device=dev).to(ent.dtype)
+    n_lists = 8
+
+    def gather_point(s_bs: int):
+        rows = 2 * s_bs + N
+        lists = [torch.randint(big.shape[0], (rows,), generator=g, dtype=torch.int32).to(dev)
+                 for _ in range(n_lists)]
+        out = torch.empty(rows, W, dtype=big.dtype, device=dev)
+        it = [0]
+
+        def fn():
+            K.gather_rows(big, lists[it[0] % n_lists], out)
+            it[0] += 1
+        t = time_kernel(fn, iters=3 * n_lists, warm=n_lists)
+        nbytes = rows * (W * es + 4) + rows * W * es
+        return dict(kernel="gather_route_kernel", bound="hbm", achieved=nbytes / t / 1e9,
+                    peak=pk["hbm"], unit="GB/s", frac=nbytes / t / 1e9 / pk["hbm"],
+                    launch_us=t * 1e6, rows=rows, row_bytes=W * es, shard_bs=s_bs,
+                    table_bytes=big.shape[0] * W * es,
+                    cold=f"{n_lists} distinct random index lists in rotation over a "
+                         f"{big.shape[0] * W * es / 1e9:.2f} GB table (>> 126 MB L2)"
+                         + ("" if own_table else
+                            "; wikikg2-sized stand-in table of this workload's row width: the "
+                            "workload's own shard would fit in L2"))
+
+    def scatter_point(s_bs: int):
+        rows = 2 * s_bs + N
+        key_bits = max(1, int(big.shape[0] - 1).bit_length())
+        ws = torch.empty(K.sort_workspace(rows) // 4 + 64, dtype=torch.int32, device=dev)
+        grad = torch.randn(rows, W, device=dev) * 1e-3
+        lists, uniq = [], 0
+        for _ in range(n_lists):
+            idx = torch.randint(big.shape[0], (rows,), generator=g, dtype=torch.int32)
+            uniq += int(torch.unique(idx).numel())
+            idx = idx.to(dev)
+            sk, sp = torch.empty_like(idx), torch.empty_like(idx)
+            K.sort_keys(idx, rows, key_bits, sk, sp, ws)
+            lists.append((sk, sp))
+        table = big.clone() if own_table else big  # never touch the model's weights
+        it = [0]
+
+        def fn():
+            sk, sp = lists[it[0] % n_lists]
+            K.scatter_sgd(table, sk, sp, rows, rows, 1, grad, 0, 0, 1e-6)
+            it[0] += 1
+        t = time_kernel(fn, iters=3 * n_lists, warm=n_lists)
+        u = uniq / n_lists
+        nbytes = rows * (W * 4 + 8) + u * W * es * 2
+        return dict(kernel="segment_kernel (deterministic segmented scatter-add + SGD; the "
+                           "radix sort runs on a side stream under the forward)",
+                    bound="hbm", achieved=nbytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
+                    frac=nbytes / t / 1e9 / pk["hbm"], launch_us=t * 1e6, rows=rows,
+                    unique_rows=u, grad_row_bytes=W * 4, shard_bs=s_bs,
+                    cold=f"{n_lists} distinct index lists in rotation, {big.shape[0] * W * es / 1e9:.2f} GB table")
+
+    gather = gather_point(S)
+    gather["at_shard_bs_65536"] = gather_point(65536)
+    scatter = scatter_point(S)
+    scatter["at_shard_bs_65536"] = scatter_point(65536)
+    del big
+
+    # ---- dense optimizer pass (momentum / AdamW: every row moves every step) ---------------
+    opt_dense = None
+    if optimizer != "sgd":
+        kind = L.OPT_SGDM if optimizer == "sgdm" else L.OPT_ADAMW
+        Es = ent.shape[0]
+        table = ent.clone()
+        G = 2 * S + N
+        seg = torch.randn(G, W, device=dev) * 1e-3
+        r2s = torch.full((Es,), -1, dtype=torch.int32, device=dev)
+        r2s[torch.randperm(Es, device=dev)[:min(G, Es)]] = torch.arange(min(G, Es), dtype=torch.int32,
+                                                                       device=dev)
+        s0, s1 = torch.zeros(Es, W, device=dev), torch.zeros(Es, W, device=dev)
+        t = time_kernel(lambda: K.opt_dense(kind, table, seg, r2s, s0, s1, 1e-3, 0.95, 0.0, 0.9, 0.999,
+                                            1e-8, 0.01, 2))
+        state = 4 if kind == L.OPT_SGDM else 8
+        nbytes = Es * W * (es + state) * 2 + min(G, Es) * W * 4 + Es * 4
+        opt_dense = dict(kernel="opt_dense_kernel (dense-semantics " + OPTIMIZERS[optimizer] + ")",
+                         bound="hbm", achieved=nbytes / t / 1e9, peak=pk["hbm"], unit="GB/s",
+                         frac=nbytes / t / 1e9 / pk["hbm"], launch_us=t * 1e6, rows=Es,
+                         bytes_per_row=W * (es + state) * 2,
+                         note="table + state exceed L2" if Es * W * (es + state) > 2 * L2_BYTES
+                         else "table + state are L2-resident at this shard size: effective GB/s")
+        del table, s0, s1
+
+    # ---- dominant scoring kernel ------------------------------------------------------------
     nvec = K.call("bess_query_nvec", L.C.byref(cfg))
     qv = torch.randn(S, nvec, W, device=dev)
-    cand = out[2 * S:]
+    cand_idx = torch.randint(ent.shape[0], (N,), generator=g, dtype=torch.int32).to(dev)
+    cand = torch.empty(N, W, dtype=ent.dtype, device=dev)
+    K.gather_rows(ent, cand_idx, cand)
     scores = torch.empty(S, N, device=dev)
-    if prob["fam"] in ("DistMult", "ComplEx"):
-        # dominant kernel: the tcgen05 contraction (forward scores = Q C^T; the two backward
-        # contractions have the same flop count)
+    import besskge_b200.bess as bess_mod
+    tc_l2 = (prob["p"] == 2 and prob["fam"] in ("TransE", "RotatE") and bess_mod.USE_L2_TENSOR_CORES
+             and S * N * W >= bess_mod.L2_TC_MIN_WORK)
+    if prob["fam"] in ("DistMult", "ComplEx") or tc_l2:
+        # dominant kernel: the tcgen05 contraction (forward scores = Q C^T, or the q.c block of the
+        # norm-expanded L2 distance; the two backward contractions have the same flop count)
         from besskge_b200.bess import _TcOperand
         ws = K.Workspace(dev)
         q_op = _TcOperand(ws, "bq", S, W, ent.dtype, False)
-        q_op.fill(L.F32, L.rows(qv.view(S, W)), dt, None, dev)
+        q_op.fill(L.F32, L.rows(qv.view(-1, W)[:S]), dt, None, dev)
         c_op = _TcOperand(ws, "bc", N, W, ent.dtype, False)
         c_op.fill(dt, L.rows(cand), dt, None, dev)
         gws = torch.empty(max(K.dot_gemm_workspace(S, N, W) // 4, 1), device=dev)
@@ -207,39 +344,37 @@ def kernel_rooflines(model, sf, prob, pk):
                                                  S, N, W, scores, L.IDENT, N, 0, False, gws))
         passes = 3 if ent.dtype == torch.float32 else 1
         work = 2.0 * S * N * W
-        roof = dict(kernel="gemm_tc_kernel (tcgen05 shared-negative scores = Q C^T, "
+        what = ("shared-negative scores = Q C^T" if not tc_l2 else
+                "q.c block of the norm-expanded L2 distance ||q||^2 + ||c||^2 - 2 q.c")
+        roof = dict(kernel=f"gemm_tc_kernel (tcgen05, {what}; "
                            + ("3xTF32: 3 tf32 MMAs per product = 6 bf16-equivalent passes"
                               if passes == 3 else "one kind::f16 MMA per product") + ")",
                     bound="tensor", achieved=work / t_score / 1e12, peak=pk["tensor"],
                     unit="TFLOP/s", traffic=None, mma_passes=passes,
                     tensor_pipe_tflops=work * passes * (2 if passes == 3 else 1) / t_score / 1e12)
-    elif prob["p"] == 2:
-        t_score = time_kernel(lambda: K.shared_fwd(cfg, dt, L.MODE_TAILS, qv, S, L.rows(cand), None, N,
-                                                   scores, L.IDENT, N, 0, None))
-        work = 2.0 * S * N * W
-        roof = dict(kernel="pair_fwd_kernel (shared-negative L2 scoring, CUDA-core fp32 path)",
-                    bound="tensor", achieved=work / t_score / 1e12, peak=pk["tensor"],
-                    unit="TFLOP/s", traffic=None)
     else:
+        # CUDA-core register-tiled distance kernel (L1 / small L2 / PairRE / BoxE): S*N*W pair
+        # elements with no reuse a tensor core could exploit; bytes are negligible, the roofline
+        # that binds is the FP32 pipe (148 SMs x 128 lanes x SM clock lane-instr/s)
         t_score = time_kernel(lambda: K.shared_fwd(cfg, dt, L.MODE_TAILS, qv, S, L.rows(cand), None, N,
                                                    scores, L.IDENT, N, 0, None))
-        work = (S * nvec * W * 4) + N * W * es + S * N * 4
-        # the contract's roofline object (HBM bytes) + the roofline that actually binds this kernel:
-        # S*N*W pair elements x 2 FADD on the FP32 pipe (148 SMs x 128 lanes x SM clock), the
-        # algorithmic bytes being only ~17 MB per launch
+        nbytes = (S * nvec * W * 4) + N * W * es + S * N * 4
         try:
             sm_ghz = torch.cuda.get_device_properties(dev).clock_rate * 1e-6
         except AttributeError:
             sm_ghz = 1.965
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = n_sm * 128 * sm_ghz * 1e9
-        fp32_ach = 2.0 * S * N * W / t_score
-        roof = dict(kernel="pair_fwd_kernel (shared-negative L1 scoring)", bound="hbm",
-                    achieved=work / t_score / 1e9, peak=pk["hbm"], unit="GB/s", traffic=None,
-                    note="bytes are negligible here; the binding roofline is fp32_pipe",
+        instr = 2.0 if prob["p"] == 1 else 2.0  # L1: FADD + FADD(|.|); L2: FADD + FFMA
+        fp32_ach = instr * S * N * W / t_score
+        roof = dict(kernel=f"pair_fwd_kernel (shared-negative L{prob['p']} distance, CUDA cores)",
+                    bound="hbm", achieved=nbytes / t_score / 1e9, peak=pk["hbm"], unit="GB/s",
+                    traffic=None,
+                    note="contract object is in HBM bytes, which are negligible for this kernel; the "
+                         "binding roofline is fp32_pipe below",
                     fp32_pipe=dict(achieved=fp32_ach / 1e12, peak=fp32_peak / 1e12,
                                    unit="T lane-instr/s", frac=fp32_ach / fp32_peak,
-                                   work="S*N*W pair elements x 2 FADD"))
+                                   work="S*N*W pair elements x 2 FP32-pipe instructions"))
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists() and prob["fam"] == "DistMult" and (S, N, W) == (16384, 2048, 256) and es == 4:
         roof["traffic"] = json.loads(tf.read_text()).get("gemm_tc_kernel<TF32X3> fwd S=16384 N=2048 W=256")
@@ -249,35 +384,29 @@ def kernel_rooflines(model, sf, prob, pk):
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["launch_us"] = t_score * 1e6
     roof["peak_source"] = pk["source"]
-    gather = dict(kernel="gather_route_kernel", bound="hbm", achieved=gather_bytes / t_gather / 1e9,
-                  peak=pk["hbm"], unit="GB/s", launch_us=t_gather * 1e6, rows=rows,
-                  row_bytes=W * es)
-    gather["frac"] = gather["achieved"] / gather["peak"]
-    return roof, gather
+    return roof, gather, scatter, opt_dense
 
 
-def cpu_port_steps(prob, n_steps: int, shard_bs: int, threads: int):
-    """The reference's plain-PyTorch CPU path (n_shard = 1 arithmetic of bess.py +
-    scoring.py + loss.py, torch autograd, dense torch.optim.SGD) restated by the
-    oracle; returns seconds per step."""
-    from besskge_b200.batch_sampler import RandomShardedBatchSampler
-    from besskge_b200.negative_sampler import RandomShardedNegativeSampler
-    from besskge_b200.sharding import PartitionedTripleSet, Sharding
+def cpu_port_steps(prob, n_steps: int, threads: int, optimizer: str = "sgd"):
+    """The reference's plain-PyTorch CPU path (arithmetic of bess.py + scoring.py + loss.py with
+    emulated cross-replica collectives, torch autograd, dense torch.optim) restated by the
+    oracle, on the SAME sharded workload as the B200 arm (same n_shard, shard_bs, negatives);
+    returns seconds per step."""
     from oracle import besskge_oracle as O
 
     torch.set_num_threads(threads)
-    ds = prob["ds"]
-    sh = Sharding.create(ds.n_entity, 1, seed=1234)
-    pts = PartitionedTripleSet.create_from_dataset(ds, "train", sh)
-    ns = RandomShardedNegativeSampler(prob["negatives"], sh, 1234, "t", False, True)
-    bs = RandomShardedBatchSampler(pts, ns, shard_bs=shard_bs, batches_per_step=1, seed=1234)
+    ds, sh, bs = prob["ds"], prob["sh"], prob["bs"]
+    n = sh.n_shard
     fam, d = prob["fam"], prob["d"]
     W = d * (2 if fam in ("RotatE", "ComplEx", "BoxE") else 1)
     Wr = {"ComplEx": 2 * d, "PairRE": 2 * d, "BoxE": 4 * d + 2}.get(fam, d)
     torch.manual_seed(1234)
-    ent = (torch.rand(1, sh.max_entity_per_shard, W) * 2 - 1).div_(W).requires_grad_(True)
+    ent = (torch.rand(n, sh.max_entity_per_shard, W) * 2 - 1).div_(W).requires_grad_(True)
     rel = (torch.rand(ds.n_relation_type, Wr) * 2 - 1).div_(Wr).requires_grad_(True)
-    opt = torch.optim.SGD([ent, rel], lr=1e-3)
+    if optimizer == "adamw":
+        opt = torch.optim.AdamW([ent, rel], lr=1e-3)
+    else:
+        opt = torch.optim.SGD([ent, rel], lr=1e-3, momentum=0.95 if optimizer == "sgdm" else 0.0)
     cfg = dict(family=fam, d=d, norm_p=prob["p"])
     lcfg = dict(kind="logsigmoid", margin=12.0, adversarial=True, adv_scale=1.0)
     w = torch.tensor([1.0])
@@ -288,8 +417,10 @@ def cpu_port_steps(prob, n_steps: int, shard_bs: int, threads: int):
         opt.zero_grad()
         pos, neg = O.embedding_moving_forward(cfg, ent, rel, b["head"], b["relation"], b["tail"],
                                               b["negative"], "t", True, True)
-        loss = O.loss_value(lcfg, pos[0].float(), neg[0].float(), w)
+        loss = sum(O.loss_value(lcfg, pos[r].float(), neg[r].float(), w) for r in range(n))
         loss.backward()
+        if n > 1:
+            rel.grad.div_(n)
         opt.step()
         times.append(time.perf_counter() - t0)
     return times
@@ -299,26 +430,24 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    prob = build_problem(args, 1)
+    n = max(args.gpus, 1)
+    prob = build_problem(args.workload, n, args.shard_bs, args.negatives, args.n_triple)
     threads = os.cpu_count() or 1
-    sbs = min(args.ref_shard_bs, prob["shard_bs"])
-    times = cpu_port_steps(prob, args.warmup + args.steps, sbs, threads)
+    times = cpu_port_steps(prob, args.warmup + args.steps, threads, args.optimizer)
     t = float(np.mean(times[args.warmup:]))
-    value = sbs / t
+    value = n * prob["shard_bs"] / t
+    sample = (f"{args.steps} whole steps ({args.warmup} warm-up) of the same workload as the B200 arm: "
+              f"n_shard={n} replicas x shard_bs={prob['shard_bs']} triples x {prob['negatives']} shared "
+              "negatives — oracle port of the reference's plain-PyTorch path (forward with emulated "
+              f"collectives + autograd + dense torch.optim) on {threads} host threads")
     line = {
         "impl": "reference", "metric": "train_triples_per_sec", "value": value, "unit": "triples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "dataset_shape": prob["shape"],
-                   "n_entity": prob["ds"].n_entity, "n_shard": 1, "shard_bs": sbs,
-                   "negatives_per_triple": prob["negatives"], "loss": "LogSigmoid(12, adversarial)",
-                   "optimizer": "SGD(1e-3)", "score_fn": prob["fam"], "embedding_size": prob["d"],
-                   "sample": f"bounded sample of the workload: micro-batches of {sbs} triples "
-                             f"(the B200 arm uses {prob['shard_bs']}) on the host cores"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32"}.get(prob["dtype"], prob["dtype"]), "data": "synthetic",
+        "config": workload_config(prob, n, args.optimizer),
         "cpu_baseline": {"value": value, "unit": "triples/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of shard_bs={sbs} (oracle port of the reference's "
-                                   "plain-PyTorch n_shard=1 path: forward + autograd + dense SGD)"},
+                         "sample": sample},
         "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -605,20 +734,106 @@ def main() -> None:
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     import besskge_b200  # noqa: F401  (fails loudly without the CUDA library)
-    from besskge_b200.bess import training_model
-    from besskge_b200.optim import SGD
 
     pk = peaks()
-    n_shard = world
-    prob = build_problem(args, n_shard)
-    model, sf = make_model(prob, dev)
-    step = training_model(model, SGD(lr=1e-3))
+    ctx = dict(world=world, rank=rank, dev=dev, local_rank=local_rank, pk=pk)
+    prob = build_problem(args.workload, world, args.shard_bs, args.negatives, args.n_triple)
+    res = train_leg(ctx, prob, args.optimizer, args.steps, args.warmup, sample_clocks=True)
     S, N = prob["shard_bs"], prob["negatives"]
 
-    total = args.warmup + args.steps
-    # every rank draws the same batches (same seeds); distinct batch per step
+    line = None
+    if rank == 0:
+        roof, gather, scatter, opt_dense = kernel_rooflines(res["sf"], prob, pk, args.optimizer)
+        # the kernel's share of the step (to be compared with the ncu launch list in profiles/)
+        roof["step_share"] = roof["launch_us"] * 1e-3 * (3 if roof["bound"] == "tensor" else 1) \
+            / res["ms_per_step"]
+        line = {
+            "metric": "train_triples_per_sec", "value": res["value"], "unit": "triples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32"}.get(prob["dtype"], prob["dtype"]),
+            "data": "synthetic",
+            "config": workload_config(prob, world, args.optimizer),
+            "e2e": res["e2e"],
+            "gpu_launches": int(res["launches_per_step"]) * args.steps,
+            "gpu_launches_per_step": int(res["launches_per_step"]),
+            "clocks": res["clocks"],
+            "roofline": roof,
+            "gather": gather,
+            "scatter": scatter,
+            "workspace_mb": res["workspace_mb"],
+        }
+        if opt_dense is not None:
+            line["opt_dense"] = opt_dense
+    del res
+
+    # ---- correctness of THIS run's code path at the benchmark shape: step 1 on randn tables
+    # against the oracle (replaces the old `final_loss`, which default-initialised tables make
+    # the same number at every N)
+    if not args.no_parity:
+        par = parity_check(ctx, prob, args.optimizer)
+        if rank == 0:
+            line["parity_check"] = par
+
+    # ---- secondary workload + the shard_bs 65536 points of SURVEY 8(d) --------------------
+    if not args.no_secondary and args.workload == "biokg-distmult-d256-fp32":
+        sec_name = "wikikg2-transe-l1-d256-bf16"  # north_star's scaling workload (configs[3])
+        sprob = build_problem(sec_name, world, 0, 0, args.n_triple)
+        sres = train_leg(ctx, sprob, "sgd", args.steps, args.warmup)
+        points = []
+        for name, sbs in ((args.workload, 65536), (sec_name, 65536)):
+            pprob = build_problem(name, world, sbs, 0, args.n_triple)
+            pres = train_leg(ctx, pprob, "sgd", max(args.steps // 2, 3), 3, want_e2e=False)
+            if rank == 0:
+                points.append({"workload": name, "shard_bs": sbs,
+                               "negatives_per_triple": pprob["negatives"],
+                               "value": pres["value"], "unit": "triples/s",
+                               "ms_per_step": pres["ms_per_step"]})
+            del pres, pprob
+        if rank == 0:
+            sroof, sgather, sscatter, _ = kernel_rooflines(sres["sf"], sprob, pk, "sgd")
+            line["secondary"] = {
+                "metric": "train_triples_per_sec", "value": sres["value"], "unit": "triples/s",
+                "ms_per_step": sres["ms_per_step"], "n_gpus": world, "scaling": "weak",
+                "dtype": sprob["dtype"], "config": workload_config(sprob, world, "sgd"),
+                "e2e": sres["e2e"], "gpu_launches_per_step": int(sres["launches_per_step"]),
+                "roofline": sroof, "gather": sgather, "scatter": sscatter}
+            line["points"] = points
+        del sres
+
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            times = cpu_port_steps(prob, 5, threads, args.optimizer)
+            tc = float(np.mean(times[2:]))
+            line["cpu_baseline"] = {
+                "value": S / tc, "unit": "triples/s", "cores": threads, "kind": "port",
+                "sample": f"3 timed steps (2 warm-up) of the SAME workload (n_shard=1, shard_bs={S}, "
+                          f"{N} shared negatives): oracle port of the reference's plain-PyTorch path "
+                          "(forward + autograd + dense torch.optim)"}
+        else:
+            line["cpu_baseline"] = None
+        emit(line)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool = True,
+              sample_clocks: bool = False):
+    """One workload through the public training call: `value` with the index tensors already
+    staged in HBM (graph replay per step), `e2e` with pinned host batches in and the loss read
+    back every step.  CUDA events on the launching stream, max over ranks."""
+    from besskge_b200 import _lib as L_
+    from besskge_b200.bess import training_model
+
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    model, sf, _ = make_model(prob, dev)
+    step = training_model(model, make_optimizer(optimizer))
+    S = prob["shard_bs"]
+    total = warmup + steps
     host_batches = []
-    for i in range(total):
+    for i in range(total):  # every rank draws the same batches (same seeds); one per step
         b = flat_batch(prob["bs"][[i]])
         host_batches.append({k: v.pin_memory() for k, v in b.items()})
 
@@ -627,91 +842,102 @@ def main() -> None:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
     # -------- kernel-only leg: inputs resident in HBM ------------------------
-    from besskge_b200 import _lib as L_
     staged = [step.stage(**b) for b in host_batches]
     torch.cuda.synchronize()
     launches_per_step = 0
-    for i in range(args.warmup):
+    for i in range(warmup):
         c0 = L_.call("bess_launch_count")
         step.run_staged(staged[i])
         if i == 0:  # the first call runs eagerly: every kernel launch of one step is counted
             launches_per_step = L_.call("bess_launch_count") - c0
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(ctx["local_rank"]) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st.record()
-    for i in range(args.warmup, total):
-        out = step.run_staged(staged[i])
+    for i in range(warmup, total):
+        step.run_staged(staged[i])
     en.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    t_dev = torch.tensor([st.elapsed_time(en) * 1e-3], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t_dev, op=torch.distributed.ReduceOp.MAX)
-    t_dev = float(t_dev.item())
-    loss_last = float(out["loss"].sum().item())
+    clocks = sampler.stop() if sampler else None
+    t_dev = max_over_ranks(st.elapsed_time(en) * 1e-3)
+    out = dict(value=world * S * steps / t_dev, ms_per_step=t_dev / steps * 1e3, clocks=clocks,
+               launches_per_step=launches_per_step, sf=sf, e2e=None)
 
     # -------- end-to-end leg: host batch in, loss out, every step -------------
-    for i in range(min(2, args.warmup)):
-        step(**host_batches[i])["loss"].cpu()
-    barrier()
-    st.record()
-    d2h = 0
-    for i in range(args.warmup, total):
-        l = step(**host_batches[i])["loss"].cpu()
-        d2h = l.numel() * l.element_size()
-    en.record()
-    barrier()
-    t_e2e = torch.tensor([st.elapsed_time(en) * 1e-3], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t_e2e, op=torch.distributed.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
-    h2d = staged[0].h2d_bytes
+    if want_e2e:
+        for i in range(min(2, warmup)):
+            step(**host_batches[i])["loss"].cpu()
+        barrier()
+        st.record()
+        d2h = 0
+        for i in range(warmup, total):
+            l = step(**host_batches[i])["loss"].cpu()
+            d2h = l.numel() * l.element_size()
+        en.record()
+        barrier()
+        t_e2e = max_over_ranks(st.elapsed_time(en) * 1e-3)
+        out["e2e"] = {"value": world * S * steps / t_e2e, "unit": "triples/s",
+                      "h2d_bytes_per_step": staged[0].h2d_bytes, "d2h_bytes_per_step": d2h,
+                      "ms_per_step": t_e2e / steps * 1e3}
+    out["workspace_mb"] = model._ws.bytes() / 1e6
+    del staged, step, model
+    return out
 
+
+def parity_check(ctx, prob, optimizer: str) -> dict:
+    """One training step of the benchmark workload (same shapes, same code path, CUDA graph
+    off) on randn tables, checked against the oracle (CPU): loss of every replica, this
+    rank's updated entity shard and the relation table.  Errors are relative to the largest
+    magnitude of the reference quantity."""
+    from besskge_b200.bess import training_model
+    from oracle import besskge_oracle as O
+
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    model, sf, init = make_model(prob, dev, randn_scale=0.3)
+    lr = 0.05
+    o = make_optimizer(optimizer)
+    o.lr = lr
+    step = training_model(model, o, cuda_graph=False)
+    batch = prob["bs"][[0]]
+    res = step(**flat_batch(batch))
+    torch.cuda.synchronize()
+    got_loss = res["loss"].cpu()
+    got_ent = sf.entity_embedding.detach()[rank if world > 1 else slice(None)].float().cpu()
+    got_rel = sf.relation_embedding.detach().float().cpu()
+    out = None
     if rank == 0:
-        roof, gather = kernel_rooflines(model, sf, prob, pk)
-        cpu = None
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            sbs = min(args.ref_shard_bs, S)
-            times = cpu_port_steps(prob, 5, sbs, threads)
-            tc = float(np.mean(times[2:]))
-            cpu = {"value": sbs / tc, "unit": "triples/s", "cores": threads, "kind": "port",
-                   "sample": f"3 timed steps (2 warm-up) of shard_bs={sbs}, {N} shared negatives, "
-                             "n_shard=1: oracle port of the reference's plain-PyTorch path"}
-        triples = world * S * args.steps
-        ws_bytes = model._ws.bytes()
-        line = {
-            "metric": "train_triples_per_sec", "value": triples / t_dev, "unit": "triples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32"}.get(prob["dtype"], prob["dtype"]),
-            "data": "synthetic",
-            "config": {"workload": args.workload, "dataset_shape": prob["shape"],
-                       "n_entity": prob["ds"].n_entity, "n_shard": n_shard, "shard_bs": S,
-                       "negatives_per_triple": N, "loss": "LogSigmoid(12, adversarial)",
-                       "optimizer": "SGD(1e-3)", "score_fn": prob["fam"], "embedding_size": prob["d"],
-                       "l2": f"no flush: per-step working set {ws_bytes / 1e6:.0f} MB of buffers "
-                             f"+ table > 126 MB L2",
-                       "final_loss": loss_last},
-            "e2e": {"value": triples / t_e2e, "unit": "triples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3},
-            "gpu_launches": None,
-            "clocks": clocks,
-            "roofline": roof,
-            "gather": gather,
-            "cpu_baseline": cpu,
-        }
-        # kernels of this library per step (counted by the library on the eager first step;
-        # later steps replay the same launches from the captured CUDA graph) x timed steps
-        line["gpu_launches"] = int(launches_per_step) * args.steps
-        line["gpu_launches_per_step"] = int(launches_per_step)
-        emit(line)
+        ocfg = {"sgd": dict(kind="sgd", lr=lr), "sgdm": dict(kind="sgd", lr=lr, momentum=0.95),
+                "adamw": dict(kind="adamw", lr=lr)}[optimizer]
+        t0 = time.perf_counter()
+        want = O.training_steps(
+            dict(family=prob["fam"], d=prob["d"], norm_p=prob["p"]),
+            dict(kind="logsigmoid", margin=12.0, adversarial=True, adv_scale=1.0), ocfg,
+            init["entity_initializer"], init["relation_initializer"],
+            [{k: v[0] for k, v in batch.items()}], "t", True, True, "mean")
+
+        def rel_err(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        want_loss = want["loss"][0][rank:rank + 1] if world > 1 else want["loss"][0]
+        want_ent = want["ent"][rank] if world > 1 else want["ent"]
+        tol = 1e-5 if prob["dtype"] == "fp32" else 1e-2
+        errs = dict(loss=rel_err(got_loss, want_loss), entity_table=rel_err(got_ent, want_ent),
+                    relation_table=rel_err(got_rel, want["rel"]))
+        out = dict(what="step 1 on randn(0.3) tables vs the oracle (fp32 CPU autograd + torch.optim)",
+                   max_rel_err=errs, tolerance=tol, ok=bool(max(errs.values()) <= tol * 4),
+                   loss=float(got_loss.sum()), oracle_s=time.perf_counter() - t0)
+    del step, model, sf
     if world > 1:
-        torch.distributed.destroy_process_group()
+        torch.distributed.barrier()
+    return out
 
 
 if __name__ == "__main__":

@@ -122,6 +122,11 @@ SIGNATURES = {
     "bess_peer_wait": [_P, _P, _I, _L, _P],
     "bess_peer_push": [_P, _L, C.POINTER(_P), _I, _L, _P],
     "bess_peer_reduce": [_P, _I, _L, _F, _P, _P],
+    "bess_peer_alloc": [_L, C.POINTER(_P)],
+    "bess_peer_free": [_P],
+    "bess_peer_export": [_P, _P],
+    "bess_peer_import": [_P, C.POINTER(_P)],
+    "bess_peer_unmap": [_P],
     "bess_take_along_rows": [_P, _I, _L, _I, _P, _I, _I, _P, _P],
     "bess_complex_mul": [_I, _P, _P, _I, _I, _I, _P, _P],
     "bess_fill_f32": [_P, _L, _F, _P],

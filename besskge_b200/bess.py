@@ -139,29 +139,58 @@ class _PeerExchange:
         want = (_up(tn_bytes), _up(grad_bytes), _up(rel_bytes))
         if self.buf is not None and all(w <= h for w, h in zip(want, self.sizes)):
             return
-        import torch.distributed._symmetric_memory as symm
-
         sizes = tuple(max(w, h) for w, h in zip(want, self.sizes))
         total = _up(self.FLAG_BYTES) + sum(sizes)
         torch.cuda.synchronize(self.device)
         torch.distributed.barrier()
-        group = torch.distributed.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:  # newer torch enables it implicitly
-            pass
-        buf = symm.empty(total, dtype=torch.uint8, device=self.device)
-        hdl = symm.rendezvous(buf, group)
-        buf.zero_()
+        if self._transport() == "ipc":
+            # this library's own mapping: cudaMalloc + CUDA IPC handles (csrc/peer.cu), the
+            # handles exchanged through the process group's object collective
+            pbuf = K.PeerBuffer(total, self.device)
+            handles: List[Any] = [None] * self.n
+            torch.distributed.all_gather_object(handles, pbuf.export())
+            ptrs = [pbuf.ptr if j == self.rank else K.peer_import(handles[j], self.device)
+                    for j in range(self.n)]
+            buf, hdl = pbuf.tensor, pbuf
+        else:
+            import torch.distributed._symmetric_memory as symm
+
+            group = torch.distributed.group.WORLD
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:  # newer torch enables it implicitly
+                pass
+            buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+            hdl = symm.rendezvous(buf, group)
+            buf.zero_()
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
         self.generation += 1
         torch.cuda.synchronize(self.device)
         torch.distributed.barrier()  # nobody signals before every flag row is zero
         self._keep.append((self.buf, getattr(self, "hdl", None)))  # peers may still map it
         self.buf, self.hdl, self.sizes = buf, hdl, sizes
-        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.ptrs = ptrs
         self.off_tn = _up(self.FLAG_BYTES)
         self.off_grad = self.off_tn + sizes[0]
         self.off_rel = self.off_grad + sizes[1]
+
+    def _transport(self) -> str:
+        """"symm": torch symmetric memory (default on multi-GPU nodes); "ipc": this library's
+        CUDA-IPC mapping — chosen by BESS_PEER_TRANSPORT, or automatically when two ranks share
+        a device (symmetric memory refuses that) or the process group has no NCCL backend."""
+        if getattr(self, "_transport_name", None) is None:
+            name = os.environ.get("BESS_PEER_TRANSPORT", "auto")
+            if name == "auto":
+                ids: List[Any] = [None] * self.n
+                me = (os.uname().nodename, os.environ.get("CUDA_VISIBLE_DEVICES", ""),
+                      torch.cuda.current_device())
+                torch.distributed.all_gather_object(ids, me)
+                backend = str(torch.distributed.get_backend())
+                name = "ipc" if len(set(ids)) < self.n or "nccl" not in backend else "symm"
+            if name not in ("symm", "ipc"):
+                raise ValueError(f"BESS_PEER_TRANSPORT={name!r}: expected auto, symm or ipc")
+            self._transport_name = name
+        return self._transport_name
 
     def view(self, offset: int, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
         nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
@@ -1430,12 +1459,14 @@ class TrainingModel:
             torch.cuda.synchronize()
             with torch.cuda.graph(graph):
                 out = self._eager(staged)
-            if self._graph_gen != self._generation():  # sized differently than the warm run
+            if self._graph_gen != self._generation():
+                # capture re-allocated a buffer (sized differently than the warm run): the
+                # recorded pointers are already stale; nothing ran, so run this call eagerly
                 self._graphs.clear()
                 self._graph_gen = None
-                return out
-            self._graphs[key] = (graph, out)
-            return out
+                del graph
+                return self._eager(staged)
+            entry = self._graphs[key] = (graph, out)
         graph, out = entry
         graph.replay()
         return out

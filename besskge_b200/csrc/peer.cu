@@ -18,6 +18,7 @@
 // Waits are bounded in wall-clock time (caller-chosen, minutes by default): a peer that never
 // arrives traps the launch instead of hanging the GPU for ever.
 #include <cstdio>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -157,5 +158,58 @@ extern "C" int bess_peer_reduce(const float* slots, int n, int64_t count, float 
   if (blocks > 4 * kNumSM) blocks = 4 * kNumSM;
   peer_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(slots, n, count, scale, out);
   BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Peer-mapped buffers without any framework: cudaMalloc + CUDA IPC handles.
+// Every rank allocates its receive buffer with bess_peer_alloc, exports a 64-byte handle,
+// the handles travel through whatever side channel the host has (torch.distributed
+// all_gather_object here) and bess_peer_import maps each peer's buffer into this process.
+// Works between GPUs of one node (peer access over NVLink is enabled lazily by the driver)
+// and between two processes that share ONE GPU — which is how the 2-rank protocol test runs
+// on a single-GPU box.  torch's symmetric-memory allocator (the default transport on
+// multi-GPU nodes) refuses the latter.
+// ---------------------------------------------------------------------------
+#define BESS_CUDA_TRY(expr, what)                                                   \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      bess_set_error("%s: %s", what, cudaGetErrorString(_e));                       \
+      return BESS_ERR_CUDA;                                                         \
+    }                                                                               \
+  } while (0)
+
+extern "C" int bess_peer_alloc(int64_t bytes, void** ptr) {
+  BESS_CHECK_ARG(bytes > 0 && ptr != nullptr, "bess_peer_alloc: bytes > 0 and an out pointer required");
+  BESS_CUDA_TRY(cudaMalloc(ptr, (size_t)bytes), "bess_peer_alloc (cudaMalloc)");
+  BESS_CUDA_TRY(cudaMemset(*ptr, 0, (size_t)bytes), "bess_peer_alloc (cudaMemset)");
+  BESS_CUDA_TRY(cudaDeviceSynchronize(), "bess_peer_alloc (sync)");
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_free(void* ptr) {
+  if (ptr != nullptr) BESS_CUDA_TRY(cudaFree(ptr), "bess_peer_free");
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_export(void* ptr, void* handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == BESS_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  BESS_CUDA_TRY(cudaIpcGetMemHandle(&h, ptr), "bess_peer_export (cudaIpcGetMemHandle)");
+  memcpy(handle_out, &h, sizeof(h));
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_import(const void* handle, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  BESS_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess),
+                "bess_peer_import (cudaIpcOpenMemHandle)");
+  return BESS_OK;
+}
+
+extern "C" int bess_peer_unmap(void* ptr) {
+  if (ptr != nullptr) BESS_CUDA_TRY(cudaIpcCloseMemHandle(ptr), "bess_peer_unmap");
   return BESS_OK;
 }

@@ -433,6 +433,35 @@ def peer_reduce(slots: torch.Tensor, n: int, count: int, scale: float, out: torc
     call("bess_peer_reduce", slots.data_ptr(), n, count, float(scale), out.data_ptr(), _st(out))
 
 
+class PeerBuffer:
+    """A zero-filled device buffer from bess_peer_alloc, exportable to other processes
+    through a CUDA IPC handle; `tensor` is a zero-copy uint8 view of it."""
+
+    def __init__(self, nbytes: int, device: torch.device) -> None:
+        p = C.c_void_p()
+        with torch.cuda.device(device):
+            call("bess_peer_alloc", int(nbytes), C.byref(p))
+        self.ptr, self.nbytes, self.device = int(p.value), int(nbytes), device
+        self.__cuda_array_interface__ = dict(shape=(self.nbytes,), typestr="|u1",
+                                             data=(self.ptr, False), version=3, strides=None)
+        self.tensor = torch.as_tensor(self, device=device)
+        assert self.tensor.data_ptr() == self.ptr
+
+    def export(self) -> bytes:
+        h = (C.c_ubyte * 64)()
+        call("bess_peer_export", self.ptr, h)
+        return bytes(h)
+
+
+def peer_import(handle: bytes, device: torch.device) -> int:
+    """Map another process's PeerBuffer (by its exported handle); returns the device pointer."""
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    with torch.cuda.device(device):
+        call("bess_peer_import", buf, C.byref(p))
+    return int(p.value)
+
+
 def fill_f32(t: torch.Tensor, v: float) -> None:
     call("bess_fill_f32", t.data_ptr(), t.numel(), float(v), _st(t))
 

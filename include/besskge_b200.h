@@ -434,6 +434,17 @@ int bess_peer_push(const void* src, int64_t src_stride_bytes, void* const* dst /
                    int n, int64_t bytes_each, void* stream);
 int bess_peer_reduce(const float* slots, int n, int64_t count, float scale, float* out, void* stream);
 
+/* Peer-mapped receive buffers through CUDA IPC (no framework involved): alloc (zero-filled,
+ * synchronous) -> export a BESS_IPC_HANDLE_BYTES-byte handle -> ship it to the peers over any
+ * host channel -> import maps the peer's buffer into this process (between GPUs of a node, or
+ * between two processes sharing one GPU).  A process must not import its own handle. */
+#define BESS_IPC_HANDLE_BYTES 64
+int bess_peer_alloc(int64_t bytes, void** ptr);
+int bess_peer_free(void* ptr);
+int bess_peer_export(void* ptr, void* handle_out /* BESS_IPC_HANDLE_BYTES */);
+int bess_peer_import(const void* handle, void** ptr);
+int bess_peer_unmap(void* ptr);
+
 /* Python-surface helpers of the reference's utils.py.
  * take_along_rows (utils.py:10-33 `gather_indices`): out[i, j] = x[i or 0, index[i or 0, j]];
  *   x [a, e] of elem_bytes-wide words (1/2/4/8), index int32 [b, k], a == b or one of them 1,

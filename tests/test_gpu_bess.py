@@ -50,7 +50,9 @@ def test_bess_forward_vs_reference_golden(name):
     lower = 1.0 + (neg_g > pos_g + 2 * err).sum(-1).float()
     upper = 1.0 + (neg_g >= pos_g - 2 * err).sum(-1).float()
     assert bool(((ranks >= lower) & (ranks <= upper)).all())
-    assert int(near.sum()) <= 0.1 * near.numel(), f"{int(near.sum())} near-tie rows (err {err:g})"
+    # (the fixtures draw candidates from few entities, so 10-20 % of the rows have the true entity
+    # among their candidates: an exact tie in exact arithmetic, an ulp apart in any fp32 one)
+    assert int(near.sum()) <= 0.25 * near.numel(), f"{int(near.sum())} near-tie rows (err {err:g})"
     assert res["metrics"].shape == tuple(g["metrics"].shape)
     assert_close((1.0 / ranks[~near]).sum(), (1.0 / want[~near]).sum(), rtol=1e-6, atol=0)
 
