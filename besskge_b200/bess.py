@@ -248,6 +248,9 @@ class _Pass:
 # (csrc/gemm_tc.cu).  The exact-fp32 CUDA-core tile kernel (csrc/pair.cu)
 # computes the same thing and is kept selectable for A/B parity tests only.
 USE_TENSOR_CORES = True
+# score_triple fwd / bwd and the relation-table reduce on a second stream, concurrent with the
+# negative-scoring / contraction kernels (A/B switch: BESS_OVERLAP=0)
+OVERLAP_SMALL_KERNELS = os.environ.get("BESS_OVERLAP", "1") != "0"
 # TransE / RotatE with scoring_norm=2 against shared negatives: norm-expanded distance
 # ||q||^2 + ||c||^2 - 2 q.c with the q.c block (and both backward contractions) on the tcgen05
 # GEMM (csrc/l2.cu).  The expansion carries an absolute error of ~1e-6 (||q||^2 + ||c||^2) in the
@@ -404,6 +407,14 @@ class BessKGE(torch.nn.Module, ABC):
             self._side = torch.cuda.Stream(dev)
         return self._side
 
+    def _aux_stream(self, dev: torch.device) -> "torch.cuda.Stream":
+        """Second side stream: small HBM-bound kernels that are independent of the big
+        scoring / contraction kernels (score_triple forward and backward, the relation-table
+        reduce) run here, concurrently with them (fork / join is part of the captured graph)."""
+        if getattr(self, "_aux", None) is None or self._aux.device != dev:
+            self._aux = torch.cuda.Stream(dev)
+        return self._aux
+
     # -------------------------------------------------------------- forward
     def forward(
         self,
@@ -438,6 +449,38 @@ class BessKGE(torch.nn.Module, ABC):
         buf = self._ws.get("in_" + name, tuple(t.shape), dtype)
         buf.copy_(t, non_blocking=True)
         return buf
+
+    _PIN_SLOTS = 4
+
+    def _pinned(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+        """Next slot of the pinned staging ring of `name` (host side of an async H2D copy).
+        A slot is reused only after the copy that last read it has completed."""
+        ring = self.__dict__.setdefault("_pin_rings", {})
+        ent = ring.get(name)
+        n = int(np.prod(shape)) if len(shape) else 1
+        if ent is None or ent["dtype"] != dtype or ent["numel"] < n:
+            ent = ring[name] = dict(dtype=dtype, numel=max(n, 1), pos=-1, used=False,
+                                    bufs=[torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+                                          for _ in range(self._PIN_SLOTS)],
+                                    events=[None] * self._PIN_SLOTS)
+        ent["pos"] = (ent["pos"] + 1) % self._PIN_SLOTS
+        ev = ent["events"][ent["pos"]]
+        if ev is not None:
+            ev.synchronize()
+        ent["used"] = True
+        return ent["bufs"][ent["pos"]][:n].view(*shape)
+
+    def _pinned_done(self, name: str) -> None:
+        """Record, on the current stream, that the H2D copy out of the current slot of `name`
+        has been enqueued."""
+        ent = self.__dict__.get("_pin_rings", {}).get(name)
+        if ent is None or not ent["used"]:
+            return
+        ev = ent["events"][ent["pos"]]
+        if ev is None:
+            ev = ent["events"][ent["pos"]] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self._ws.device))
+        ent["used"] = False
 
     def _step_rows(self, placement: _Placement, bps: int) -> List[List[int]]:
         """rows of the STAGED inputs used at each step, one per local replica
@@ -558,26 +601,42 @@ class EmbeddingMovingBessKGE(BessKGE):
         B, Nn = negative.shape[-2], negative.shape[-1]
         S = n * p
         local = bool(self.negative_sampler.local_sampling)
-        h2 = _as_i32(head).reshape(L_rows, S)
-        t3 = _as_i32(tail).reshape(L_rows, n, p)
-        n3 = _as_i32(negative).reshape(L_rows, n, B * Nn)
+        # distributed mode: this rank needs (and packs, and copies) only its own rows
+        mine = slice(pl.rank, None, n) if pl.distributed else slice(None)
+        h2 = _as_i32(head).reshape(L_rows, S)[mine]
+        t3 = _as_i32(tail).reshape(L_rows, n, p)[mine]
+        n3 = _as_i32(negative).reshape(L_rows, n, B * Nn)[mine]
+        rows = h2.shape[0]
+        G = S + n * (p + B * Nn)
+        # the packed gather list is assembled directly in pinned memory (one slot of a small
+        # ring, so the asynchronous H2D copy of a previous call is never overwritten)
+        gidx_h = self._pinned("gidx", (rows, G), torch.int32)
+        gidx_h[:, :S] = h2
         if local:
-            gidx_h = torch.cat([h2, n3.reshape(L_rows, -1), t3.reshape(L_rows, -1)], dim=1)
+            gidx_h[:, S:S + n * B * Nn] = n3.reshape(rows, -1)
+            gidx_h[:, S + n * B * Nn:] = t3.reshape(rows, -1)
         else:
-            gidx_h = torch.cat([h2, torch.cat([t3, n3], dim=2).reshape(L_rows, -1)], dim=1)
+            body = gidx_h[:, S:].view(rows, n, p + B * Nn)
+            body[:, :, :p] = t3
+            body[:, :, p:] = n3
 
-        def put(name, t, dtype):
+        def put(name, t, dtype, sliced=False):
             if t is None:
                 return None
-            if pl.distributed:  # this rank only needs (and copies) its own rows
-                t = t[pl.rank::n]
+            if not sliced:
+                t = t[mine]
             if persistent:
                 return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+            if not t.is_pinned() or t.dtype != dtype or not t.is_contiguous():
+                host = self._pinned(name, tuple(t.shape), dtype)
+                host.copy_(t)
+                t = host
             return self._stage(name, t, dtype, dev)
 
         st = _Staged()
         st.dims = (L_rows, n, p, B, Nn)
-        st.gidx = put("gidx", gidx_h, torch.int32)
+        st.gidx = put("gidx", gidx_h, torch.int32, sliced=True)
+        self._pinned_done("gidx")
         st.rel = put("rel", relation.reshape(L_rows, S), torch.int32)
         st.tw = put("tw", None if triple_weight is None else triple_weight.reshape(L_rows, -1),
                     torch.float32)
@@ -587,6 +646,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                            torch.bool if negative_mask.dtype == torch.bool else torch.uint8)
         st.tmask = put("tmask", None if triple_mask is None else triple_mask.reshape(L_rows, -1),
                        torch.bool)
+        for name in ("rel", "tw", "nmask", "tmask"):
+            self._pinned_done(name)
         st.h2d_bytes = sum(t.numel() * t.element_size()
                            for t in (st.gidx, st.rel, st.tw, st.nmask, st.tmask) if t is not None)
         return st
@@ -751,6 +812,11 @@ class EmbeddingMovingBessKGE(BessKGE):
         scheme = self.negative_sampler.corruption_scheme
 
         side = self._side_stream(dev) if train else None
+        # score_triple (forward and backward) only touches rows that the negative-scoring
+        # kernels never write — unless augment_negative makes the micro-batch's own heads /
+        # tails candidates as well — so it runs on a second stream next to them
+        overlap = OVERLAP_SMALL_KERNELS and not self.augment_negative
+        aux_st = self._aux_stream(dev) if overlap else None
         for s, step_rows in enumerate(self._step_rows(pl, bps)):
             if train:
                 # The sort permutations of the scatter depend only on the step's indices:
@@ -804,8 +870,15 @@ class EmbeddingMovingBessKGE(BessKGE):
                 head_rows = L.rows(Hl)
                 tail_rows = L.rows(TNl, rmap=L.rowmap(p, per, 0))
                 # ================= positive scores =================
-                K.triple_fwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S, pos,
-                             L.IDENT)
+                if overlap:
+                    main = torch.cuda.current_stream(dev)
+                    aux_st.wait_stream(main)
+                    with torch.cuda.stream(aux_st):
+                        K.triple_fwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S,
+                                     pos, L.IDENT)
+                else:
+                    K.triple_fwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S,
+                                 pos, L.IDENT)
                 # ================= negative scores =================
                 for pi, ps in enumerate(passes):
                     fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
@@ -857,6 +930,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                         K.pertriple_fwd(cfg, dt, ps.mode, qv, ps.n_query, cand, ps.q_stride,
                                         ps.n_cand, neg, ps.qmap, N, ps.col0,
                                         None if aux is None else aux[li])
+                if overlap:
+                    torch.cuda.current_stream(dev).wait_stream(aux_st)  # positive scores ready
                 # ================= masks (bess.py:182-245) =================
                 self._apply_masks(neg, S, N, p, B, Nn, n, nmask[row] if nmask is not None else None,
                                   flat, scheme)
@@ -891,10 +966,22 @@ class EmbeddingMovingBessKGE(BessKGE):
                     if ce_copy and want_scores:
                         score_for_bwd = ws.get("neg_unshift", (R, S, N), torch.float32)[li]
                     dHl, dTNl = dH[li], dTN[li].view(n * per, W)
-                    K.triple_bwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S,
-                                 pos, d_pos[li], L.IDENT, L.rows(dHl),
-                                 L.rows(dTNl, rmap=L.rowmap(p, per, 0)), dRq[li], False, False,
-                                 False)
+                    main = torch.cuda.current_stream(dev)
+                    if overlap:
+                        aux_st.wait_stream(main)
+                    with torch.cuda.stream(aux_st if overlap else main):
+                        K.triple_bwd(cfg, dt, head_rows, tail_rows, rel_table, rel[row], L.IDENT, S,
+                                     pos, d_pos[li], L.IDENT, L.rows(dHl),
+                                     L.rows(dTNl, rmap=L.rowmap(p, per, 0)), dRq[li], False, False,
+                                     False)
+                    tb_joined = not overlap
+
+                    def join_triple_bwd():
+                        # score_triple's gradients (dH, tail rows of dTN, dRq) are complete
+                        nonlocal tb_joined
+                        if not tb_joined:
+                            torch.cuda.current_stream(dev).wait_stream(aux_st)
+                            tb_joined = True
                     if early_push:
                         for pi, ps in enumerate(passes):
                             d_cand = self._cand_rows(ps, dHl, dTNl, local)
@@ -902,6 +989,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                                        tc_q[pi].ldt, ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
                                        d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base,
                                        a_mn_major=True, a_offset_elems=ps.col0)
+                        join_triple_bwd()
                         main = torch.cuda.current_stream(dev)
                         side.wait_stream(main)
                         with torch.cuda.stream(side):
@@ -943,6 +1031,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                                 K.dot_gemm(dt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot,
                                            q_op.ldt, ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
                                            d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base)
+                            join_triple_bwd()
                             K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                            ps.n_query, d_qv, d_fixed, dRq[li], True, True)
                             continue
@@ -970,6 +1059,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                                        W, nq_, d_qv, d_cand.map, d_cand.pitch, 0, ps.aug, gemm_ws,
                                        out_ptr=d_cand.base)
                             K.rows_axpy(dt, cb, -1.0, cand, d_cand, nc_, W)
+                            join_triple_bwd()
                             K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                            nq_, d_qv, d_fixed, dRq[li], True, True)
                             continue
@@ -978,20 +1068,30 @@ class EmbeddingMovingBessKGE(BessKGE):
                             if need_scale:
                                 scale = scale_buf[:ps.n_cand]
                                 K.cand_inv_norm(dt, cand, ps.n_cand, W, scale)
+                            # dQ and dC are independent: the candidate-gradient kernel goes
+                            # to the second stream (after score_triple's backward there)
+                            cand_st = aux_st if (overlap and not need_scale) else main
+                            if cand_st is not main:
+                                cand_st.wait_stream(torch.cuda.current_stream(dev))
+                            with torch.cuda.stream(cand_st):
+                                K.shared_bwd_cand(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
+                                                  ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
+                                                  ps.col0, a, d_cand, cand_ws, add=ps.aug)
                             K.shared_bwd_query(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
                                                ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
                                                ps.col0, a, d_qv)
-                            K.shared_bwd_cand(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
-                                              ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
-                                              ps.col0, a, d_cand, cand_ws, add=ps.aug)
+                            if cand_st is not main:
+                                tb_joined = False  # more work on the second stream: join again
                             if need_scale:
                                 K.cand_norm_bwd(dt, cand, ps.n_cand, W, scale, d_cand)
                         else:
                             K.pertriple_bwd(cfg, dt, ps.mode, qv, ps.n_query, cand, ps.q_stride,
                                             ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
                                             ps.col0, a, d_qv, d_cand)
+                        join_triple_bwd()
                         K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                        ps.n_query, d_qv, d_fixed, dRq[li], True, True)
+                    join_triple_bwd()
                     if cfg.family == L.BOXE:
                         K.boxe_rel_finalize(cfg, dt, rel_table, rel[row], S, dRq[li])
 
@@ -1008,27 +1108,29 @@ class EmbeddingMovingBessKGE(BessKGE):
                 hyper = self._hyper(bps)[s]  # filled by TrainingModel before this call / replay
                 main = torch.cuda.current_stream(dev)
                 main.wait_stream(side)  # join: permutations ready (and the early gradient push)
-                # relation table (replicated): reduce per-query rows of all local replicas; its
-                # all-reduce over peer memory runs on the side stream under the entity scatter
-                K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
-                                       rel_table.shape[0], d_rel_table)
+                # relation table (replicated): reduce per-query rows of all local replicas, then
+                # its all-reduce over peer memory — on the side stream, under the entity scatter
                 mean = getattr(optimizer, "relation_grad_reduction", "mean") == "mean"
-                if px is not None:
-                    # every rank pushes its partial into slot [rank] of every rank, then sums the
-                    # n slots in rank order (bit-identical tables on all ranks)
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
+                rel_st = side if (px is not None or overlap) else main
+                if rel_st is not main:
+                    rel_st.wait_stream(main)
+                with torch.cuda.stream(rel_st):
+                    K.relation_grad_reduce(dRq.view(R * S, Wr), Wr, rk, rp, R * S,
+                                           rel_table.shape[0], d_rel_table)
+                    if px is not None:
+                        # every rank pushes its partial into slot [rank] of every rank, then sums
+                        # the n slots in rank order (bit-identical tables on all ranks)
                         cnt = _up(rel_table.numel() * 4, 16) // 4
                         K.peer_push(d_rel_table, 0,
                                     [q + px.off_rel + pl.rank * cnt * 4 for q in px.ptrs], cnt * 4)
                         px.handshake(2)
                         K.peer_reduce(px.view(px.off_rel, (n, cnt), torch.float32), n, cnt,
                                       1.0 / n if mean else 1.0, d_rel_table)
-                else:
-                    if pl.distributed:
-                        torch.distributed.all_reduce(d_rel_table)
-                    if mean and n > 1:
-                        d_rel_table.mul_(1.0 / n)
+                    else:
+                        if pl.distributed:
+                            torch.distributed.all_reduce(d_rel_table)
+                        if mean and n > 1:
+                            d_rel_table.mul_(1.0 / n)
                 acc_k = self._accum_k
                 acc_phase = (self._accum_phase0 + s) % acc_k
                 for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
@@ -1044,8 +1146,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                     else:
                         self._update_entity(optimizer, ent[shard], shard, sk[li], sp[li], G,
                                             n_loc_rows, per, dH[li], g_dst, stride_rows, hyper, ws)
-                if px is not None:
-                    main.wait_stream(side)  # relation all-reduce done
+                if rel_st is not main:
+                    main.wait_stream(rel_st)  # relation gradient reduced (and all-reduced)
                 if acc_k > 1:
                     # relation table: one slot per micro-batch of the cycle, summed in slot
                     # order on the last one (deterministic), then one optimizer step
