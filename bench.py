@@ -335,23 +335,28 @@ def kernel_rooflines(sf, prob, pk, optimizer: str):
         # norm-expanded L2 distance; the two backward contractions have the same flop count)
         from besskge_b200.bess import _TcOperand
         ws = K.Workspace(dev)
-        q_op = _TcOperand(ws, "bq", S, W, ent.dtype, False)
+        fmt = dt if tc_l2 else bess_mod._operand_format(ent.dtype)
+        q_op = _TcOperand(ws, "bq", S, W, ent.dtype, False, fmt)
         q_op.fill(L.F32, L.rows(qv.view(-1, W)[:S]), dt, None, dev)
-        c_op = _TcOperand(ws, "bc", N, W, ent.dtype, False)
+        c_op = _TcOperand(ws, "bc", N, W, ent.dtype, False, fmt)
         c_op.fill(dt, L.rows(cand), dt, None, dev)
         gws = torch.empty(max(K.dot_gemm_workspace(S, N, W) // 4, 1), device=dev)
-        t_score = time_kernel(lambda: K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
-                                                 S, N, W, scores, L.IDENT, N, 0, False, gws))
-        passes = 3 if ent.dtype == torch.float32 else 1
+        t_score = time_kernel(lambda: K.dot_gemm(fmt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo,
+                                                 c_op.ld, S, N, W, scores, L.IDENT, N, 0, False, gws,
+                                                 a_scale=q_op.scale, b_scale=c_op.scale))
+        passes = 3 if fmt in (L.F32, L.F16X3) else 1
+        equiv = passes * (2 if fmt == L.F32 else 1)  # bf16-equivalent tensor-pipe passes per product
         work = 2.0 * S * N * W
         what = ("shared-negative scores = Q C^T" if not tc_l2 else
                 "q.c block of the norm-expanded L2 distance ||q||^2 + ||c||^2 - 2 q.c")
-        roof = dict(kernel=f"gemm_tc_kernel (tcgen05, {what}; "
-                           + ("3xTF32: 3 tf32 MMAs per product = 6 bf16-equivalent passes"
-                              if passes == 3 else "one kind::f16 MMA per product") + ")",
+        how = {L.F32: "3xTF32: 3 tf32 MMAs per product = 6 bf16-equivalent passes (ceiling 1/6 of peak)",
+               L.F16X3: "3xFP16: fp32 operands as scaled fp16 hi/lo pairs, 3 kind::f16 MMAs per "
+                        "product = 3 bf16-equivalent passes (ceiling 1/3 of peak), fp32-grade products"
+               }.get(fmt, "one kind::f16 MMA per product")
+        roof = dict(kernel=f"gemm_tc_kernel (tcgen05, {what}; {how})",
                     bound="tensor", achieved=work / t_score / 1e12, peak=pk["tensor"],
                     unit="TFLOP/s", traffic=None, mma_passes=passes,
-                    tensor_pipe_tflops=work * passes * (2 if passes == 3 else 1) / t_score / 1e12)
+                    tensor_pipe_tflops=work * equiv / t_score / 1e12)
     else:
         # CUDA-core register-tiled distance kernel (L1 / small L2 / PairRE / BoxE): S*N*W pair
         # elements with no reuse a tensor core could exploit; bytes are negligible, the roofline
@@ -377,7 +382,9 @@ def kernel_rooflines(sf, prob, pk, optimizer: str):
                                    work="S*N*W pair elements x 2 FP32-pipe instructions"))
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists() and prob["fam"] == "DistMult" and (S, N, W) == (16384, 2048, 256) and es == 4:
-        roof["traffic"] = json.loads(tf.read_text()).get("gemm_tc_kernel<TF32X3> fwd S=16384 N=2048 W=256")
+        key = ("gemm_tc_kernel<F16X3> fwd S=16384 N=2048 W=256" if bess_mod.USE_F16X3 else
+               "gemm_tc_kernel<TF32X3> fwd S=16384 N=2048 W=256")
+        roof["traffic"] = json.loads(tf.read_text()).get(key)
     if tf.exists() and prob["fam"] == "TransE" and prob["p"] == 1 and (S, N, W) == (8192, 256, 256) and es == 2:
         # (the score matrix written by this launch stays in L2: the capture shows 0 bytes written to DRAM)
         roof["traffic"] = json.loads(tf.read_text()).get("pair_fwd_kernel L1 bf16 S=8192 N=256 W=256")

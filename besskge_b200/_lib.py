@@ -14,6 +14,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libbesskge_b200.so"
 
 F32, F16, BF16 = 0, 1, 2
+F16X3 = 3  # operand format of the tensor-core path: scaled fp16 (hi, lo) pairs of fp32 values
 TRANSE, ROTATE, DISTMULT, COMPLEX, PAIRRE, BOXE, TRIPLERE = range(7)
 MODE_TAILS, MODE_HEADS = 0, 1
 LOSS_LOGSIGMOID, LOSS_MARGIN_RANKING, LOSS_SOFTMAX_CE = 0, 1, 2
@@ -83,8 +84,10 @@ SIGNATURES = {
     "bess_score_shared_bwd_cand": [_CFG, _I, _I, _P, _I, Rows, _P, _I, _P, _P, RowMap, _L, _I, _P,
                                    Rows, _I, _P, _P],
     "bess_dot_gemm_workspace": [_I, _I, _I],
-    "bess_dot_gemm": [_I, _P, _P, _L, _I, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P],
-    "bess_split_operand": [_I, Rows, _I, _I, _P, _I, _P, _P, _L, _P, _P, _L, _P],
+    "bess_dot_gemm": [_I, _P, _P, _L, _I, _P, _P, _L, _I, _I, _I, _P, RowMap, _L, _I, _I, _P, _L, _P, _P,
+                      _P],
+    "bess_split_operand": [_I, Rows, _I, _I, _P, _I, _P, _P, _L, _P, _P, _L, _P, _P],
+    "bess_operand_scale": [_I, Rows, _I, _I, _P, _F, _P, _P, _P],
     "bess_row_sqnorm": [_I, Rows, _I, _I, _P, _P],
     "bess_l2_from_dot": [_P, RowMap, _L, _I, _I, _I, _P, _P, _P],
     "bess_l2_coef_workspace": [_I, _I],
@@ -98,7 +101,7 @@ SIGNATURES = {
     "bess_mask_diag": [_P, _I, _L, _I, _I, _I, _F, _P],
     "bess_loss_fwd_bwd": [_I, _F, _I, _F, _F, _L, _P, _P, _I, _I, _L, _P, _I, _P, _P, _P, _P],
     "bess_loss_fwd_bwd_operand": [_I, _F, _I, _F, _F, _L, _P, _P, _I, _I, _L, _P, _I, _P, _P, _I, _P, _P,
-                                  _L, _P],
+                                  _L, _P, _P],
     "bess_sum_f32": [_P, _I, _P, _P],
     "bess_rank_from_scores": [_P, _P, _I, _I, _L, _I, _I, _P, _P],
     "bess_sort_workspace": [_I],

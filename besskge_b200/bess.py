@@ -248,6 +248,9 @@ class _Pass:
 # (csrc/gemm_tc.cu).  The exact-fp32 CUDA-core tile kernel (csrc/pair.cu)
 # computes the same thing and is kept selectable for A/B parity tests only.
 USE_TENSOR_CORES = True
+# fp32 tables on the tensor cores: 3xFP16 (scaled fp16 hi / lo pairs, csrc/gemm_tc.cu) instead of
+# 3xTF32 for the DistMult / ComplEx training contractions.  BESS_F16X3=0 selects 3xTF32.
+USE_F16X3 = os.environ.get("BESS_F16X3", "1") != "0"
 # score_triple fwd / bwd and the relation-table reduce on a second stream, concurrent with the
 # negative-scoring / contraction kernels (A/B switch: BESS_OVERLAP=0)
 OVERLAP_SMALL_KERNELS = os.environ.get("BESS_OVERLAP", "1") != "0"
@@ -268,26 +271,48 @@ def _pad8(x: int) -> int:
     return (x + 7) // 8 * 8
 
 
+def _operand_format(table_dtype: torch.dtype, allow_f16x3: bool = True) -> int:
+    """GEMM operand format of a table dtype: halves as they are; fp32 as scaled fp16 (hi, lo)
+    pairs (3xFP16, twice the tensor-core rate of 3xTF32 at the same 22-bit products) or, when
+    that is switched off, tf32 pairs."""
+    if table_dtype != torch.float32:
+        return L.dtype_code(table_dtype)
+    return L.F16X3 if (USE_F16X3 and allow_f16x3) else L.F32
+
+
 class _TcOperand:
-    """Dense K-major operand arrays of one matrix for bess_dot_gemm: hi (+ lo
-    for 3xTF32) [rows, ld] and, when `transpose`, hiT (+ loT) [width, ldt]."""
+    """Dense K-major operand arrays of one matrix for bess_dot_gemm: hi (+ lo for the split
+    formats 3xTF32 / 3xFP16) [rows, ld] and, when `transpose`, hiT (+ loT) [width, ldt].
+    `fmt` is the operand format (L.F32 = tf32 pairs, L.F16X3 = scaled fp16 pairs with the
+    {s, 1 / s} pair in `scale`, L.F16 / L.BF16 = plain halves)."""
 
     def __init__(self, ws: "K.Workspace", tag: str, n_rows: int, width: int,
-                 dtype: torch.dtype, transpose: bool) -> None:
-        two = dtype == torch.float32
+                 dtype: torch.dtype, transpose: bool, fmt: Optional[int] = None) -> None:
+        self.fmt = L.dtype_code(dtype) if fmt is None else fmt
+        two = self.fmt in (L.F32, L.F16X3)
+        adt = torch.float16 if self.fmt == L.F16X3 else dtype
+        tag = f"{tag}_x3" if self.fmt == L.F16X3 else tag
         self.n_rows, self.width = n_rows, width
         self.ld, self.ldt = _pad8(width), _pad8(n_rows)
-        self.hi = ws.get(f"tc_{tag}_hi", (n_rows, self.ld), dtype)
-        self.lo = ws.get(f"tc_{tag}_lo", (n_rows, self.ld), dtype) if two else None
+        self.hi = ws.get(f"tc_{tag}_hi", (n_rows, self.ld), adt)
+        self.lo = ws.get(f"tc_{tag}_lo", (n_rows, self.ld), adt) if two else None
         self.hit = self.lot = None
         if transpose:
-            self.hit = ws.get(f"tc_{tag}_hiT", (width, self.ldt), dtype)
-            self.lot = ws.get(f"tc_{tag}_loT", (width, self.ldt), dtype) if two else None
+            self.hit = ws.get(f"tc_{tag}_hiT", (width, self.ldt), adt)
+            self.lot = ws.get(f"tc_{tag}_loT", (width, self.ldt), adt) if two else None
+        self.scale = self.state = None
+        if self.fmt == L.F16X3:
+            self.scale = ws.get(f"tc_{tag}_scale", (2,), torch.float32)
+            self.state = ws.get_zeroed(f"tc_{tag}_state", (2,), torch.int32)
 
     def fill(self, src_dt: int, src: L.Rows, out_dt: int, scale: Optional[torch.Tensor],
              device: torch.device) -> None:
-        K.split_operand(src_dt, src, self.n_rows, self.width, scale, out_dt, self.hi, self.lo,
-                        self.ld, self.hit, self.lot, self.ldt, device)
+        """`out_dt` is kept for call-site symmetry; the operand's own format decides."""
+        if self.fmt == L.F16X3:
+            K.operand_scale(src_dt, src, self.n_rows, self.width, scale, 1.0, self.scale,
+                            self.state)
+        K.split_operand(src_dt, src, self.n_rows, self.width, scale, self.fmt, self.hi, self.lo,
+                        self.ld, self.hit, self.lot, self.ldt, device, self.scale)
 
 
 def _as_i32(t: torch.Tensor) -> torch.Tensor:
@@ -803,10 +828,19 @@ class EmbeddingMovingBessKGE(BessKGE):
         # handshake go to the side stream and overlap that remaining compute.
         early_push = bool(px is not None and direct_ds and R == 1
                           and all(ps.fixed_from_head for ps in passes))
-        ds_hi = ds_lo = None
+        # operand format of the DOT contractions (fp32 tables: scaled fp16 pairs, 3xFP16); the
+        # norm-expanded L2 path keeps tf32 pairs
+        gdt = _operand_format(tdt) if use_tc else dt
+        ds_hi = ds_lo = ds_scale = ds_state = None
         if direct_ds:
-            ds_hi = ws.get("tc_dsd_hi", (S, ldN), tdt)
-            ds_lo = ws.get("tc_dsd_lo", (S, ldN), tdt) if tdt == torch.float32 else None
+            ds_dt = torch.float16 if gdt == L.F16X3 else tdt
+            sfx = "_x3" if gdt == L.F16X3 else ""
+            ds_hi = ws.get("tc_dsd_hi" + sfx, (S, ldN), ds_dt)
+            ds_lo = (ws.get("tc_dsd_lo" + sfx, (S, ldN), ds_dt)
+                     if gdt in (L.F32, L.F16X3) else None)
+            if gdt == L.F16X3:
+                ds_scale = ws.get("tc_dsd_scale", (2,), torch.float32)
+                ds_state = ws.get_zeroed("tc_dsd_state", (2,), torch.int32)
 
         flat = self.negative_sampler.flat_negative_format
         scheme = self.negative_sampler.corruption_scheme
@@ -855,7 +889,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     K.prologue_fwd(cfg, dt, ps0.mode, L.rows(H[0], rmap=ps0.fixed_map), rel_table,
                                    rel[row0], ps0.qmap, ps0.n_query, qv)
                     if ps0.shared and (use_tc or l2tc[0]):
-                        q0 = tc_q[0] = _TcOperand(ws, "q0", ps0.n_query, W, tdt, train)
+                        q0 = tc_q[0] = _TcOperand(ws, "q0", ps0.n_query, W, tdt, train, gdt)
                         q0.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
                     pre_done = True
                 px.wait(0)
@@ -892,13 +926,14 @@ class EmbeddingMovingBessKGE(BessKGE):
                         if pre_done:
                             q_op = tc_q[pi]
                         else:
-                            q_op = tc_q[pi] = _TcOperand(ws, f"q{pi}", ps.n_query, W, tdt, train)
+                            q_op = tc_q[pi] = _TcOperand(ws, f"q{pi}", ps.n_query, W, tdt, train,
+                                                         gdt)
                             q_op.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
-                        c_op = tc_c[pi] = _TcOperand(ws, f"c{pi}", ps.n_cand, W, tdt, train)
+                        c_op = tc_c[pi] = _TcOperand(ws, f"c{pi}", ps.n_cand, W, tdt, train, gdt)
                         c_op.fill(dt, cand, dt, None, dev)
-                        K.dot_gemm(dt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
+                        K.dot_gemm(gdt, q_op.hi, q_op.lo, q_op.ld, c_op.hi, c_op.lo, c_op.ld,
                                    ps.n_query, ps.n_cand, W, neg, ps.qmap, N, ps.col0, False,
-                                   gemm_ws)
+                                   gemm_ws, a_scale=q_op.scale, b_scale=c_op.scale)
                     elif l2tc[pi]:
                         # -||q - c||_2 from ||q||^2 + ||c||^2 - 2 q.c, q.c on the tensor cores
                         if pre_done:
@@ -943,10 +978,15 @@ class EmbeddingMovingBessKGE(BessKGE):
                         neg_l.copy_(neg)
                         neg_for_loss = neg_l
                     if direct_ds:
+                        if gdt == L.F16X3:
+                            # |dL/dscore| <= loss_scale * max(weight) for every loss here: the
+                            # power-of-two scale of the gradient operand comes from that bound
+                            K.operand_scale(L.F32, L.rows(w.view(1, -1)), 1, w.numel(), None,
+                                            abs(float(lp["loss_scale"])), ds_scale, ds_state)
                         K.loss_fwd_bwd_operand(lp["kind"], lp["margin"], lp["adversarial"],
                                                lp["adv_scale"], lp["loss_scale"], lp["n_entity"],
                                                pos, neg_for_loss, S, N, N, w, row_loss, d_pos[li],
-                                               dt, ds_hi, ds_lo, ldN)
+                                               gdt, ds_hi, ds_lo, ldN, ds_scale)
                     else:
                         K.loss_fwd_bwd(lp["kind"], lp["margin"], lp["adversarial"],
                                        lp["adv_scale"], lp["loss_scale"], lp["n_entity"], pos,
@@ -985,10 +1025,11 @@ class EmbeddingMovingBessKGE(BessKGE):
                     if early_push:
                         for pi, ps in enumerate(passes):
                             d_cand = self._cand_rows(ps, dHl, dTNl, local)
-                            K.dot_gemm(dt, ds_hi, ds_lo, ldN, tc_q[pi].hit, tc_q[pi].lot,
+                            K.dot_gemm(gdt, ds_hi, ds_lo, ldN, tc_q[pi].hit, tc_q[pi].lot,
                                        tc_q[pi].ldt, ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
                                        d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base,
-                                       a_mn_major=True, a_offset_elems=ps.col0)
+                                       a_mn_major=True, a_offset_elems=ps.col0,
+                                       a_scale=ds_scale, b_scale=tc_q[pi].scale)
                         join_triple_bwd()
                         main = torch.cuda.current_stream(dev)
                         side.wait_stream(main)
@@ -1012,25 +1053,28 @@ class EmbeddingMovingBessKGE(BessKGE):
                             if direct_ds:
                                 # dS operand arrays came straight from the loss kernel; dC reads
                                 # them MN-major (dS^T without a transposed copy)
-                                K.dot_gemm(dt, ds_hi, ds_lo, ldN, c_op.hit, c_op.lot, c_op.ldt,
+                                K.dot_gemm(gdt, ds_hi, ds_lo, ldN, c_op.hit, c_op.lot, c_op.ldt,
                                            ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
-                                           gemm_ws, a_offset_elems=ps.col0)
+                                           gemm_ws, a_offset_elems=ps.col0, a_scale=ds_scale,
+                                           b_scale=c_op.scale)
                                 if not early_push:
-                                    K.dot_gemm(dt, ds_hi, ds_lo, ldN, q_op.hit, q_op.lot, q_op.ldt,
+                                    K.dot_gemm(gdt, ds_hi, ds_lo, ldN, q_op.hit, q_op.lot, q_op.ldt,
                                                ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
                                                d_cand.pitch, 0, ps.aug, gemm_ws,
                                                out_ptr=d_cand.base, a_mn_major=True,
-                                               a_offset_elems=ps.col0)
+                                               a_offset_elems=ps.col0, a_scale=ds_scale,
+                                               b_scale=q_op.scale)
                             else:
-                                ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True)
+                                ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True, gdt)
                                 ds.fill(L.F32, L.rows(d_neg[li], rmap=ps.qmap, pitch=N,
                                                       offset_elems=ps.col0), dt, None, dev)
-                                K.dot_gemm(dt, ds.hi, ds.lo, ds.ld, c_op.hit, c_op.lot, c_op.ldt,
+                                K.dot_gemm(gdt, ds.hi, ds.lo, ds.ld, c_op.hit, c_op.lot, c_op.ldt,
                                            ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
-                                           gemm_ws)
-                                K.dot_gemm(dt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot,
+                                           gemm_ws, a_scale=ds.scale, b_scale=c_op.scale)
+                                K.dot_gemm(gdt, ds.hit, ds.lot, ds.ldt, q_op.hit, q_op.lot,
                                            q_op.ldt, ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
-                                           d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base)
+                                           d_cand.pitch, 0, ps.aug, gemm_ws, out_ptr=d_cand.base,
+                                           a_scale=ds.scale, b_scale=q_op.scale)
                             join_triple_bwd()
                             K.prologue_bwd(cfg, dt, ps.mode, fixed, rel_table, rel[row], ps.qmap,
                                            ps.n_query, d_qv, d_fixed, dRq[li], True, True)

@@ -16,11 +16,21 @@
 //     kernel issues hi*hi + hi*lo + lo*hi per k-step, which restores fp32-grade
 //     products (dropped term ~2^-22) so the 1e-5 fp32 parity bar holds.
 //   * bf16 / fp16 tables -> one kind::f16 MMA per k-step, fp32 accumulate.
+//   * fp32 tables, "3xFP16" (BESS_F16X3, the default for the training contractions): the same
+//     hi / lo split carried by fp16 pairs — fp16 has the same 11-bit significand as tf32, so
+//     hi + lo again covers 22 bits — of the operand multiplied by a power-of-two scale that
+//     puts its largest element near 2^14 (fp16's exponent range is the only thing it lacks;
+//     bess_operand_scale picks the scale from the operand's max |x| on the device, the
+//     epilogue multiplies the accumulator by the two inverse scales, both exact).  kind::f16
+//     consumes 32 bytes of K per instruction like kind::tf32 but they are 16 elements, not 8:
+//     twice the flops per issue, half the operand bytes — the 3-pass product at 3 instead of 6
+//     bf16-equivalent passes.
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      TMA producer (one lane)
 //   warp 1      TMEM allocator + MMA issuer (one lane)
 //   warps 2..5  epilogue (TMEM lane quarter = warp_idx % 4)
+#include <math_constants.h>
 #include <cuda.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time
 #include <cstdio>
 #include <cstdlib>
@@ -37,12 +47,13 @@ constexpr int kThreads = 192;
 constexpr int kAccCols = kBlockN;        // fp32 accumulator columns per buffer
 constexpr int kTmemCols = 2 * kAccCols;  // double-buffered
 
-enum GemmMode { GEMM_TF32X3 = 0, GEMM_F16 = 1, GEMM_BF16 = 2 };
+enum GemmMode { GEMM_TF32X3 = 0, GEMM_F16 = 1, GEMM_BF16 = 2, GEMM_F16X3 = 3 };
 
 template <int MODE>
 struct ModeTraits {
-  static constexpr int kOperandTiles = MODE == GEMM_TF32X3 ? 2 : 1;  // hi (+ lo)
-  static constexpr int kRowBytes = MODE == GEMM_TF32X3 ? 64 : 128;   // bytes of K per smem row
+  static constexpr bool kSplit = MODE == GEMM_TF32X3 || MODE == GEMM_F16X3;  // hi + lo operands
+  static constexpr int kOperandTiles = kSplit ? 2 : 1;                // hi (+ lo)
+  static constexpr int kRowBytes = kSplit ? 64 : 128;                 // bytes of K per smem row
   static constexpr int kElemBytes = MODE == GEMM_TF32X3 ? 4 : 2;
   static constexpr int kBlockK = kRowBytes / kElemBytes;              // elements of K per stage
   static constexpr int kKSteps = kRowBytes / 32;                      // one MMA consumes 32 B of K
@@ -50,7 +61,7 @@ struct ModeTraits {
   static constexpr int kBTile = kBlockN * kRowBytes;
   static constexpr int kStageBytes = kOperandTiles * (kATile + kBTile);
   // UMMA smem-descriptor layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-  static constexpr uint64_t kLayoutType = MODE == GEMM_TF32X3 ? 4 : 2;
+  static constexpr uint64_t kLayoutType = kSplit ? 4 : 2;
   // instruction-descriptor operand format: 0 = F16, 1 = BF16, 2 = TF32
   static constexpr uint32_t kFmt = MODE == GEMM_TF32X3 ? 2u : (MODE == GEMM_BF16 ? 1u : 0u);
   // MN-major A (A stored [K, M], M contiguous): SWIZZLE_128B atoms of 8 K-rows x 128 B of M
@@ -308,6 +319,8 @@ struct GemmParams {
   float* partial;   // ... or [n_split, M, ld_partial] partial sums
   int64_t ld_partial;
   int tma_store;    // epilogue stages 32 x 32 chunks in smem and TMA-stores them (map_out)
+  const float* a_scale;  // 3xFP16: {scale, 1 / scale} of each operand (device), else null
+  const float* b_scale;
 };
 
 // CS = cluster size along M: the CS CTAs of a cluster work on CS consecutive m-blocks of the
@@ -350,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tma_prefetch_desc(&map_a_hi);
     tma_prefetch_desc(&map_b_hi);
     if (p.tma_store) tma_prefetch_desc(&map_out);
-    if (MODE == GEMM_TF32X3) {
+    if (T::kSplit) {
       tma_prefetch_desc(&map_a_lo);
       tma_prefetch_desc(&map_b_lo);
     }
@@ -396,16 +409,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
               for (int i = 0; i < T::kMnAtoms; ++i) {
                 tma_load_2d_2sm(sa + i * T::kMnSlab, &map_a_hi, lbar, m0 + i * T::kMnAtom, k);
-                if (MODE == GEMM_TF32X3)
+                if (T::kSplit)
                   tma_load_2d_2sm(sa + T::kATile + i * T::kMnSlab, &map_a_lo, lbar, m0 + i * T::kMnAtom, k);
               }
             } else {
               tma_load_2d_2sm(sa, &map_a_hi, lbar, k, m0);
-              if (MODE == GEMM_TF32X3) tma_load_2d_2sm(sa + T::kATile, &map_a_lo, lbar, k, m0);
+              if (T::kSplit) tma_load_2d_2sm(sa + T::kATile, &map_a_lo, lbar, k, m0);
             }
             const int nb0 = n0 + cta_rank * (kBlockN / 2);
             tma_load_2d_2sm(sb, &map_b_hi, lbar, k, nb0);
-            if (MODE == GEMM_TF32X3) tma_load_2d_2sm(sb + kBTileCta, &map_b_lo, lbar, k, nb0);
+            if (T::kSplit) tma_load_2d_2sm(sb + kBTileCta, &map_b_lo, lbar, k, nb0);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
             continue;
           }
@@ -414,24 +427,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int i = 0; i < T::kMnAtoms; ++i) {
               tma_load_2d(sa + i * T::kMnSlab, &map_a_hi, full_bar(stage), m0 + i * T::kMnAtom, k);
-              if (MODE == GEMM_TF32X3)
+              if (T::kSplit)
                 tma_load_2d(sa + T::kATile + i * T::kMnSlab, &map_a_lo, full_bar(stage),
                             m0 + i * T::kMnAtom, k);
             }
           } else {
             tma_load_2d(sa, &map_a_hi, full_bar(stage), k, m0);
-            if (MODE == GEMM_TF32X3) tma_load_2d(sa + T::kATile, &map_a_lo, full_bar(stage), k, m0);
+            if (T::kSplit) tma_load_2d(sa + T::kATile, &map_a_lo, full_bar(stage), k, m0);
           }
           if (CS > 1) {
             constexpr int kSliceRows = kBlockN / CS;
             const uint32_t off = (uint32_t)(cta_rank * kSliceRows * T::kRowBytes);
             tma_load_2d_mc(sb + off, &map_b_hi, full_bar(stage), k, n0 + cta_rank * kSliceRows, kMcMask);
-            if (MODE == GEMM_TF32X3)
+            if (T::kSplit)
               tma_load_2d_mc(sb + T::kBTile + off, &map_b_lo, full_bar(stage), k,
                              n0 + cta_rank * kSliceRows, kMcMask);
           } else {
             tma_load_2d(sb, &map_b_hi, full_bar(stage), k, n0);
-            if (MODE == GEMM_TF32X3) tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
+            if (T::kSplit) tma_load_2d(sb + T::kBTile, &map_b_lo, full_bar(stage), k, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -466,7 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int ks = 0; ks < T::kKSteps; ++ks) {
             const uint64_t a_hi = A_MN ? smem_desc_mn<MODE>(sa + ks * T::kMnKStep) : smem_desc<MODE>(sa + ks * 32);
             const uint64_t b_hi = smem_desc<MODE>(sb + ks * 32);
-            if (MODE == GEMM_TF32X3) {
+            if (T::kSplit) {
               const uint64_t a_lo = A_MN ? smem_desc_mn<MODE>(sa + T::kATile + ks * T::kMnKStep)
                                          : smem_desc<MODE>(sa + T::kATile + ks * 32);
               const uint64_t b_lo = smem_desc<MODE>(sb + kBTileCta + ks * 32);
@@ -521,6 +534,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         accumulate = p.accumulate != 0;
       }
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+      // scaled operands (3xFP16): undo the two power-of-two operand scales, exactly
+      const float oscale = p.a_scale != nullptr ? __ldg(p.a_scale + 1) * __ldg(p.b_scale + 1) : 1.f;
+      const bool scaled = p.a_scale != nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kAccCols);
       if (p.tma_store) {
         // TMEM -> registers -> swizzled smem chunk -> one coalesced TMA store per 32 x 32 chunk
@@ -531,6 +547,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           tmem_ld_wait();
+          if (scaled) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * oscale);
+          }
           const uint32_t chunk = my_epi + (uint32_t)((c >> 5) & 1) * kEpiChunkBytes;
           if (lane == 0) tma_store_wait_read<1>();  // the store that last used this chunk has read it
           __syncwarp();
@@ -555,6 +575,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
+        if (scaled) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * oscale);
+        }
         if (row < p.M) {
           const int n_left = p.N - (n0 + c);
           if (n_left >= 32 && vec_ok && !accumulate) {
@@ -633,7 +657,12 @@ struct OutConv<float> {
 };
 template <>
 struct OutConv<__half> {
-  static BESS_D void put(float x, __half* hi, __half*, int64_t i) { hi[i] = __float2half_rn(x); }
+  // lo != null: the fp16 hi / lo pair of 3xFP16 (x already multiplied by the operand scale)
+  static BESS_D void put(float x, __half* hi, __half* lo, int64_t i) {
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    if (lo != nullptr) lo[i] = __float2half_rn(x - __half2float(h));
+  }
 };
 template <>
 struct OutConv<__nv_bfloat16> {
@@ -644,10 +673,53 @@ struct OutConv<__nv_bfloat16> {
 
 // 32 x 32 tiles through shared memory so that both the straight and the
 // transposed stores are coalesced.
+// Power-of-two operand scale of 3xFP16 from the operand's max |x| * factor: the largest
+// scaled element lands in [2^13, 2^14] (fp16 overflows at 2^16), so that an element needs to
+// be ~2^27 times smaller than the largest before its hi part turns subnormal.
+BESS_D void scale_from_max(float mx, float* scale /* {s, 1 / s} */) {
+  int e = 0;
+  if (mx > 0.f && mx < CUDART_INF_F) frexpf(mx, &e);  // mx = m * 2^e, m in [0.5, 1)
+  int se = 14 - e;
+  se = se > 100 ? 100 : (se < -100 ? -100 : se);
+  scale[0] = ldexpf(1.f, se);
+  scale[1] = ldexpf(1.f, -se);
+}
+
+// state = {raw max bits, ticket} (zero between calls: the last block resets both)
+template <typename ST>
+__global__ void __launch_bounds__(256) operand_absmax_kernel(bess_rows_t src, int n_rows, int width,
+                                                             const float* row_scale, float factor,
+                                                             float* scale, unsigned* state) {
+  const ST* base = reinterpret_cast<const ST*>(src.base);
+  float mx = 0.f;
+  const int64_t total = (int64_t)n_rows * width;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / width), c = (int)(t - (int64_t)r * width);
+    float x = fabsf(ldf(base + src_row(src, r) * src.pitch + c));
+    if (row_scale != nullptr) x *= fabsf(row_scale[r]);
+    mx = fmaxf(mx, x);  // NaN operands are ignored here (and poison the product, as they should)
+  }
+  __shared__ float red[8];
+  mx = block_max<256>(mx, red);
+  if (threadIdx.x == 0) {
+    atomicMax(&state[0], __float_as_uint(mx));  // non-negative floats order like their bits
+    __threadfence();
+    if (atomicAdd(&state[1], 1u) == gridDim.x - 1) {
+      __threadfence();
+      scale_from_max(__uint_as_float(atomicAdd(&state[0], 0u)) * factor, scale);
+      state[0] = 0u;
+      state[1] = 0u;
+    }
+  }
+}
+
 template <typename ST, typename OT>
 __global__ void split_operand_kernel(bess_rows_t src, int n_rows, int width, const float* row_scale,
-                                     OT* hi, OT* lo, int64_t ld, OT* hiT, OT* loT, int64_t ldT) {
+                                     OT* hi, OT* lo, int64_t ld, OT* hiT, OT* loT, int64_t ldT,
+                                     const float* op_scale) {
   __shared__ float tile[32][33];
+  const float os = op_scale != nullptr ? __ldg(op_scale) : 1.f;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const ST* base = reinterpret_cast<const ST*>(src.base);
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -656,6 +728,7 @@ __global__ void split_operand_kernel(bess_rows_t src, int n_rows, int width, con
     if (r < n_rows && c < width) {
       x = ldf(base + src_row(src, r) * src.pitch + c);
       if (row_scale != nullptr) x *= row_scale[r];
+      x *= os;
       if (hi != nullptr) OutConv<OT>::put(x, hi, lo, (int64_t)r * ld + c);
     }
     tile[i][threadIdx.x] = x;
@@ -784,7 +857,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int K, int64_t
   cuuint64_t strides[1] = {(cuuint64_t)ld * T::kElemBytes};
   cuuint32_t box[2] = {(cuuint32_t)T::kBlockK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = MODE == GEMM_TF32X3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw = T::kSplit ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -838,13 +911,13 @@ template <int MODE, bool A_MN, int CS, bool TWO = false>
 static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
                        int64_t ldb, int M, int N, int K, float* out, bess_rowmap_t out_map, int64_t ld_out,
                        int col0, int accumulate, float* workspace, int64_t workspace_bytes,
-                       cudaStream_t stream) {
+                       const float* a_scale, const float* b_scale, cudaStream_t stream) {
   using T = ModeTraits<MODE>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int e = A_MN ? make_map_mn<MODE>(&ma_hi, a_hi, M, K, lda) : make_map<MODE>(&ma_hi, a_hi, M, K, lda, kBlockM))
     return e;
   if (int e = make_map<MODE>(&mb_hi, b_hi, N, K, ldb, kBlockN / CS)) return e;
-  if (MODE == GEMM_TF32X3) {
+  if (T::kSplit) {
     if (int e = A_MN ? make_map_mn<MODE>(&ma_lo, a_lo, M, K, lda) : make_map<MODE>(&ma_lo, a_lo, M, K, lda, kBlockM))
       return e;
     if (int e = make_map<MODE>(&mb_lo, b_lo, N, K, ldb, kBlockN / CS)) return e;
@@ -863,6 +936,8 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, const vo
   }
   p.out = out; p.out_map = out_map; p.ld_out = ld_out; p.col0 = col0; p.accumulate = accumulate;
   p.partial = workspace;
+  p.a_scale = MODE == GEMM_F16X3 ? a_scale : nullptr;
+  p.b_scale = MODE == GEMM_F16X3 ? b_scale : nullptr;
   // coalesced TMA-store epilogue when the output is a plain (row-identity) 16-byte aligned matrix
   CUtensorMap m_out = ma_hi;
   p.tma_store = 0;
@@ -933,18 +1008,23 @@ extern "C" int64_t bess_dot_gemm_workspace(int M, int N, int K) {
   int kps;
   const int s0 = choose_split(M, N, K, ModeTraits<GEMM_TF32X3>::kBlockK, &kps);
   const int s1 = choose_split(M, N, K, ModeTraits<GEMM_BF16>::kBlockK, &kps);
-  const int s = s0 > s1 ? s0 : s1;
+  const int s2 = choose_split(M, N, K, ModeTraits<GEMM_F16X3>::kBlockK, &kps);
+  const int s = (s0 > s1 ? s0 : s1) > s2 ? (s0 > s1 ? s0 : s1) : s2;
   return s > 1 ? (int64_t)s * M * ((N + 3) & ~3) * 4 : 0;
 }
 
 extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, int a_mn_major,
                              const void* b_hi, const void* b_lo, int64_t ldb, int M, int N, int K,
                              float* out, bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate,
-                             void* workspace, int64_t workspace_bytes, void* stream) {
+                             void* workspace, int64_t workspace_bytes, const float* a_scale,
+                             const float* b_scale, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return BESS_OK;
   const int es = dtype == BESS_F32 ? 4 : 2;
+  const bool split = dtype == BESS_F32 || dtype == BESS_F16X3;
   BESS_CHECK_ARG(a_hi && b_hi && out, "bess_dot_gemm: null operand");
-  BESS_CHECK_ARG(dtype != BESS_F32 || (a_lo && b_lo), "bess_dot_gemm: fp32 needs the lo operands");
+  BESS_CHECK_ARG(!split || (a_lo && b_lo), "bess_dot_gemm: split modes need the lo operands");
+  BESS_CHECK_ARG(dtype != BESS_F16X3 || (a_scale && b_scale),
+                 "bess_dot_gemm: BESS_F16X3 needs the operand scales");
   BESS_CHECK_ARG((lda * es) % 16 == 0 && (ldb * es) % 16 == 0,
                  "bess_dot_gemm: operand leading dimensions must be multiples of 16 bytes");
   BESS_CHECK_ARG(((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) % 16 == 0,
@@ -955,14 +1035,14 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
   int cs = m_blocks_ >= 4 ? 2 : 1;
   // cta_group::2 pair MMA (256 x 256 per CTA pair, half of B per CTA): measured 5-8 % faster than
   // cluster multicast for the L2-bound 3xTF32 contractions, slower for the epilogue-bound half ones
-  bool two = cs == 2 && dtype == BESS_F32;
+  bool two = cs == 2 && split;
   if (const char* env = getenv("BESSKGE_GEMM_CLUSTER")) {
     const int v = atoi(env);
     if (v == 1 || v == 2 || v == 4) { cs = v; two = false; }
     if (v == 22) { cs = 2; two = true; }
   }
 #define GEMM_ARGS a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, out, out_map, ld_out, col0, accumulate, \
-                  (float*)workspace, workspace_bytes, st
+                  (float*)workspace, workspace_bytes, a_scale, b_scale, st
 #define GEMM_GO(MODE)                                                                    \
   if (cs == 4) return a_mn_major ? launch_gemm<MODE, true, 4>(GEMM_ARGS) : launch_gemm<MODE, false, 4>(GEMM_ARGS); \
   if (cs == 2 && two) return a_mn_major ? launch_gemm<MODE, true, 2, true>(GEMM_ARGS) : launch_gemm<MODE, false, 2, true>(GEMM_ARGS); \
@@ -972,6 +1052,7 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
     case BESS_F32: GEMM_GO(GEMM_TF32X3);
     case BESS_F16: GEMM_GO(GEMM_F16);
     case BESS_BF16: GEMM_GO(GEMM_BF16);
+    case BESS_F16X3: GEMM_GO(GEMM_F16X3);
     default:
       bess_set_error("bess_dot_gemm: unknown dtype %d", dtype);
       return BESS_ERR_INVALID_ARG;
@@ -980,18 +1061,45 @@ extern "C" int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int6
 #undef GEMM_ARGS
 }
 
+extern "C" int bess_operand_scale(int src_dtype, bess_rows_t src, int n_rows, int width,
+                                  const float* row_scale, float factor, float* scale, void* state,
+                                  void* stream) {
+  BESS_CHECK_ARG(scale != nullptr && state != nullptr, "bess_operand_scale: scale / state required");
+  if (n_rows <= 0 || width <= 0) return BESS_OK;
+  const int64_t total = (int64_t)n_rows * width;
+  int blocks = (int)((total + 256 * 8 - 1) / (256 * 8));
+  blocks = blocks < 1 ? 1 : (blocks > 2 * kNumSM ? 2 * kNumSM : blocks);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (src_dtype) {
+    case BESS_F32: operand_absmax_kernel<float><<<blocks, 256, 0, st>>>(src, n_rows, width, row_scale, factor, scale, (unsigned*)state); break;
+    case BESS_F16: operand_absmax_kernel<__half><<<blocks, 256, 0, st>>>(src, n_rows, width, row_scale, factor, scale, (unsigned*)state); break;
+    case BESS_BF16: operand_absmax_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, n_rows, width, row_scale, factor, scale, (unsigned*)state); break;
+    default: bess_set_error("bess_operand_scale: unknown src dtype %d", src_dtype); return BESS_ERR_INVALID_ARG;
+  }
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
 extern "C" int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,
                                   const float* row_scale, int out_dtype, void* hi, void* lo, int64_t ld,
-                                  void* hiT, void* loT, int64_t ldT, void* stream) {
+                                  void* hiT, void* loT, int64_t ldT, const float* op_scale,
+                                  void* stream) {
   if (n_rows <= 0 || width <= 0) return BESS_OK;
   BESS_CHECK_ARG(hi != nullptr || hiT != nullptr, "bess_split_operand: no output");
-  BESS_CHECK_ARG(out_dtype != BESS_F32 || ((hi == nullptr || lo != nullptr) && (hiT == nullptr || loT != nullptr)),
-                 "bess_split_operand: fp32 output needs the lo arrays");
+  const bool pair = out_dtype == BESS_F32 || out_dtype == BESS_F16X3;
+  BESS_CHECK_ARG(!pair || ((hi == nullptr || lo != nullptr) && (hiT == nullptr || loT != nullptr)),
+                 "bess_split_operand: split outputs need the lo arrays");
+  BESS_CHECK_ARG(out_dtype != BESS_F16X3 || op_scale != nullptr,
+                 "bess_split_operand: BESS_F16X3 needs the operand scale (bess_operand_scale)");
+  if (out_dtype != BESS_F16X3) {
+    op_scale = nullptr;
+    if (!pair) { lo = nullptr; loT = nullptr; }
+  }
   const dim3 grid(ceil_div(width, 32), ceil_div(n_rows, 32)), block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define SPLIT_LAUNCH(ST, OT)                                                                          \
   split_operand_kernel<ST, OT><<<grid, block, 0, st>>>(src, n_rows, width, row_scale, (OT*)hi, (OT*)lo, \
-                                                       ld, (OT*)hiT, (OT*)loT, ldT)
+                                                       ld, (OT*)hiT, (OT*)loT, ldT, op_scale)
 #define SPLIT_SRC(OT)                                                           \
   switch (src_dtype) {                                                          \
     case BESS_F32: SPLIT_LAUNCH(float, OT); break;                              \
@@ -1003,6 +1111,7 @@ extern "C" int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, in
   switch (out_dtype) {
     case BESS_F32: SPLIT_SRC(float); break;
     case BESS_F16: SPLIT_SRC(__half); break;
+    case BESS_F16X3: SPLIT_SRC(__half); break;
     case BESS_BF16: SPLIT_SRC(__nv_bfloat16); break;
     default: bess_set_error("bess_split_operand: unknown out dtype %d", out_dtype); return BESS_ERR_INVALID_ARG;
   }

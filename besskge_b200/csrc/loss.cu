@@ -49,7 +49,7 @@ __global__ void mask_diag_kernel(float* score, int n_row, int64_t ld, int step, 
 // separate split pass over the [S, N] gradient.
 // ---------------------------------------------------------------------------
 constexpr int L_CACHE = 16;  // scores per thread kept in registers
-enum GradOut { GRAD_F32 = 0, GRAD_TF32 = 1, GRAD_BF16 = 2, GRAD_F16 = 3 };
+enum GradOut { GRAD_F32 = 0, GRAD_TF32 = 1, GRAD_BF16 = 2, GRAD_F16 = 3, GRAD_F16X3 = 4 };
 
 BESS_D float rna_tf32_(float x) {
   uint32_t r;
@@ -58,8 +58,33 @@ BESS_D float rna_tf32_(float x) {
 }
 
 template <int OUT>
-BESS_D void store_grad4(void* g_hi, void* g_lo, int64_t at, const float (&g)[4], int n_valid, bool vec) {
-  if (OUT == GRAD_F32 || OUT == GRAD_TF32) {
+BESS_D void store_grad4(void* g_hi, void* g_lo, int64_t at, const float (&g)[4], int n_valid, bool vec,
+                        float gscale) {
+  if (OUT == GRAD_F16X3) {
+    // scaled fp16 pair: hi = fp16(g * s), lo = fp16(g * s - hi)  (3xFP16 operand, gemm_tc.cu)
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x = g[j] * gscale;
+      h[j] = __float2half_rn(x);
+      l[j] = __float2half_rn(x - __half2float(h[j]));
+    }
+    __half* ph = reinterpret_cast<__half*>(g_hi) + at;
+    __half* pl = reinterpret_cast<__half*>(g_lo) + at;
+    if (vec && n_valid == 4) {
+      uint2 uh, ul;
+      __half2 a = __halves2half2(h[0], h[1]), b = __halves2half2(h[2], h[3]);
+      uh.x = *reinterpret_cast<uint32_t*>(&a); uh.y = *reinterpret_cast<uint32_t*>(&b);
+      a = __halves2half2(l[0], l[1]); b = __halves2half2(l[2], l[3]);
+      ul.x = *reinterpret_cast<uint32_t*>(&a); ul.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(ph) = uh;
+      *reinterpret_cast<uint2*>(pl) = ul;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < n_valid) { ph[j] = h[j]; pl[j] = l[j]; }
+    }
+  } else if (OUT == GRAD_F32 || OUT == GRAD_TF32) {
     float h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -123,6 +148,7 @@ struct LossArgs {
   void* g_hi;
   void* g_lo;
   int64_t ld_g;
+  const float* g_scale;  // GRAD_F16X3: {scale, 1 / scale} of the gradient operand (device)
 };
 
 // registers <- one row of scores: slot (i, j) <-> column (i * TPB + tid) * 4 + j
@@ -160,9 +186,11 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
   const float w = weight_n == 1 ? weight[0] : weight[r];
   const float p = pos[r];
   const bool vec_in = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(neg) & 15) == 0;
-  constexpr int kGradBytes = (OUT == GRAD_BF16 || OUT == GRAD_F16) ? 2 : 4;
+  constexpr int kGradBytes = (OUT == GRAD_BF16 || OUT == GRAD_F16 || OUT == GRAD_F16X3) ? 2 : 4;
   const bool vec_out = (ld_g & 3) == 0 && (reinterpret_cast<uintptr_t>(g_hi) & 15) == 0 &&
-                       (OUT != GRAD_TF32 || (reinterpret_cast<uintptr_t>(g_lo) & 15) == 0);
+                       ((OUT != GRAD_TF32 && OUT != GRAD_F16X3) ||
+                        (reinterpret_cast<uintptr_t>(g_lo) & 15) == 0);
+  const float gscale = OUT == GRAD_F16X3 ? __ldg(a.g_scale) : 1.f;
   (void)kGradBytes;
 
   (void)vec_in;
@@ -207,12 +235,12 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
         float g[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) g[j] = loss_scale * w * expf(v[4 * i + j] - lse);
-        store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out);
+        store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out, gscale);
       }
     }
     for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) {
       float g[4] = {loss_scale * w * expf(nrow[c] - lse), 0.f, 0.f, 0.f};
-      store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false);
+      store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false, gscale);
     }
     if (threadIdx.x == 0) {
       row_loss[r] = loss_scale * w * (lse - p);
@@ -276,12 +304,12 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
       float g[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) g[j] = c + j < n_neg ? one(v[4 * i + j]) : 0.f;
-      store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out);
+      store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out, gscale);
     }
   }
   for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) {
     float g[4] = {one(nrow[c]), 0.f, 0.f, 0.f};
-    store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false);
+    store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false, gscale);
   }
   part = block_sum<L_THREADS>(part, red);
   if (KIND == BESS_LOSS_MARGIN_RANKING) dp = block_sum<L_THREADS>(dp, red);
@@ -647,8 +675,9 @@ template <int OUT>
 static int launch_loss(int kind, float margin, int adversarial, float adv_scale, float loss_scale,
                        int64_t n_entity, const float* pos, float* neg, int n, int n_neg, int64_t ld,
                        const float* weight, int weight_n, float* row_loss, float* d_pos, void* g_hi,
-                       void* g_lo, int64_t ld_g, cudaStream_t st) {
+                       void* g_lo, int64_t ld_g, cudaStream_t st, const float* g_scale = nullptr) {
   LossArgs a;
+  a.g_scale = g_scale;
   a.margin = margin; a.adversarial = adversarial; a.adv_scale = adv_scale; a.loss_scale = loss_scale;
   a.ce_shift = 0.f; a.pos = pos; a.neg = neg; a.n = n; a.n_neg = n_neg; a.ld = ld; a.weight = weight;
   a.weight_n = weight_n; a.row_loss = row_loss; a.d_pos = d_pos; a.g_hi = g_hi; a.g_lo = g_lo;
@@ -686,14 +715,21 @@ extern "C" int bess_loss_fwd_bwd_operand(int kind, float margin, int adversarial
                                          float* neg, int n, int n_neg, int64_t ld,
                                          const float* weight, int weight_n, float* row_loss,
                                          float* d_pos, int grad_dtype, void* d_neg_hi, void* d_neg_lo,
-                                         int64_t ld_grad, void* stream) {
+                                         int64_t ld_grad, const float* grad_scale, void* stream) {
   if (n == 0) return BESS_OK;
   BESS_CHECK_ARG(n_neg > 0, "loss needs at least one negative");
   BESS_CHECK_ARG(weight_n == 1 || weight_n == n, "triple_weight has %d entries, need 1 or %d", weight_n, n);
-  BESS_CHECK_ARG(d_neg_hi != nullptr && (grad_dtype != BESS_F32 || d_neg_lo != nullptr),
+  BESS_CHECK_ARG(d_neg_hi != nullptr &&
+                     ((grad_dtype != BESS_F32 && grad_dtype != BESS_F16X3) || d_neg_lo != nullptr),
                  "bess_loss_fwd_bwd_operand: missing gradient output");
+  BESS_CHECK_ARG(grad_dtype != BESS_F16X3 || grad_scale != nullptr,
+                 "bess_loss_fwd_bwd_operand: BESS_F16X3 needs the gradient operand's scale");
   cudaStream_t st = (cudaStream_t)stream;
   switch (grad_dtype) {
+    case BESS_F16X3:
+      return launch_loss<GRAD_F16X3>(kind, margin, adversarial, adv_scale, loss_scale, n_entity, pos,
+                                     neg, n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg_hi,
+                                     d_neg_lo, ld_grad, st, grad_scale);
     case BESS_F32:
       return launch_loss<GRAD_TF32>(kind, margin, adversarial, adv_scale, loss_scale, n_entity, pos, neg,
                                     n, n_neg, ld, weight, weight_n, row_loss, d_pos, d_neg_hi, d_neg_lo,

@@ -45,6 +45,16 @@ class Workspace:
             self._buf[name] = cur
         return cur[:n].view(*shape)
 
+    def get_zeroed(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        """Like `get`, but the buffer is zero-filled when it is first created (kernel-owned
+        state words that the kernels themselves leave zero afterwards)."""
+        fresh = name not in self._buf
+        t = self.get(name, shape, dtype)
+        if fresh or self._buf[name].data_ptr() != getattr(self, "_zeroed", {}).get(name):
+            self._buf[name].zero_()
+            self.__dict__.setdefault("_zeroed", {})[name] = self._buf[name].data_ptr()
+        return t
+
     def release_retired(self) -> None:
         """Free replaced buffers; call only when no captured graph refers to them."""
         self._retired.clear()
@@ -156,10 +166,19 @@ def split_operand(src_dt: int, src: Rows, n_rows: int, width: int,
                   row_scale: Optional[torch.Tensor], out_dt: int,
                   hi: Optional[torch.Tensor], lo: Optional[torch.Tensor], ld: int,
                   hi_t: Optional[torch.Tensor], lo_t: Optional[torch.Tensor], ld_t: int,
-                  device: torch.device) -> None:
+                  device: torch.device, op_scale: Optional[torch.Tensor] = None) -> None:
     """rows -> dense K-major GEMM operand(s); see bess_split_operand."""
     call("bess_split_operand", src_dt, src, n_rows, width, ptr(row_scale), out_dt, ptr(hi), ptr(lo),
-         ld, ptr(hi_t), ptr(lo_t), ld_t, torch.cuda.current_stream(device).cuda_stream)
+         ld, ptr(hi_t), ptr(lo_t), ld_t, ptr(op_scale),
+         torch.cuda.current_stream(device).cuda_stream)
+
+
+def operand_scale(src_dt: int, src: Rows, n_rows: int, width: int,
+                  row_scale: Optional[torch.Tensor], factor: float, scale: torch.Tensor,
+                  state: torch.Tensor) -> None:
+    """{s, 1 / s} of a 3xFP16 operand from factor * max |x|; see bess_operand_scale."""
+    call("bess_operand_scale", src_dt, src, n_rows, width, ptr(row_scale), float(factor),
+         scale.data_ptr(), state.data_ptr(), _st(scale))
 
 
 # ------------------------------------------ norm-expanded L2 (tensor cores) --
@@ -205,7 +224,8 @@ def dot_gemm(dt: int, a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], lda: int
              b_hi: torch.Tensor, b_lo: Optional[torch.Tensor], ldb: int, m: int, n: int, k: int,
              out: torch.Tensor, out_map: RowMap, ld_out: int, col0: int, accumulate: bool,
              workspace: Optional[torch.Tensor], out_ptr: Optional[int] = None,
-             a_mn_major: bool = False, a_offset_elems: int = 0) -> None:
+             a_mn_major: bool = False, a_offset_elems: int = 0,
+             a_scale: Optional[torch.Tensor] = None, b_scale: Optional[torch.Tensor] = None) -> None:
     """out[out_map(i) * ld_out + col0 + j] (+)= sum_k A[i, k] * B[j, k] on the tcgen05 path.
     a_mn_major: A is stored transposed [K, M] (M contiguous, leading dimension lda)."""
     ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
@@ -213,7 +233,7 @@ def dot_gemm(dt: int, a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], lda: int
     call("bess_dot_gemm", dt, a_hi.data_ptr() + off, None if a_lo is None else a_lo.data_ptr() + off,
          lda, int(a_mn_major), b_hi.data_ptr(), ptr(b_lo), ldb, m, n, k,
          out.data_ptr() if out_ptr is None else out_ptr, out_map, ld_out, col0, int(accumulate),
-         ptr(workspace), ws_bytes, _st(a_hi))
+         ptr(workspace), ws_bytes, ptr(a_scale), ptr(b_scale), _st(a_hi))
 
 
 def pertriple_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
@@ -260,12 +280,13 @@ def loss_fwd_bwd_operand(kind: int, margin: float, adversarial: bool, adv_scale:
                          loss_scale: float, n_entity: int, pos: torch.Tensor, neg: torch.Tensor,
                          n: int, n_neg: int, ld: int, weight: torch.Tensor, row_loss: torch.Tensor,
                          d_pos: torch.Tensor, grad_dt: int, d_neg_hi: torch.Tensor,
-                         d_neg_lo: Optional[torch.Tensor], ld_grad: int) -> None:
+                         d_neg_lo: Optional[torch.Tensor], ld_grad: int,
+                         grad_scale: Optional[torch.Tensor] = None) -> None:
     """loss + dL/dscore with the [n, n_neg] gradient written as GEMM operand arrays."""
     call("bess_loss_fwd_bwd_operand", kind, float(margin), int(adversarial), float(adv_scale),
          float(loss_scale), int(n_entity), pos.data_ptr(), neg.data_ptr(), n, n_neg, ld,
          weight.data_ptr(), weight.numel(), row_loss.data_ptr(), d_pos.data_ptr(), grad_dt,
-         d_neg_hi.data_ptr(), ptr(d_neg_lo), ld_grad, _st(pos))
+         d_neg_hi.data_ptr(), ptr(d_neg_lo), ld_grad, ptr(grad_scale), _st(pos))
 
 
 def sum_f32(x: torch.Tensor, n: int, out: torch.Tensor) -> None:

@@ -29,7 +29,9 @@ typedef enum {
   BESS_ERR_UNSUPPORTED = -3
 } bess_status;
 
-typedef enum { BESS_F32 = 0, BESS_F16 = 1, BESS_BF16 = 2 } bess_dtype;
+/* BESS_F16X3 is an OPERAND format of the tensor-core path, not a table dtype: fp32 values
+ * carried as scaled fp16 (hi, lo) pairs, see bess_dot_gemm. */
+typedef enum { BESS_F32 = 0, BESS_F16 = 1, BESS_BF16 = 2, BESS_F16X3 = 3 } bess_dtype;
 
 /* score-function families (scoring.py) */
 typedef enum {
@@ -185,6 +187,13 @@ int bess_score_shared_bwd_cand(const bess_score_cfg_t* cfg, int dtype, int mode,
  *   dtype BESS_F32        : fp32 arrays hi / lo (3xTF32: hi*hi + hi*lo + lo*hi,
  *                           fp32-grade products, fp32 accumulate in TMEM)
  *   dtype BESS_F16 / BF16 : half arrays in *_hi (one MMA per k-step), *_lo unused
+ *   dtype BESS_F16X3      : fp16 arrays hi / lo of the SCALED operand, x * s = hi + lo with
+ *                           s a power of two chosen per operand matrix by bess_operand_scale
+ *                           (3xFP16: the same three products as 3xTF32 — fp16 and tf32 share
+ *                           the 11-bit significand — at twice the tensor-core rate and half
+ *                           the operand bytes); a_scale / b_scale point at the operands'
+ *                           {s, 1 / s} pairs on the device and the epilogue multiplies the
+ *                           accumulator by the two inverse scales (exact).  NULL otherwise.
  * a_mn_major != 0: A is given transposed, as [K, M] with M contiguous (leading
  * dimension lda) and consumed through MN-major UMMA descriptors — how the
  * dC = dS^T Q contraction reads the [S, N] score gradient without a transposed copy.
@@ -195,15 +204,24 @@ int64_t bess_dot_gemm_workspace(int M, int N, int K);
 int bess_dot_gemm(int dtype, const void* a_hi, const void* a_lo, int64_t lda, int a_mn_major,
                   const void* b_hi, const void* b_lo, int64_t ldb, int M, int N, int K, float* out,
                   bess_rowmap_t out_map, int64_t ld_out, int col0, int accumulate, void* workspace,
-                  int64_t workspace_bytes, void* stream);
+                  int64_t workspace_bytes, const float* a_scale, const float* b_scale, void* stream);
 /* Operand pre-pass for bess_dot_gemm: rows of `src` (dtype src_dtype, addressed
  * through map / idx / pitch, optionally scaled per row) -> dense operand arrays
  * hi / lo [n_rows, ld] and / or their transposes hiT / loT [width, ldT].
  * out_dtype BESS_F32: hi = rna_tf32(x), lo = rna_tf32(x - hi); BESS_F16 / BF16:
- * hi = x rounded to that type (lo / loT ignored).  Any output may be NULL. */
+ * hi = x rounded to that type (lo / loT ignored); BESS_F16X3: fp16 arrays,
+ * hi = fp16(x * s), lo = fp16(x * s - hi) with s = op_scale[0] (device, from
+ * bess_operand_scale; NULL for the other formats).  Any output may be NULL. */
 int bess_split_operand(int src_dtype, bess_rows_t src, int n_rows, int width,
                        const float* row_scale, int out_dtype, void* hi, void* lo, int64_t ld,
-                       void* hiT, void* loT, int64_t ldT, void* stream);
+                       void* hiT, void* loT, int64_t ldT, const float* op_scale, void* stream);
+/* Power-of-two scale of a BESS_F16X3 operand: scale[0] = s = 2^(14 - e), scale[1] = 1 / s,
+ * where factor * max |x| over the rows (times |row_scale|) = m * 2^e, m in [0.5, 1): the
+ * largest scaled element lies in [2^13, 2^14].  One kernel, no host sync; `state` = 2 x
+ * uint32 owned by the caller, zero-initialised once (the kernel leaves it zero). */
+int bess_operand_scale(int src_dtype, bess_rows_t src, int n_rows, int width,
+                       const float* row_scale, float factor, float* scale, void* state,
+                       void* stream);
 /* Cached 3xTF32 operands of a whole fp32 table for inference (TopKQueryBessKGE scores
  * every window of a constant shard on every call, bess.py:771-853): streams the
  * table once to form a 64-bit position-dependent checksum, compares it ON THE
@@ -273,12 +291,16 @@ int bess_loss_fwd_bwd(int kind, float margin, int adversarial, float adv_scale, 
 /* Same loss, but dL/dneg is written directly in the operand form bess_dot_gemm
  * consumes for the backward contractions: grad_dtype BESS_F32 -> d_neg_hi =
  * rna_tf32(g), d_neg_lo = rna_tf32(g - hi) (fp32 arrays); BESS_BF16 / BESS_F16 ->
- * d_neg_hi = g rounded to that type, d_neg_lo unused.  ld_grad in elements. */
+ * d_neg_hi = g rounded to that type, d_neg_lo unused; BESS_F16X3 -> fp16 arrays,
+ * d_neg_hi = fp16(g * s), d_neg_lo = fp16(g * s - hi) with s = grad_scale[0] (device; the
+ * caller derives it from the bound |g| <= loss_scale * max(weight) with bess_operand_scale
+ * over the weight vector).  ld_grad in elements; grad_scale NULL for the other formats. */
 int bess_loss_fwd_bwd_operand(int kind, float margin, int adversarial, float adv_scale,
                               float loss_scale, int64_t n_entity, const float* pos, float* neg, int n,
                               int n_neg, int64_t ld, const float* weight, int weight_n,
                               float* row_loss, float* d_pos, int grad_dtype, void* d_neg_hi,
-                              void* d_neg_lo, int64_t ld_grad, void* stream);
+                              void* d_neg_lo, int64_t ld_grad, const float* grad_scale,
+                              void* stream);
 /* deterministic sum of n floats (fixed order) -> out[0] */
 int bess_sum_f32(const float* x, int n, float* out, void* stream);
 

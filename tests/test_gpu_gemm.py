@@ -160,3 +160,107 @@ def test_dot_gemm_rowmap_accumulate_and_determinism():
     untouched = torch.ones(160, dtype=torch.bool, device="cuda")
     untouched[rows] = False
     assert torch.equal(outs[0][untouched], base[untouched])
+
+
+# ----------------------------------------------------------------------------
+# 3xFP16 (BESS_F16X3): fp32 operands as scaled fp16 (hi, lo) pairs
+# ----------------------------------------------------------------------------
+def _operands_x3(K_, L, x, transpose=False, row_scale=None):
+    R, W = x.shape
+    ld, ldt = (W + 7) // 8 * 8, (R + 7) // 8 * 8
+    hi = torch.zeros(R, ld, dtype=torch.float16, device="cuda")
+    lo = torch.zeros_like(hi)
+    hit = lot = None
+    if transpose:
+        hit = torch.zeros(W, ldt, dtype=torch.float16, device="cuda")
+        lot = torch.zeros_like(hit)
+    scale = torch.zeros(2, device="cuda")
+    state = torch.zeros(2, dtype=torch.int32, device="cuda")
+    K_.operand_scale(L.F32, L.rows(x), R, W, row_scale, 1.0, scale, state)
+    K_.split_operand(L.F32, L.rows(x), R, W, row_scale, L.F16X3, hi, lo, ld, hit, lot, ldt, x.device,
+                     scale)
+    return hi, lo, ld, hit, lot, ldt, scale, state
+
+
+@pytest.mark.parametrize("magnitude", [1.0, 1.0 / 256, 3e-5, 4e4])
+def test_split_operand_f16x3_scale_and_precision(magnitude):
+    """scale = power of two with the largest scaled element in [2^13, 2^14]; hi + lo
+    reproduces x * s to 2^-21 relative for everything within ~2^20 of the largest element —
+    whatever the operand's own magnitude (default-initialised tables are ~1/256, products of
+    two of them ~1e-5: far below fp16's normal range without the scale)."""
+    L, K = _imports()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(70, 100, generator=g) * magnitude).cuda()
+    x[5, 7] = 0.0
+    hi, lo, ld, hit, lot, ldt, scale, state = _operands_x3(K, L, x, transpose=True)
+    torch.cuda.synchronize()
+    s, inv = float(scale[0]), float(scale[1])
+    assert s * inv == 1.0 and s == 2.0 ** round(torch.log2(scale[0]).item())
+    top = float(x.abs().max()) * s
+    assert 2.0 ** 13 <= top <= 2.0 ** 14
+    assert int(state.abs().max()) == 0  # the kernel leaves its state words zero
+    eff = (hi[:, :100].double() + lo[:, :100].double()) * inv
+    big = x.abs() > float(x.abs().max()) * 2.0 ** -18
+    assert float(((eff - x.double()).abs() / x.double().abs().clamp_min(1e-300))[big].max()) < 2.0 ** -21
+    # every element, however small, is off by at most ~2^-36 of the largest one
+    assert float((eff - x.double()).abs().max()) <= float(x.abs().max()) * 2.0 ** -35
+    assert torch.equal(hit[:, :70], hi[:, :100].t()) and torch.equal(lot[:, :70], lo[:, :100].t())
+
+
+@pytest.mark.parametrize("aligned", [False, True])
+@pytest.mark.parametrize("scales", [(1.0, 1.0), (1.0 / 256, 1.0 / 256), (2e-5, 0.5), (3e3, 1e-3)])
+@pytest.mark.parametrize("M,N,Kd", SHAPES)
+def test_dot_gemm_f16x3_matches_fp64(M, N, Kd, scales, aligned):
+    """Same bound as 3xTF32 (4e-6 of sum |a_k b_k|), for operands of very different magnitudes,
+    K-major and MN-major A, TMA-store and direct-store epilogues, split-K shapes."""
+    L, K = _imports()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + Kd)
+    a = (torch.randn(M, Kd, generator=g) * scales[0]).cuda()
+    b = (torch.randn(N, Kd, generator=g) * scales[1]).cuda()
+    # a wide dynamic range inside one operand as well (rows spread over 4 decades)
+    a *= torch.logspace(-2, 2, M).cuda()[:, None]
+    a_hi, a_lo, lda, _, _, _, sa, _ = _operands_x3(K, L, a)
+    b_hi, b_lo, ldb, _, _, _, sb, _ = _operands_x3(K, L, b)
+    c0 = 4 if aligned else 1
+    ld_out = (N + 11) // 4 * 4 if aligned else N + 5
+    out = torch.full((M, ld_out), 7.0, device="cuda")
+    ws = torch.empty(max(K.dot_gemm_workspace(M, N, Kd) // 4, 1), device="cuda")
+    K.dot_gemm(L.F16X3, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, Kd, out, L.IDENT, ld_out, c0, False,
+               ws, a_scale=sa, b_scale=sb)
+    at_hi, at_lo, ldat, _, _, _, sat, _ = _operands_x3(K, L, a.t().contiguous())
+    out_mn = torch.full((M, ld_out), 7.0, device="cuda")
+    K.dot_gemm(L.F16X3, at_hi, at_lo, ldat, b_hi, b_lo, ldb, M, N, Kd, out_mn, L.IDENT, ld_out, c0,
+               False, ws, a_mn_major=True, a_scale=sat, b_scale=sb)
+    torch.cuda.synchronize()
+    assert torch.all(out[:, :c0] == 7.0) and torch.all(out[:, N + c0:] == 7.0)
+    assert torch.equal(out, out_mn)
+    got = out[:, c0:N + c0].double()
+    ref = a.double() @ b.double().t()
+    bound = a.double().abs() @ b.double().abs().t()
+    assert float(((got - ref).abs() / bound).max()) < 4e-6
+
+
+def test_dot_gemm_f16x3_vs_tf32x3_same_grade():
+    """The two split formats deliver the same accuracy class on the cfg-2 shape."""
+    L, K = _imports()
+    g = torch.Generator().manual_seed(11)
+    M, N, Kd = 2048, 2048, 256
+    a = (torch.randn(M, Kd, generator=g) * 0.3).cuda()
+    b = (torch.randn(N, Kd, generator=g) * 0.3).cuda()
+    ref = a.double() @ b.double().t()
+    bound = a.double().abs() @ b.double().abs().t()
+    ws = torch.empty(max(K.dot_gemm_workspace(M, N, Kd) // 4, 1), device="cuda")
+    errs = {}
+    a_hi, a_lo, lda, *_ = _operands(K, L, a, torch.float32)
+    b_hi, b_lo, ldb, *_ = _operands(K, L, b, torch.float32)
+    out = torch.empty(M, N, device="cuda")
+    K.dot_gemm(L.F32, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, Kd, out, L.IDENT, N, 0, False, ws)
+    errs["tf32x3"] = float(((out.double() - ref).abs() / bound).max())
+    a_hi, a_lo, lda, _, _, _, sa, _ = _operands_x3(K, L, a)
+    b_hi, b_lo, ldb, _, _, _, sb, _ = _operands_x3(K, L, b)
+    K.dot_gemm(L.F16X3, a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, Kd, out, L.IDENT, N, 0, False, ws,
+               a_scale=sa, b_scale=sb)
+    errs["f16x3"] = float(((out.double() - ref).abs() / bound).max())
+    print(errs)
+    assert errs["f16x3"] < 4e-6 and errs["tf32x3"] < 4e-6
+    assert errs["f16x3"] < 4 * errs["tf32x3"] + 1e-7

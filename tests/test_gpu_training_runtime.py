@@ -170,12 +170,21 @@ def test_gradient_accumulation_vs_oracle(opt_kind, k, reduction):
         res = step(**b)
         assert_close(res["loss"].cpu(), want["loss"][s], rtol=3e-4 if adam else 1e-5, atol=1e-4)
     torch.cuda.synchronize()
-    tol = dict(rtol=1e-3, atol=0.02 * 0.01) if adam else dict(rtol=1e-5, atol=2e-6)
-    assert_close(sf.entity_embedding.detach().cpu(), want["ent"], **tol)
-    assert_close(sf.relation_embedding.detach().cpu(), want["rel"], **tol)
-    if adam:
-        bad = ~torch.isclose(sf.entity_embedding.detach().cpu(), want["ent"], rtol=1e-4, atol=1e-5)
-        assert int(bad.sum()) <= 1e-3 * bad.numel()
+    got_e, got_r = sf.entity_embedding.detach().cpu(), sf.relation_embedding.detach().cpu()
+    if not adam:
+        assert_close(got_e, want["ent"], rtol=1e-5, atol=2e-6)
+        assert_close(got_r, want["rel"], rtol=1e-5, atol=2e-6)
+        return
+    # AdamW turns a gradient of one fp32 ulp into a step of ~lr: coordinates whose accumulated
+    # gradient is the residual of cancelling +-0.5 sigmoid-saturated terms (1.5e-8 in the oracle,
+    # 0 or 3e-8 under another rounding) are ill-conditioned by construction.  They are excluded
+    # by the ORACLE's gradient magnitude, must be few, and stay within Adam's maximal travel.
+    n_opt = len(want["grad_ent"])
+    for got, ref, grads in ((got_e, want["ent"], want["grad_ent"]), (got_r, want["rel"], want["grad_rel"])):
+        tiny = torch.stack([(g.abs() > 0) & (g.abs() < 1e-6) for g in grads]).any(0)
+        assert int(tiny.sum()) <= 0.02 * tiny.numel()
+        assert_close(got[~tiny], ref[~tiny], rtol=1e-4, atol=1e-5)
+        assert float((got - ref)[tiny].abs().max() if tiny.any() else 0.0) <= n_opt * 0.01 * 1.01
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
