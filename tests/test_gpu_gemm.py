@@ -202,8 +202,10 @@ def test_split_operand_f16x3_scale_and_precision(magnitude):
     eff = (hi[:, :100].double() + lo[:, :100].double()) * inv
     big = x.abs() > float(x.abs().max()) * 2.0 ** -18
     assert float(((eff - x.double()).abs() / x.double().abs().clamp_min(1e-300))[big].max()) < 2.0 ** -21
-    # every element, however small, is off by at most ~2^-36 of the largest one
-    assert float((eff - x.double()).abs().max()) <= float(x.abs().max()) * 2.0 ** -35
+    # every element, however small: 2^-21 of itself + ~2^-37 of the largest one (fp16 subnormal
+    # spacing 2^-24 against a largest scaled element >= 2^13)
+    err = (eff - x.double()).abs()
+    assert bool((err <= x.double().abs() * 2.0 ** -21 + float(x.abs().max()) * 2.0 ** -36).all())
     assert torch.equal(hit[:, :70], hi[:, :100].t()) and torch.equal(lot[:, :70], lo[:, :100].t())
 
 

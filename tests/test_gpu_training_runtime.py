@@ -44,6 +44,12 @@ def _problem(fam="DistMult", p=2, n=2, p_part=8, Nn=6, d=32, n_rel=5, n_ent=120,
 
 
 LCFG = dict(kind="logsigmoid", margin=2.0, negative_adversarial_sampling=True)
+# Adam with its default eps = 1e-8 turns a gradient of ONE fp32 ulp (the residual of two
+# sigmoid-saturated +-0.5 terms that cancel: 1.5e-8 under one rounding, 0 or 3e-8 under another)
+# into a step of ~lr/2 — in torch.optim as much as here.  The wrapper tests therefore run Adam
+# with eps = 1e-4, where the update is a well-conditioned function of the gradient, and keep
+# tight tolerances; the reference-fixture tests (tests/test_gpu_bess.py) cover default eps.
+ADAM_EPS = 1e-4
 
 
 def _model(H, fam, p, sh, n_rel, d, ent, rel):
@@ -66,28 +72,22 @@ def test_lr_schedule_and_step_count_survive_graph_replay(opt_kind):
     lrs = [0.1, 0.05, 0.2, 0.01, 0.15, 0.07]
     ocfg = {"sgd": dict(kind="sgd", lr=lrs[0]),
             "sgdm": dict(kind="sgd", lr=lrs[0], momentum=0.9),
-            "adamw": dict(kind="adamw", lr=lrs[0], weight_decay=0.01)}[opt_kind]
+            "adamw": dict(kind="adamw", lr=lrs[0], weight_decay=0.01, eps=ADAM_EPS)}[opt_kind]
     want = O.training_steps(H.score_cfg(fam, d, p), H.oracle_loss_cfg(LCFG), ocfg, ent, rel,
                             batches, "t", True, True, "mean", lr_schedule=lrs)
     sf, model = _model(H, fam, p, sh, n_rel, d, ent, rel)
-    opt = (AdamW(lr=lrs[0], weight_decay=0.01) if opt_kind == "adamw"
+    opt = (AdamW(lr=lrs[0], weight_decay=0.01, eps=ADAM_EPS) if opt_kind == "adamw"
            else SGD(lr=lrs[0], momentum=0.9 if opt_kind == "sgdm" else 0.0))
     step = training_model(model, opt)
     assert step.cuda_graph
-    # AdamW: a coordinate whose gradient is ~eps moves by lr * g / (|g| + eps), which amplifies
-    # the last bits of g into a visible fraction of lr — inherent to Adam, same in torch.optim
-    # run twice with different reduction orders; hence tolerances scaled by lr for it
     adam = opt_kind == "adamw"
     for s, b in enumerate(batches):
         opt.lr = lrs[s]
         res = step(**b)
-        assert_close(res["loss"].cpu(), want["loss"][s], rtol=3e-4 if adam else 1e-5, atol=1e-4)
+        assert_close(res["loss"].cpu(), want["loss"][s], rtol=2e-5 if adam else 1e-5, atol=1e-4)
     torch.cuda.synchronize()
     assert len([g for g in step._graphs.values() if g != "warm"]) == 1  # replays did happen
-    tol = dict(rtol=1e-3, atol=0.02 * max(lrs)) if adam else dict(rtol=1e-5, atol=2e-6)
-    if adam:  # ... and all but a handful of coordinates agree tightly
-        bad = ~torch.isclose(sf.entity_embedding.detach().cpu(), want["ent"], rtol=1e-4, atol=1e-5)
-        assert int(bad.sum()) <= 1e-3 * bad.numel()
+    tol = dict(rtol=1e-4, atol=2e-5) if adam else dict(rtol=1e-5, atol=2e-6)
     assert_close(sf.entity_embedding.detach().cpu(), want["ent"], **tol)
     assert_close(sf.relation_embedding.detach().cpu(), want["rel"], **tol)
 
@@ -158,33 +158,21 @@ def test_gradient_accumulation_vs_oracle(opt_kind, k, reduction):
     fam, p, d, n_rel = "RotatE", 1, 16, 5
     sh, ent, rel, batches, _ = _problem(fam, p, d=d, n_rel=n_rel, n_batch=6)
     ocfg = {"sgd": dict(kind="sgd", lr=0.1), "sgdm": dict(kind="sgd", lr=0.1, momentum=0.9),
-            "adamw": dict(kind="adamw", lr=0.01, weight_decay=0.01)}[opt_kind]
+            "adamw": dict(kind="adamw", lr=0.01, weight_decay=0.01, eps=ADAM_EPS)}[opt_kind]
     want = O.training_steps(H.score_cfg(fam, d, p), H.oracle_loss_cfg(LCFG), ocfg, ent, rel, batches,
                             "t", True, True, "mean", accumulate=k, accumulation_reduction=reduction)
     sf, model = _model(H, fam, p, sh, n_rel, d, ent, rel)
-    opt = (AdamW(lr=0.01, weight_decay=0.01) if opt_kind == "adamw"
+    opt = (AdamW(lr=0.01, weight_decay=0.01, eps=ADAM_EPS) if opt_kind == "adamw"
            else SGD(lr=0.1, momentum=0.9 if opt_kind == "sgdm" else 0.0))
     step = training_model(model, opt, gradient_accumulation=k, accumulation_reduction=reduction)
-    adam = opt_kind == "adamw"  # see the note on AdamW's conditioning above
+    adam = opt_kind == "adamw"
     for s, b in enumerate(batches):
         res = step(**b)
-        assert_close(res["loss"].cpu(), want["loss"][s], rtol=3e-4 if adam else 1e-5, atol=1e-4)
+        assert_close(res["loss"].cpu(), want["loss"][s], rtol=2e-5 if adam else 1e-5, atol=1e-4)
     torch.cuda.synchronize()
-    got_e, got_r = sf.entity_embedding.detach().cpu(), sf.relation_embedding.detach().cpu()
-    if not adam:
-        assert_close(got_e, want["ent"], rtol=1e-5, atol=2e-6)
-        assert_close(got_r, want["rel"], rtol=1e-5, atol=2e-6)
-        return
-    # AdamW turns a gradient of one fp32 ulp into a step of ~lr: coordinates whose accumulated
-    # gradient is the residual of cancelling +-0.5 sigmoid-saturated terms (1.5e-8 in the oracle,
-    # 0 or 3e-8 under another rounding) are ill-conditioned by construction.  They are excluded
-    # by the ORACLE's gradient magnitude, must be few, and stay within Adam's maximal travel.
-    n_opt = len(want["grad_ent"])
-    for got, ref, grads in ((got_e, want["ent"], want["grad_ent"]), (got_r, want["rel"], want["grad_rel"])):
-        tiny = torch.stack([(g.abs() > 0) & (g.abs() < 1e-6) for g in grads]).any(0)
-        assert int(tiny.sum()) <= 0.02 * tiny.numel()
-        assert_close(got[~tiny], ref[~tiny], rtol=1e-4, atol=1e-5)
-        assert float((got - ref)[tiny].abs().max() if tiny.any() else 0.0) <= n_opt * 0.01 * 1.01
+    tol = dict(rtol=1e-4, atol=2e-5) if adam else dict(rtol=1e-5, atol=2e-6)
+    assert_close(sf.entity_embedding.detach().cpu(), want["ent"], **tol)
+    assert_close(sf.relation_embedding.detach().cpu(), want["rel"], **tol)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
