@@ -541,12 +541,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (p.tma_store) {
         // TMEM -> registers -> swizzled smem chunk -> one coalesced TMA store per 32 x 32 chunk
         const uint32_t my_epi = epi_base + (uint32_t)(warp - 2) * 2 * kEpiChunkBytes;
-#pragma unroll 1
-        for (int c = 0; c < kBlockN; c += 32) {
-          if (n0 + c >= p.N) break;  // chunk entirely out of range (warp-uniform)
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)c, v);
-          tmem_ld_wait();
+        // software pipeline over the 32-column chunks: the TMEM load of chunk c + 1 is in
+        // flight while chunk c goes registers -> swizzled smem -> TMA store
+        auto put_chunk = [&](uint32_t (&v)[32], int c) {
           if (scaled) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * oscale);
@@ -567,6 +564,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (lane == 0) {
             tma_store_2d(&map_out, chunk, n0 + c, m0 + quarter * 32);
             tma_store_commit();
+          }
+        };
+        const int n_chunks = min(kBlockN, p.N - n0 + 31) >> 5;  // chunks with columns in range
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+#pragma unroll 1
+        for (int ci = 0; ci < n_chunks; ci += 2) {
+          tmem_ld_wait();
+          if (ci + 1 < n_chunks) tmem_ld32(taddr + (uint32_t)((ci + 1) << 5), vb);
+          put_chunk(va, ci << 5);
+          if (ci + 1 < n_chunks) {
+            tmem_ld_wait();
+            if (ci + 2 < n_chunks) tmem_ld32(taddr + (uint32_t)((ci + 2) << 5), va);
+            put_chunk(vb, (ci + 1) << 5);
           }
         }
       } else {
@@ -685,20 +696,33 @@ BESS_D void scale_from_max(float mx, float* scale /* {s, 1 / s} */) {
   scale[1] = ldexpf(1.f, -se);
 }
 
-// state = {raw max bits, ticket} (zero between calls: the last block resets both)
+// state = {raw max bits, ticket} (zero between calls: the last block resets both).
+// Warp per row, 128-bit loads along the row when the row start is 16-byte aligned.
 template <typename ST>
 __global__ void __launch_bounds__(256) operand_absmax_kernel(bess_rows_t src, int n_rows, int width,
                                                              const float* row_scale, float factor,
                                                              float* scale, unsigned* state) {
   const ST* base = reinterpret_cast<const ST*>(src.base);
-  float mx = 0.f;
-  const int64_t total = (int64_t)n_rows * width;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(t / width), c = (int)(t - (int64_t)r * width);
-    float x = fabsf(ldf(base + src_row(src, r) * src.pitch + c));
-    if (row_scale != nullptr) x *= fabsf(row_scale[r]);
-    mx = fmaxf(mx, x);  // NaN operands are ignored here (and poison the product, as they should)
+  constexpr int V = Elem<ST>::kVec;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  float mx = 0.f;  // NaN operands are ignored here (and poison the product, as they should)
+  for (int r = warp; r < n_rows; r += n_warps) {
+    const ST* row = base + src_row(src, r) * src.pitch;
+    float m = 0.f;
+    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0 && width % V == 0) {
+      for (int c = lane * V; c < width; c += 32 * V) {
+        float x[V];
+        Elem<ST>::load_vec(row + c, x);
+#pragma unroll
+        for (int j = 0; j < V; ++j) m = fmaxf(m, fabsf(x[j]));
+      }
+    } else {
+      for (int c = lane; c < width; c += 32) m = fmaxf(m, fabsf(ldf(row + c)));
+    }
+    if (row_scale != nullptr) m *= fabsf(row_scale[r]);
+    mx = fmaxf(mx, m);
   }
   __shared__ float red[8];
   mx = block_max<256>(mx, red);
@@ -1066,9 +1090,9 @@ extern "C" int bess_operand_scale(int src_dtype, bess_rows_t src, int n_rows, in
                                   void* stream) {
   BESS_CHECK_ARG(scale != nullptr && state != nullptr, "bess_operand_scale: scale / state required");
   if (n_rows <= 0 || width <= 0) return BESS_OK;
-  const int64_t total = (int64_t)n_rows * width;
-  int blocks = (int)((total + 256 * 8 - 1) / (256 * 8));
-  blocks = blocks < 1 ? 1 : (blocks > 2 * kNumSM ? 2 * kNumSM : blocks);
+  // a warp per row (a single long row, e.g. the weight vector, is one warp's work)
+  int blocks = (n_rows + 7) / 8;
+  blocks = blocks < 1 ? 1 : (blocks > 4 * kNumSM ? 4 * kNumSM : blocks);
   cudaStream_t st = (cudaStream_t)stream;
   switch (src_dtype) {
     case BESS_F32: operand_absmax_kernel<float><<<blocks, 256, 0, st>>>(src, n_rows, width, row_scale, factor, scale, (unsigned*)state); break;

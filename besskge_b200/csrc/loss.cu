@@ -251,6 +251,7 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
 
   // negative weights: softmax(adv_scale * neg) (detached) or 1/N (loss.py:28-51)
   float mx = 0.f, inv_se = 1.f / (float)n_neg;
+  float ev[L_CACHE];  // adversarial: exp(adv_scale * score - max) of the cached columns
   if (adversarial) {
     mx = -CUDART_INF_F;
 #pragma unroll
@@ -267,8 +268,11 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
     for (int i = 0; i < L_CACHE / 4; ++i) {
       const int c = (i * L_THREADS + threadIdx.x) * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (c + j < n_neg) se += __expf(adv_scale * v[4 * i + j] - mx);
+      for (int j = 0; j < 4; ++j) {
+        // the un-normalised softmax weight is kept for the second pass (one ex2 less per score)
+        ev[4 * i + j] = c + j < n_neg ? __expf(adv_scale * v[4 * i + j] - mx) : 0.f;
+        se += ev[4 * i + j];
+      }
     }
     for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) se += __expf(adv_scale * nrow[c] - mx);
     se = block_sum<L_THREADS>(se, red);
@@ -279,8 +283,9 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
   // issue-bound on the libm expansions (ncu: 69 % issue active, DRAM 24 %).  Every term enters
   // the row loss / gradient through a weighted SUM with weights summing to 1, so the absolute
   // error stays ~1e-7 of a row loss of order 1..10 — far inside the 1e-5 bar (tests).
-  auto one = [&](float s) -> float {  // gradient of column with score s; accumulates the loss
-    const float wj = adversarial ? __expf(adv_scale * s - mx) * inv_se : inv_se;
+  // gradient of a column with score s (e = its un-normalised softmax weight); accumulates the loss
+  auto one = [&](float s, float e) -> float {
+    const float wj = adversarial ? e * inv_se : inv_se;
     if (KIND == BESS_LOSS_LOGSIGMOID) {
       // x = -s - m;  t = exp(-|x|);  logsigmoid(x) = min(x, 0) - log(1 + t);
       // sigmoid(s + m) = sigmoid(-x) = (x >= 0 ? t : 1) / (1 + t)
@@ -303,12 +308,14 @@ BESS_D void loss_row(const LossArgs& a, int r, float (&v)[L_CACHE], float* red) 
     if (c < n_neg) {
       float g[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) g[j] = c + j < n_neg ? one(v[4 * i + j]) : 0.f;
+      for (int j = 0; j < 4; ++j)
+        g[j] = c + j < n_neg ? one(v[4 * i + j], adversarial ? ev[4 * i + j] : 0.f) : 0.f;
       store_grad4<OUT>(g_hi, g_lo, grow + c, g, min(4, n_neg - c), vec_out, gscale);
     }
   }
   for (int c = kCached + threadIdx.x; c < n_neg; c += L_THREADS) {
-    float g[4] = {one(nrow[c]), 0.f, 0.f, 0.f};
+    const float sc = nrow[c];
+    float g[4] = {one(sc, adversarial ? __expf(adv_scale * sc - mx) : 0.f), 0.f, 0.f, 0.f};
     store_grad4<OUT>(g_hi, g_lo, grow + c, g, 1, false, gscale);
   }
   part = block_sum<L_THREADS>(part, red);
