@@ -1323,12 +1323,17 @@ class ScoreMovingBessKGE(BessKGE):
     replicated (AllGather) and the SCORES travel back (AllToAll) — reference
     bess.py:471-603.  The candidate rows are read in place from the shard
     through the index list (fused gather + score), so the [Q, Nn, D] negative
-    tensor of the reference is never materialised.  Inference only."""
+    tensor of the reference is never materialised.
+
+    Training (under `training_model`) runs the transposed exchange: dL/dscore travels to the
+    shards that scored (AllToAll), each computes the gradients of ITS candidate rows — which
+    never leave the shard — and of the replicated query vectors; the query gradients are summed
+    over the scoring shards in shard order at the shard that owns the query (the transpose of
+    the AllGather), then flow through the query prologue into the head / tail rows and the
+    relation table.  Eager (not graph-captured)."""
 
     def _run(self, head, relation, tail, negative, triple_mask, triple_weight, negative_mask,
              optimizer) -> Dict[str, Any]:
-        if optimizer is not None:
-            raise NotImplementedError("ScoreMovingBessKGE is inference-only in this build")
         ws, pl = self._setup()
         dev = ws.device
         ent, rel_table = self._tables()
@@ -1338,7 +1343,7 @@ class ScoreMovingBessKGE(BessKGE):
         p = head.shape[-1]
         B, Nn = negative.shape[-2], negative.shape[-1]
         S = n * p
-        W = ent.shape[-1]
+        W, Wr = ent.shape[-1], rel_table.shape[-1]
         cfg = self.score_fn.kernel_cfg()
         dt = L.dtype_code(ent.dtype)
         tdt = ent.dtype
@@ -1348,6 +1353,9 @@ class ScoreMovingBessKGE(BessKGE):
         shared = bool(self.score_fn.negative_sample_sharing)
         R = pl.n_local
         dist = pl.distributed
+        train = optimizer is not None
+        if train and self.loss_fn is None:
+            raise ValueError("training needs a loss_fn")
 
         def put(name, t, dtype):
             if t is None:
@@ -1372,8 +1380,16 @@ class ScoreMovingBessKGE(BessKGE):
         one = ws.get("one", (1,), torch.float32)
         one.fill_(1.0)
 
-        # candidates per scoring shard: X columns contributed to every query
-        X = Nn if (flat and triple_based) or not flat else n * Nn
+        half = p // 2
+        # columns every scoring shard contributes to a query: a flat list (replicated for
+        # triple-based samplers), the query's own Nn candidates, or — shared, non-flat — the
+        # candidates of every query of the group (bess.py:523-534 with negative sample sharing)
+        if flat:
+            X = Nn if triple_based else n * Nn
+        elif shared:
+            X = n * (B // 2 if scheme == "ht" else B) * Nn
+        else:
+            X = Nn
         N = n * X
         # rows of the replicated query arrays are ordered (query shard j, q)
         H = ws.get("H", (n, S, W), tdt)        # head rows of every shard's queries
@@ -1397,8 +1413,22 @@ class ScoreMovingBessKGE(BessKGE):
             SEND_T = ws.get("SEND", (n, p, W), tdt)
             sc_local = ws.get("sc_local", (n * S, X), torch.float32)
             sc_recv = ws.get("sc_recv", (n, S, X), torch.float32)
+        ce = self.loss_fn is not None and self.loss_fn._kind == L.LOSS_SOFTMAX_CE
+        if train:
+            d_pos = ws.get("d_pos", (R * S,), torch.float32)
+            d_neg = ws.get("d_neg", (R * S, N), torch.float32)
+            dH = ws.get("sm_dH", (n, S, W), torch.float32)       # local: [replica]; dist: row `me`
+            dT = ws.get("sm_dT", (n, n, p, W), torch.float32)    # gradients of T, same layout
+            dRq = ws.get("dRq", (R * S, Wr), torch.float32)
+            d_qv = ws.get("d_qv", (n * S, nvec, W), torch.float32)
+            d_sc = d_neg if not dist else ws.get("sm_dsc", (n * S, X), torch.float32)
+            sort_n = max(2 * S, R * S, n * B * Nn, 0 if flat else n * S * Nn)
+            sort_ws = ws.get("sort_ws", (K.sort_workspace(sort_n) // 4 + 64,), torch.int32)
+            d_rel_table = ws.get("d_rel_table", (_up(rel_table.numel() * 4, 16) // 4,),
+                                 torch.float32)[:rel_table.numel()].view(rel_table.shape)
+            key_bits = max(1, int(ent.shape[1] - 1).bit_length())
+            rel_bits = max(1, int(rel_table.shape[0] - 1).bit_length())
         acc: Dict[str, List] = {}
-        half = p // 2
 
         for s in range(bps):
             if dist:
@@ -1440,39 +1470,70 @@ class ScoreMovingBessKGE(BessKGE):
                     (L.MODE_HEADS, L.rowmap(half, p, 0), n * n * half, Tall, 0),
                     (L.MODE_TAILS, L.rowmap(half, p, half), n * n * half, Hall, 1),
                 ]
-            for mode, qmap, nq, fixed_buf, bsel in groups:
-                K.prologue_fwd(cfg, dt, mode, L.rows(fixed_buf, rmap=qmap), rel_table, rel_all,
-                               qmap, nq, qv)
-                for shard, row, col0 in scorers:
-                    idx_r = nidx[row]  # [n(query shard), B, Nn]: candidates stored on `shard`
-                    table = ent[shard]
-                    if flat:
-                        if triple_based:
-                            # one replicated list; "ht": b selects the heads / tails list
-                            sel = idx_r[0, bsel if scheme == "ht" else 0]
-                            n_c = Nn
-                        elif scheme == "ht":
-                            sel = idx_r[:, bsel].contiguous().view(-1)
-                            n_c = n * Nn
-                        else:
-                            sel = idx_r.reshape(-1)
-                            n_c = n * Nn
-                        cand = L.rows(table, idx=sel)
-                        scale = None
-                        if need_scale:
-                            scale = ws.get("cand_scale", (n_c,), torch.float32)
-                            K.cand_inv_norm(dt, cand, n_c, W, scale)
+
+            def candidates(shard: int, row: int, bsel: int):
+                """(index list into shard `shard`, shared?, candidates per query) of one group."""
+                idx_r = nidx[row]  # [n(query shard), B, Nn]: candidates stored on `shard`
+                if flat:
+                    if triple_based:  # one replicated list; "ht": b selects the heads / tails list
+                        return idx_r[0, bsel if scheme == "ht" else 0].contiguous(), True, Nn
+                    if scheme == "ht":
+                        return idx_r[:, bsel].contiguous().view(-1), True, n * Nn
+                    return idx_r.reshape(-1), True, n * Nn
+                if shared and scheme == "ht":
+                    # negatives of the first half of every partition's triples corrupt heads,
+                    # of the second half tails (bess.py:556-566): the group's own sub-list
+                    blk = idx_r.view(n, n, p, Nn)[:, :, bsel * half:(bsel + 1) * half]
+                    sel = blk.contiguous().view(-1)
+                    return sel, True, sel.numel()
+                # per-query candidates: the query at position pos (among the n*S replicated
+                # queries) reads rows [pos * Nn, (pos + 1) * Nn) of the full list
+                sel = idx_r.reshape(-1)
+                return sel, shared, (sel.numel() if shared else Nn)
+
+            def score_group(gi, shard, row, col0, backward: bool):
+                mode, qmap, nq, fixed_buf, bsel = groups[gi]
+                table = ent[shard]
+                sel, is_shared, n_c = candidates(shard, row, bsel)
+                cand = L.rows(table, idx=sel)
+                scale = None
+                if is_shared and need_scale:
+                    scale = ws.get("cand_scale", (n_c,), torch.float32)
+                    K.cand_inv_norm(dt, cand, n_c, W, scale)
+                if not backward:
+                    if is_shared:
                         K.shared_fwd(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, qmap,
                                      ld_sc, col0, aux)
                     else:
-                        if shared:
-                            raise NotImplementedError(
-                                "ScoreMoving with non-flat shared negatives is not implemented"
-                            )
-                        # query at position (j, q): its Nn candidates are idx_r[j, q, :]
-                        cand = L.rows(table, idx=idx_r.reshape(-1))
-                        K.pertriple_fwd(cfg, dt, mode, qv, nq, cand, Nn, Nn, score_buf, qmap,
-                                        ld_sc, col0, aux)
+                        K.pertriple_fwd(cfg, dt, mode, qv, nq, cand, Nn, Nn, score_buf, qmap, ld_sc,
+                                        col0, aux)
+                    return None
+                # ---- backward of this (group, scoring shard): d_qv part + candidate-row grads
+                part = d_qv_parts[scorers_pos[shard]]
+                if is_shared:
+                    d_c = ws.get(f"sm_dc{gi}", (R, n_c, W), torch.float32)[scorers_pos[shard]]
+                    cws = ws.get("cand_ws", (max(K.shared_bwd_cand_workspace(cfg, nq, n_c) // 4,
+                                                 1),), torch.float32)
+                    K.shared_bwd_query(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, d_sc,
+                                       qmap, ld_sc, col0, aux, part)
+                    K.shared_bwd_cand(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, d_sc,
+                                      qmap, ld_sc, col0, aux, L.rows(d_c), cws, add=False)
+                    if need_scale:
+                        K.cand_norm_bwd(dt, cand, n_c, W, scale, L.rows(d_c))
+                    return sel, d_c
+                # one gradient row per (query position, candidate): both "ht" groups write disjoint
+                # rows of the same buffer, which is scattered once
+                d_c = ws.get("sm_dc_pt", (R, n * S * Nn, W), torch.float32)[scorers_pos[shard]]
+                K.pertriple_bwd(cfg, dt, mode, qv, nq, cand, Nn, Nn, score_buf, d_sc, qmap, ld_sc,
+                                col0, aux, part, L.rows(d_c))
+                return (sel, d_c) if gi == len(groups) - 1 else None
+
+            scorers_pos = {shard: i for i, (shard, _, _) in enumerate(scorers)}
+            for gi, (mode, qmap, nq, fixed_buf, bsel) in enumerate(groups):
+                K.prologue_fwd(cfg, dt, mode, L.rows(fixed_buf, rmap=qmap), rel_table, rel_all,
+                               qmap, nq, qv)
+                for shard, row, col0 in scorers:
+                    score_group(gi, shard, row, col0, False)
             if dist:
                 # scores back to the shards that own the queries (bess.py:583-592)
                 torch.distributed.all_to_all_single(sc_recv.view(-1), sc_local.view(-1))
@@ -1481,17 +1542,95 @@ class ScoreMovingBessKGE(BessKGE):
             else:
                 finals = [(base + r, base + r, pos[r * S:(r + 1) * S],
                            score_buf[r * S:(r + 1) * S]) for r in range(n)]
-            for o, row, pos_r, neg_r in finals:
+            for li, (o, row, pos_r, neg_r) in enumerate(finals):
                 if nmask is not None:
                     EmbeddingMovingBessKGE._mask_block(neg_r, S, N, p, n, X, nmask[row], flat,
                                                        scheme, 0)
                 if self.loss_fn is not None:
                     w = tw[row] if tw is not None else one
-                    loss, _, _ = self.loss_fn.fwd_bwd(pos_r, neg_r, w)
+                    neg_l = neg_r.clone() if (ce and train) else neg_r  # CE shifts scores in place
+                    loss, _, _ = self.loss_fn.fwd_bwd(
+                        pos_r, neg_l, w, d_pos[li * S:(li + 1) * S] if train else None,
+                        d_neg[li * S:(li + 1) * S] if train else None)
                     loss_out[o] = loss
                 if self.evaluation is not None:
                     self._finish_metrics({}, pos_r, neg_r,
                                          tmask[row] if tmask is not None else None, acc)
+            if not train:
+                continue
+
+            # ======================= backward =======================
+            hyper = self._hyper(bps)[s]
+            if dist:
+                me = pl.rank
+                # dL/dscore back to the shards that scored: transpose of the score AllToAll
+                send = ws.get("sm_dsend", (n, S, X), torch.float32)
+                send.copy_(d_neg.view(S, n, X).transpose(0, 1))
+                torch.distributed.all_to_all_single(d_sc.view(-1), send.view(-1))
+                # the scores this rank computed (sc_local) are still in place for the kernels
+                K.triple_bwd(cfg, dt, L.rows(H[me]), L.rows(T[me].view(S, W)), rel_table, rel[row0],
+                             L.IDENT, S, pos_out[s * S:(s + 1) * S], d_pos, L.IDENT, L.rows(dH[me]),
+                             L.rows(dT[me].view(S, W)), dRq, False, False, False)
+            else:
+                K.triple_bwd(cfg, dt, L.rows(Hall), L.rows(Tall), rel_table, rel_all, L.IDENT, n * S,
+                             pos, d_pos, L.IDENT, L.rows(dH.view(n * S, W)),
+                             L.rows(dT.view(n * S, W)), dRq, False, False, False)
+            cand_parts: Dict[int, List[Tuple[torch.Tensor, torch.Tensor]]] = {}
+            for gi, (mode, qmap, nq, fixed_buf, bsel) in enumerate(groups):
+                K.prologue_fwd(cfg, dt, mode, L.rows(fixed_buf, rmap=qmap), rel_table, rel_all,
+                               qmap, nq, qv)
+                cnt = nq * nvec * W
+                # one slot of query gradients per scoring shard (local mode) / this rank's (dist.)
+                d_qv_parts = ws.get("sm_dqv", (len(scorers), cnt), torch.float32)
+                for shard, row, col0 in scorers:
+                    got = score_group(gi, shard, row, col0, True)
+                    if got is not None:
+                        cand_parts.setdefault(shard, []).append(got)
+                # query gradients: sum over the scoring shards in shard order at the owner
+                if dist:
+                    # queries are ordered (owner shard j, q): block j of the part goes to rank j
+                    recv = ws.get("sm_dqv_recv", (n, cnt // n), torch.float32)
+                    torch.distributed.all_to_all_single(recv.view(-1), d_qv_parts.view(-1))
+                    K.peer_reduce(recv, n, cnt // n, 1.0, d_qv)
+                    own = nq // n  # this rank's queries of the group, at positions qmap(q) of its S
+                    d_fix = dT[me].view(S, W) if mode == L.MODE_HEADS else dH[me]
+                    fix = T[me].view(S, W) if mode == L.MODE_HEADS else H[me]
+                    K.prologue_bwd(cfg, dt, mode, L.rows(fix, rmap=qmap), rel_table, rel[row0],
+                                   qmap, own, d_qv, L.rows(d_fix, rmap=qmap), dRq, True, True)
+                else:
+                    K.peer_reduce(d_qv_parts, n, cnt, 1.0, d_qv)
+                    d_fix = dT.view(n * S, W) if mode == L.MODE_HEADS else dH.view(n * S, W)
+                    K.prologue_bwd(cfg, dt, mode, L.rows(fixed_buf, rmap=qmap), rel_table, rel_all,
+                                   qmap, nq, d_qv, L.rows(d_fix, rmap=qmap), dRq, True, True)
+            if cfg.family == L.BOXE:
+                K.boxe_rel_finalize(cfg, dt, rel_table, rel[row0] if dist else rel_all,
+                                    R * S, dRq)
+            # ---- relation table: reduce per-query rows, all-reduce over ranks, update
+            rk = ws.get("rel_keys", (R * S,), torch.int32)
+            rp = ws.get("rel_perm", (R * S,), torch.int32)
+            K.sort_keys((rel[row0] if dist else rel_all).contiguous(), R * S, rel_bits, rk, rp,
+                        sort_ws)
+            K.relation_grad_reduce(dRq, Wr, rk, rp, R * S, rel_table.shape[0], d_rel_table)
+            if dist:
+                torch.distributed.all_reduce(d_rel_table)
+            if getattr(optimizer, "relation_grad_reduction", "mean") == "mean" and n > 1:
+                d_rel_table.mul_(1.0 / n)
+            # ---- entity shards: heads (local), tails (rows this shard sent to every replica)
+            # and the candidate rows, which never left the shard
+            if dist:
+                dT_back = ws.get("sm_dT_back", (n, p, W), torch.float32)
+                pl.all_to_all(dT_back, dT[me])  # tail gradients back to the shards that own them
+            for li, (shard, row, _) in enumerate(scorers):
+                if dist:
+                    parts = [(gidx[row], 2 * S, S, p, dH[me], dT_back.data_ptr(), p)]
+                else:
+                    parts = [(gidx[row], 2 * S, S, p, dH[shard],
+                              dT.data_ptr() + shard * p * W * 4, n * p)]
+                for sel, d_c in cand_parts[shard]:
+                    parts.append((sel, sel.numel(), sel.numel(), 1, d_c, 0, 0))
+                self._apply_parts(optimizer, ent[shard], shard, parts, key_bits, hyper, sort_ws, ws)
+            self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
+
         out: Dict[str, Any] = {}
         if self.return_scores:
             out["positive_score"] = pos_out if tdt == torch.float32 else pos_out.to(tdt)
@@ -1503,6 +1642,39 @@ class ScoreMovingBessKGE(BessKGE):
         if "metrics" in acc:
             out["metrics"] = torch.cat(acc["metrics"], dim=0)
         return out
+
+    def _apply_parts(self, opt, table: torch.Tensor, shard: int, parts, key_bits: int,
+                     hyper: torch.Tensor, sort_ws: torch.Tensor, ws: K.Workspace) -> None:
+        """Scatter several (index list, gradient rows) parts into one shard and update it.
+        Plain SGD applies each part sparsely (exact); momentum / AdamW first accumulate every
+        part into the shard's dense fp32 accumulator, then run one dense-semantics pass."""
+        W = table.shape[1]
+        st = self._opt_state
+        if not opt.sparse_exact:
+            key = f"ent_acc_{shard}"
+            if key not in st:
+                st[key] = torch.zeros(table.shape[0], W, dtype=torch.float32, device=table.device)
+        for keys, G, n_local, per, g_local, g_dst, stride_rows in parts:
+            sk = ws.get("sm_sort_keys", (G,), torch.int32)
+            sp = ws.get("sm_sort_perm", (G,), torch.int32)
+            K.sort_keys(keys.contiguous(), G, key_bits, sk, sp, sort_ws)
+            if opt.sparse_exact:
+                K.scatter_sgd(table, sk, sp, G, n_local, per, g_local, g_dst, stride_rows, opt.lr,
+                              hyper)
+            else:
+                K.scatter_accumulate(W, sk, sp, G, n_local, per, g_local, g_dst, stride_rows,
+                                     st[f"ent_acc_{shard}"])
+        if opt.sparse_exact:
+            return
+        key0, key1 = f"ent_s0_{shard}", f"ent_s1_{shard}"
+        if opt.kind != L.OPT_SGD and key0 not in st:
+            st[key0] = torch.zeros_like(st[f"ent_acc_{shard}"])
+        if opt.kind == L.OPT_ADAMW and key1 not in st:
+            st[key1] = torch.zeros_like(st[f"ent_acc_{shard}"])
+        b1, b2 = getattr(opt, "betas", (0.0, 0.0))
+        K.opt_dense(opt.kind, table, st[f"ent_acc_{shard}"], None, st.get(key0), st.get(key1),
+                    opt.lr, opt.momentum, opt.dampening, b1, b2, getattr(opt, "eps", 0.0),
+                    opt.weight_decay, 1, hyper, grad_scale=1.0, zero_grad=True)
 
 
 # ---------------------------------------------------------------------------
@@ -1559,6 +1731,12 @@ class TrainingModel:
 
     def __call__(self, head, relation, tail, negative, triple_mask=None, triple_weight=None,
                  negative_mask=None) -> Dict[str, Any]:
+        if not isinstance(self.model, EmbeddingMovingBessKGE):
+            # ScoreMovingBessKGE trains eagerly (its exchange uses collectives)
+            self.model._setup()
+            self.model._begin_steps(self.optimizer, head.shape[0] // self.model.sharding.n_shard)
+            return self.model._run(head, relation, tail, negative, triple_mask, triple_weight,
+                                   negative_mask, optimizer=self.optimizer)
         staged = self.model.stage(head, relation, tail, negative, triple_mask, triple_weight,
                                   negative_mask)  # H2D into the persistent input buffers
         return self._run(staged)

@@ -590,7 +590,8 @@ def training_steps(
     shared: bool, relation_grad_reduction: str = "mean", augment: bool = False,
     weights: Optional[List[Optional[torch.Tensor]]] = None,
     lr_schedule: Optional[List[float]] = None, accumulate: int = 1,
-    accumulation_reduction: str = "mean",
+    accumulation_reduction: str = "mean", model: str = "embedding_moving",
+    triple_based: bool = False,
 ) -> Dict[str, Any]:
     """Runs len(batches) micro-batch steps (each: n replicas, summed losses, one
     optimizer step).  Entity-table gradients are the plain sum over replicas
@@ -618,9 +619,14 @@ def training_steps(
             opt_e.zero_grad(set_to_none=True)
             opt_r.zero_grad(set_to_none=True)
             rel_acc = None
-        pos, neg = embedding_moving_forward(cfg, ent, rel_table, b["head"], b["relation"], b["tail"],
-                                            b["negative"], scheme, flat, shared,
-                                            b.get("negative_mask"), augment)
+        if model == "score_moving":  # bess.py:471-603 (ScoreMovingBessKGE is a full BessKGE)
+            pos, neg = score_moving_forward(cfg, ent, rel_table, b["head"], b["relation"],
+                                            b["tail"], b["negative"], scheme, flat, shared,
+                                            triple_based, b.get("negative_mask"))
+        else:
+            pos, neg = embedding_moving_forward(cfg, ent, rel_table, b["head"], b["relation"],
+                                                b["tail"], b["negative"], scheme, flat, shared,
+                                                b.get("negative_mask"), augment)
         step_losses = []
         for r in range(n):
             w = torch.tensor([1.0]) if weights is None or weights[bi] is None else weights[bi][r]

@@ -79,9 +79,53 @@ def main() -> None:
         if rank == 0:
             print(f"distributed parity ok: {fam} {scheme} flat={flat} n={n}", flush=True)
     if not same_device:
+        score_moving_training(rank, n)
         inference_parity(rank, n)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def score_moving_training(rank: int, n: int) -> None:
+    """Distributed ScoreMovingBessKGE training steps (score gradients back to the scoring ranks,
+    query gradients summed at the owner, candidate rows updated in place) vs the oracle."""
+    from besskge_b200.bess import ScoreMovingBessKGE
+    from besskge_b200.optim import AdamW
+    for fam, p, scheme, flat, shared, opt_kind in [("TransE", 1, "t", True, True, "sgd"),
+                                                   ("RotatE", 1, "h", False, False, "sgd"),
+                                                   ("DistMult", 2, "ht", True, True, "adamw")]:
+        d, n_rel, n_ent, p_part, Nn = 16, 5, 50 * n, 6, 5
+        sh = Sharding.create(n_ent, n, seed=3)
+        gen = torch.Generator().manual_seed(13)
+        ew = 2 if fam in ("RotatE", "ComplEx") else 1
+        ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen) * 0.5
+        rel = torch.randn(n_rel, d, generator=gen) * 0.5
+        S = n * p_part
+        Bn = (2 if scheme == "ht" else 1) if flat else S
+        lo = int(sh.shard_counts.min())
+        batches = [dict(
+            head=torch.randint(lo, (n, n, p_part), generator=gen, dtype=torch.int32),
+            tail=torch.randint(lo, (n, n, p_part), generator=gen, dtype=torch.int32),
+            relation=torch.randint(n_rel, (n, n, p_part), generator=gen, dtype=torch.int32),
+            negative=torch.randint(lo, (n, n, Bn, Nn), generator=gen, dtype=torch.int32))
+            for _ in range(2)]
+        lcfg = dict(kind="logsigmoid", margin=2.0, negative_adversarial_sampling=True)
+        ocfg = dict(kind="sgd", lr=0.1) if opt_kind == "sgd" else dict(kind="adamw", lr=0.01, eps=1e-4)
+        want = O.training_steps(H.score_cfg(fam, d, p), H.oracle_loss_cfg(lcfg), ocfg, ent, rel,
+                                batches, scheme, flat, shared, "mean", model="score_moving")
+        sf = H.make_score_fn(fam, shared, p, sh, n_rel, d, ent, rel)
+        model = ScoreMovingBessKGE(H.fake_sampler(scheme, flat, triple_based=False), sf,
+                                   loss_fn=H.make_loss(lcfg))
+        step = training_model(model, SGD(lr=0.1) if opt_kind == "sgd" else AdamW(lr=0.01, eps=1e-4))
+        for s, b in enumerate(batches):
+            res = step(**b)
+            torch.testing.assert_close(res["loss"].cpu(), want["loss"][s][rank:rank + 1],
+                                       rtol=2e-5, atol=1e-4)
+        torch.cuda.synchronize()
+        tol = dict(rtol=1e-5, atol=2e-6) if opt_kind == "sgd" else dict(rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(sf.entity_embedding.detach()[rank].cpu(), want["ent"][rank], **tol)
+        torch.testing.assert_close(sf.relation_embedding.detach().cpu(), want["rel"], **tol)
+        if rank == 0:
+            print(f"distributed ScoreMoving training ok: {fam} {scheme} flat={flat} n={n}", flush=True)
 
 
 def inference_parity(rank: int, n: int) -> None:

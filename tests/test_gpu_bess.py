@@ -300,3 +300,60 @@ def test_l2_tensor_core_path_matches_tile_path_and_oracle(fam, scheme):
         assert_close(got[flag][2], want["ent"], rtol=1e-5, atol=5e-6)
         assert_close(got[flag][3], want["rel"], rtol=1e-5, atol=5e-6)
     assert_close(got[True][0], got[False][0], rtol=1e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("fam,p,scheme,flat,shared,opt_kind,loss_kind", [
+    ("TransE", 1, "t", True, True, "sgd", "logsigmoid"),
+    ("DistMult", 2, "ht", True, True, "sgd", "margin_ranking"),
+    ("RotatE", 1, "h", False, False, "sgd", "logsigmoid"),
+    ("PairRE", 1, "t", False, False, "adamw", "logsigmoid"),
+    ("TransE", 2, "ht", False, False, "sgdm", "logsigmoid"),
+    ("TransE", 2, "ht", False, True, "sgd", "logsigmoid"),    # non-flat SHARED negatives
+    ("ComplEx", 2, "t", False, True, "sgd", "softmax_ce"),
+    ("BoxE", 1, "t", True, True, "sgd", "logsigmoid"),
+])
+def test_score_moving_training_vs_oracle(fam, p, scheme, flat, shared, opt_kind, loss_kind):
+    """ScoreMovingBessKGE is a full BessKGE in the reference (bess.py:471-603 + the loss of
+    bess.py:254-261): training through it — score gradients back to the scoring shards,
+    candidate rows updated where they live, query gradients summed over the scoring shards —
+    against the oracle (reference forward restated + autograd + torch.optim)."""
+    B, H = _imports()
+    from besskge_b200.bess import ScoreMovingBessKGE, training_model
+    from besskge_b200.optim import SGD, AdamW
+    from besskge_b200.sharding import Sharding
+    n, p_part, Nn, d, n_rel, n_ent = 2, 6, 5, 16, 4, 80
+    sh = Sharding.create(n_ent, n, seed=3)
+    gen = torch.Generator().manual_seed(17)
+    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
+    rw = {"ComplEx": 2 * d, "PairRE": 2 * d, "BoxE": 4 * d + 2}.get(fam, d)
+    ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen) * 0.5
+    rel = torch.randn(n_rel, rw, generator=gen) * 0.5
+    S = n * p_part
+    Bn = (2 if scheme == "ht" else 1) if flat else S
+    lo = int(sh.shard_counts.min())
+    lcfg = dict(kind=loss_kind, margin=2.0, negative_adversarial_sampling=True, n_entity=n_ent)
+    batches = [dict(
+        head=torch.randint(lo, (n, n, p_part), generator=gen, dtype=torch.int32),
+        tail=torch.randint(lo, (n, n, p_part), generator=gen, dtype=torch.int32),
+        relation=torch.randint(n_rel, (n, n, p_part), generator=gen, dtype=torch.int32),
+        negative=torch.randint(lo, (n, n, Bn, Nn), generator=gen, dtype=torch.int32))
+        for _ in range(3)]
+    ocfg = {"sgd": dict(kind="sgd", lr=0.1), "sgdm": dict(kind="sgd", lr=0.1, momentum=0.9),
+            "adamw": dict(kind="adamw", lr=0.01, eps=1e-4)}[opt_kind]
+    want = O.training_steps(H.score_cfg(fam, d, p), H.oracle_loss_cfg(lcfg), ocfg, ent, rel, batches,
+                            scheme, flat, shared, "mean", model="score_moving", triple_based=False)
+    sf = H.make_score_fn(fam, shared, p, sh, n_rel, d, ent, rel)
+    ns = H.fake_sampler(scheme, flat, triple_based=False)
+    model = ScoreMovingBessKGE(ns, sf, loss_fn=H.make_loss(lcfg))
+    opt = {"sgd": SGD(lr=0.1), "sgdm": SGD(lr=0.1, momentum=0.9),
+           "adamw": AdamW(lr=0.01, eps=1e-4)}[opt_kind]
+    step = training_model(model, opt)
+    adam = opt_kind == "adamw"
+    for s, b in enumerate(batches):
+        res = step(**b)
+        assert_close(res["loss"].cpu(), want["loss"][s], rtol=2e-5 if adam else 1e-5, atol=1e-4,
+                     msg=lambda m: f"step {s}: {m}")
+    torch.cuda.synchronize()
+    tol = dict(rtol=1e-4, atol=2e-5) if adam else dict(rtol=1e-5, atol=2e-6)
+    assert_close(sf.entity_embedding.detach().cpu(), want["ent"], **tol)
+    assert_close(sf.relation_embedding.detach().cpu(), want["rel"], **tol)
