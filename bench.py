@@ -64,6 +64,9 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the wikikg2 secondary workload and the shard_bs 65536 points")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--step-only", action="store_true",
+                    help="only the timed steps (no stand-alone kernel timings, secondary workload, "
+                         "parity check or CPU baseline): the command the ncu launch list is taken on")
     return ap.parse_args()
 
 
@@ -748,8 +751,16 @@ def main() -> None:
     res = train_leg(ctx, prob, args.optimizer, args.steps, args.warmup, sample_clocks=True)
     S, N = prob["shard_bs"], prob["negatives"]
 
+    if args.step_only:
+        args.no_parity = args.no_secondary = args.no_cpu_baseline = True
     line = None
-    if rank == 0:
+    if rank == 0 and args.step_only:
+        line = {"metric": "train_triples_per_sec", "value": res["value"], "unit": "triples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "config": workload_config(prob, world, args.optimizer),
+                "e2e": res["e2e"], "gpu_launches_per_step": int(res["launches_per_step"]),
+                "note": "--step-only run (profiling aid, not a bench line)"}
+    elif rank == 0:
         roof, gather, scatter, opt_dense = kernel_rooflines(res["sf"], prob, pk, args.optimizer)
         # the kernel's share of the step (to be compared with the ncu launch list in profiles/)
         roof["step_share"] = roof["launch_us"] * 1e-3 * (3 if roof["bound"] == "tensor" else 1) \

@@ -1629,7 +1629,8 @@ class ScoreMovingBessKGE(BessKGE):
                 for sel, d_c in cand_parts[shard]:
                     parts.append((sel, sel.numel(), sel.numel(), 1, d_c, 0, 0))
                 self._apply_parts(optimizer, ent[shard], shard, parts, key_bits, hyper, sort_ws, ws)
-            self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
+            EmbeddingMovingBessKGE._update_relation(self, optimizer, rel_table, d_rel_table, hyper,
+                                                    ws)
 
         out: Dict[str, Any] = {}
         if self.return_scores:
