@@ -15,7 +15,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libbesskge_b200.so"
 
 F32, F16, BF16 = 0, 1, 2
 F16X3 = 3  # operand format of the tensor-core path: scaled fp16 (hi, lo) pairs of fp32 values
-TRANSE, ROTATE, DISTMULT, COMPLEX, PAIRRE, BOXE, TRIPLERE = range(7)
+TRANSE, ROTATE, DISTMULT, COMPLEX, PAIRRE, BOXE, TRIPLERE, INTERHT, TRANS = range(9)
 MODE_TAILS, MODE_HEADS = 0, 1
 LOSS_LOGSIGMOID, LOSS_MARGIN_RANKING, LOSS_SOFTMAX_CE = 0, 1, 2
 OPT_SGD, OPT_SGDM, OPT_ADAMW = 0, 1, 2

@@ -745,7 +745,7 @@ class EmbeddingMovingBessKGE(BessKGE):
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         qv = ws.get("qv", (S, nvec, W), torch.float32)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
+        need_scale = K.needs_cand_scale(cfg)
         aux = ws.get("aux", (R, S, N), torch.float32) if need_aux else None
 
         n_out = bps * R
@@ -792,7 +792,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                                  torch.float32)[:rel_table.numel()].view(rel_table.shape)
             key_bits = max(1, int(ent.shape[1] - 1).bit_length())
             rel_bits = max(1, int(rel_table.shape[0] - 1).bit_length())
-        scale_buf = ws.get("cand_scale", (max(ps.n_cand for ps in passes),), torch.float32) \
+        scale_buf = ws.get("cand_scale", (2 * max(ps.n_cand for ps in passes),), torch.float32) \
             if need_scale else None
 
         use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX)
@@ -957,8 +957,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     elif ps.shared:
                         scale = None
                         if need_scale:
-                            scale = scale_buf[:ps.n_cand]
-                            K.cand_inv_norm(dt, cand, ps.n_cand, W, scale)
+                            scale = K.cand_scales(cfg, dt, cand, ps.n_cand, W, scale_buf)
                         K.shared_fwd(cfg, dt, ps.mode, qv, ps.n_query, cand, scale, ps.n_cand,
                                      neg, ps.qmap, N, ps.col0, None if aux is None else aux[li])
                     else:
@@ -1110,8 +1109,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                         if ps.shared:
                             scale = None
                             if need_scale:
-                                scale = scale_buf[:ps.n_cand]
-                                K.cand_inv_norm(dt, cand, ps.n_cand, W, scale)
+                                scale = K.cand_scales(cfg, dt, cand, ps.n_cand, W, scale_buf)
                             # dQ and dC are independent: the candidate-gradient kernel goes
                             # to the second stream (after score_triple's backward there)
                             cand_st = aux_st if (overlap and not need_scale) else main
@@ -1127,7 +1125,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                             if cand_st is not main:
                                 tb_joined = False  # more work on the second stream: join again
                             if need_scale:
-                                K.cand_norm_bwd(dt, cand, ps.n_cand, W, scale, d_cand)
+                                K.cand_scales_bwd(cfg, dt, cand, ps.n_cand, W, scale, d_cand)
                         else:
                             K.pertriple_bwd(cfg, dt, ps.mode, qv, ps.n_query, cand, ps.q_stride,
                                             ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
@@ -1398,7 +1396,7 @@ class ScoreMovingBessKGE(BessKGE):
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         qv = ws.get("qv", (n * S, nvec, W), torch.float32)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
+        need_scale = K.needs_cand_scale(cfg)
         # local mode: the score matrix of all replicas is written in place, column block r*X by
         # scoring shard r.  distributed: this rank scores all n*S queries against ITS candidates
         # ([n*S, X]) and the scores travel back to the shards that own the queries (AllToAll).
@@ -1498,8 +1496,8 @@ class ScoreMovingBessKGE(BessKGE):
                 cand = L.rows(table, idx=sel)
                 scale = None
                 if is_shared and need_scale:
-                    scale = ws.get("cand_scale", (n_c,), torch.float32)
-                    K.cand_inv_norm(dt, cand, n_c, W, scale)
+                    scale = K.cand_scales(cfg, dt, cand, n_c, W,
+                                          ws.get("cand_scale", (2 * n_c,), torch.float32))
                 if not backward:
                     if is_shared:
                         K.shared_fwd(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, qmap,
@@ -1519,7 +1517,7 @@ class ScoreMovingBessKGE(BessKGE):
                     K.shared_bwd_cand(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, d_sc,
                                       qmap, ld_sc, col0, aux, L.rows(d_c), cws, add=False)
                     if need_scale:
-                        K.cand_norm_bwd(dt, cand, n_c, W, scale, L.rows(d_c))
+                        K.cand_scales_bwd(cfg, dt, cand, n_c, W, scale, L.rows(d_c))
                     return sel, d_c
                 # one gradient row per (query position, candidate): both "ht" groups write disjoint
                 # rows of the same buffer, which is scattered once
@@ -1998,13 +1996,13 @@ class TopKQueryBessKGE(torch.nn.Module):
         use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX) and (
             negative is None or flat)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
+        need_scale = K.needs_cand_scale(cfg)
         Q = ws.get("tk_Q", (nS, W), tdt)
         rel_all = ws.get("tk_rel", (nS,), torch.int32)
         qv = ws.get("tk_qv", (nS, nvec, W), torch.float32)
         scores = ws.get("tk_scores", (nS, win), torch.float32)
         aux = ws.get("tk_aux", (nS, win), torch.float32) if need_aux else None
-        scale = ws.get("tk_scale", (win,), torch.float32) if need_scale else None
+        scale = ws.get("tk_scale", (2 * win,), torch.float32) if need_scale else None
         # running best lists: kb entries, or kb + margin when they are re-ranked exactly
         exact = bool(self.exact_rerank and negative is None and kb + self.exact_margin <= 32
                      and K.topk_exact_supported(cfg.family))
@@ -2087,8 +2085,7 @@ class TopKQueryBessKGE(torch.nn.Module):
                     else:
                         sc_ = None
                         if need_scale:
-                            sc_ = scale[:nc]
-                            K.cand_inv_norm(dt, cand, nc, W, sc_)
+                            sc_ = K.cand_scales(cfg, dt, cand, nc, W, scale)
                         K.shared_fwd(cfg, dt, mode, qv, nS, cand, sc_, nc, scores, L.IDENT, win, 0,
                                      aux)
                     if cand_mask is not None:
@@ -2215,13 +2212,13 @@ class AllScoresBESS(torch.nn.Module):
         nvec = K.call("bess_query_nvec", L.C.byref(cfg))
         use_tc = USE_TENSOR_CORES and cfg.family in (L.DISTMULT, L.COMPLEX)
         need_aux = cfg.family == L.BOXE and cfg.norm_p == 2
-        need_scale = cfg.family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize
+        need_scale = K.needs_cand_scale(cfg)
         max_w = max(min(self.device_window, w) for _, w in windows)
         Q = ws.get("as_Q", (nS, W), tdt)
         rel_all = ws.get("as_rel", (nS,), torch.int32)
         qv = ws.get("as_qv", (nS, nvec, W), torch.float32)
         aux = ws.get("as_aux", (nS, _pad8(max_w)), torch.float32) if need_aux else None
-        scale = ws.get("as_scale", (max_w,), torch.float32) if need_scale else None
+        scale = ws.get("as_scale", (2 * max_w,), torch.float32) if need_scale else None
         gemm_ws = None
         if use_tc:
             gemm_ws = ws.get("gemm_ws", (max(K.dot_gemm_workspace(nS, _pad8(max_w), W) // 4, 1),),
@@ -2282,8 +2279,7 @@ class AllScoresBESS(torch.nn.Module):
                             else:
                                 sc_ = None
                                 if need_scale:
-                                    sc_ = scale[:real]
-                                    K.cand_inv_norm(dt, cand, real, W, sc_)
+                                    sc_ = K.cand_scales(cfg, dt, cand, real, W, scale)
                                 K.shared_fwd(cfg, dt, mode, qv, nS, cand, sc_, real, dst, L.IDENT, ld,
                                              col, aux)
                         if real < nc:  # clamped tail of the last block: entity Es - 1 again
@@ -2306,8 +2302,8 @@ class AllScoresBESS(torch.nn.Module):
         one = ws.get("as_last", (nS, 8), torch.float32)
         sc_ = None
         if need_scale:
-            sc_ = ws.get("as_scale1", (1,), torch.float32)
-            K.cand_inv_norm(dt, cand, 1, table.shape[-1], sc_)
+            sc_ = K.cand_scales(cfg, dt, cand, 1, table.shape[-1],
+                                ws.get("as_scale1", (2,), torch.float32))
         K.shared_fwd(cfg, dt, mode, qv, nS, cand, sc_, 1, one, L.IDENT, 8, 0, aux)
         return one[:, 0:1]
 

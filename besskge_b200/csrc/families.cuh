@@ -13,6 +13,9 @@
 //   ComplEx   scoring.py:905-946   sum (h (x) r) * t, halves = re | im
 //   PairRE    scoring.py:540-593   -||h^ o r_h - t^ o r_t||_p, h^ = h/max(||h||,1e-12)
 //   BoxE      scoring.py:1250-1415 box distance, see boxe_* below
+//   InterHT   scoring.py:1418-1572 -||h^ (t~^ + o) + r - t^ (h~^ + o)||_p, entity rows [main | aux],
+//   TranS     scoring.py:1575-1750 -||h^ (t~^ + o + r_bar) - t^ (h~^ + o - r_hat) + r||_p,
+//                                  relation rows [r | r_bar | r_hat]; ^ = L2-normalised half
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -28,8 +31,9 @@
 namespace bess {
 
 enum Family { FAM_TRANSE = 0, FAM_ROTATE = 1, FAM_DISTMULT = 2, FAM_COMPLEX = 3, FAM_PAIRRE = 4, FAM_BOXE = 5,
-              FAM_TRIPLERE = 6 };
-enum PairOp { OP_DIST = 0, OP_DOT = 1, OP_PAIRRE = 2, OP_BOXE = 3 };
+              FAM_TRIPLERE = 6, FAM_INTERHT = 7, FAM_TRANS = 8 };
+// OP_PAIR2: two candidate elements per coordinate (InterHT / TranS), own kernels in pair2.cu
+enum PairOp { OP_DIST = 0, OP_DOT = 1, OP_PAIRRE = 2, OP_BOXE = 3, OP_PAIR2 = 4 };
 enum Mode { MODE_TAILS = 0, MODE_HEADS = 1 };  // which side the candidates replace
 
 struct FamCfg {
@@ -40,8 +44,10 @@ struct FamCfg {
   int apply_tanh;  // BoxE
   int per_dim;     // BoxE dist_func_per_dim
   float eps;       // BoxE
-  float rel_u;     // TripleRE v2 offset added to both relation projections (0 = v1)
+  float rel_u;     // TripleRE v2 offset added to both relation projections (0 = v1);
+                   // InterHT / TranS: the `offset` added to the auxiliary entity embeddings
 };
+BESS_HD bool is_pair2(int family) { return family == FAM_INTERHT || family == FAM_TRANS; }
 
 // PairRE and TripleRE share one code path: -|| h^ (r_h + u) - t^ (r_t + u) (+ r_m) ||_p with the
 // relation row laid out [r_h | r_t] (PairRE, scoring.py:465-593) or [r_h | r_m | r_t] (TripleRE,
@@ -55,12 +61,13 @@ BESS_HD ProjLayout proj_layout(const FamCfg& c) {
 }
 
 BESS_HD int ent_width(const FamCfg& c) {
-  return (c.family == FAM_ROTATE || c.family == FAM_COMPLEX || c.family == FAM_BOXE) ? 2 * c.d : c.d;
+  return (c.family == FAM_ROTATE || c.family == FAM_COMPLEX || c.family == FAM_BOXE ||
+          is_pair2(c.family)) ? 2 * c.d : c.d;
 }
 BESS_HD int rel_width(const FamCfg& c) {
   switch (c.family) {
     case FAM_COMPLEX: case FAM_PAIRRE: return 2 * c.d;
-    case FAM_TRIPLERE: return 3 * c.d;
+    case FAM_TRIPLERE: case FAM_TRANS: return 3 * c.d;
     case FAM_BOXE: return 4 * c.d + 2;
     default: return c.d;
   }
@@ -70,11 +77,13 @@ BESS_HD int pair_op(const FamCfg& c) {
     case FAM_TRANSE: case FAM_ROTATE: return OP_DIST;
     case FAM_DISTMULT: case FAM_COMPLEX: return OP_DOT;
     case FAM_PAIRRE: case FAM_TRIPLERE: return OP_PAIRRE;
+    case FAM_INTERHT: case FAM_TRANS: return OP_PAIR2;
     default: return OP_BOXE;
   }
 }
 // number of query-side vectors of width ent_width() the pair kernels consume
 BESS_HD int pair_nvec(const FamCfg& c) {
+  if (is_pair2(c.family)) return 2;
   return (c.family == FAM_PAIRRE || c.family == FAM_TRIPLERE) ? 2 : (c.family == FAM_BOXE ? 3 : 1);
 }
 
@@ -243,6 +252,36 @@ BESS_HD void boxe_rel_finalize(const FamCfg& c, const T* r, float* g) {
 }
 
 // ---------------------------------------------------------------------------
+// InterHT / TranS helpers: entity row [main d | aux d], each half L2-normalised
+// (torch.nn.functional.normalize: x / max(||x||, 1e-12)) when cfg.normalize.
+// ---------------------------------------------------------------------------
+struct Pair2Norms {
+  float nm, na;  // norms of the two halves (1 when not normalising)
+  float im, ia;  // 1 / max(norm, 1e-12)
+};
+template <typename Ctx, typename T>
+BESS_HD Pair2Norms pair2_norms(const FamCfg& c, const T* x) {
+  Pair2Norms n;
+  n.nm = n.na = n.im = n.ia = 1.f;
+  if (c.normalize) {
+    float a = 0.f, b = 0.f;
+    for (int k = Ctx::lane(); k < c.d; k += Ctx::lanes()) {
+      const float u = Ld<T>::f(x, k), v = Ld<T>::f(x, c.d + k);
+      a += u * u; b += v * v;
+    }
+    n.nm = sqrtf(Ctx::sum(a)); n.na = sqrtf(Ctx::sum(b));
+    n.im = 1.f / fmaxf(n.nm, 1e-12f); n.ia = 1.f / fmaxf(n.na, 1e-12f);
+  }
+  return n;
+}
+// gradient w.r.t. the raw half from the gradient w.r.t. the normalised half:
+// (g - x^ (x^ . g)) / ||x|| above the clamp, g / 1e-12 below it
+BESS_HD float unnorm_grad(int normalize, float g, float xhat, float proj, float norm, float inv) {
+  if (!normalize) return g;
+  return norm > 1e-12f ? (g - xhat * proj) * inv : g * inv;
+}
+
+// ---------------------------------------------------------------------------
 // score_triple forward: one row (h, r, t) -> score.
 // ---------------------------------------------------------------------------
 template <typename Ctx, typename T>
@@ -292,6 +331,18 @@ BESS_HD float triple_fwd(const FamCfg& c, const T* h, const T* r, const T* t) {
                   Ld<T>::f(t, k) * it * (Ld<T>::f(r, pl.ot + k) + pl.u);
         if (pl.om >= 0) e += Ld<T>::f(r, pl.om + k);
         acc += nacc(p, e);
+      }
+      return -nfin(p, Ctx::sum(acc));
+    }
+    case FAM_INTERHT: case FAM_TRANS: {
+      const Pair2Norms nh = pair2_norms<Ctx, T>(c, h), nt = pair2_norms<Ctx, T>(c, t);
+      const bool ts = c.family == FAM_TRANS;
+      const float o = c.rel_u;
+      for (int k = l0; k < d; k += ls) {
+        const float hm = Ld<T>::f(h, k) * nh.im, ha = Ld<T>::f(h, d + k) * nh.ia;
+        const float tm = Ld<T>::f(t, k) * nt.im, ta = Ld<T>::f(t, d + k) * nt.ia;
+        const float rb = ts ? Ld<T>::f(r, d + k) : 0.f, rh = ts ? Ld<T>::f(r, 2 * d + k) : 0.f;
+        acc += nacc(p, hm * (ta + o + rb) - tm * (ha + o - rh) + Ld<T>::f(r, k));
       }
       return -nfin(p, Ctx::sum(acc));
     }
@@ -420,6 +471,36 @@ BESS_HD void triple_bwd(const FamCfg& c, const T* h, const T* r, const T* t, flo
       }
       return;
     }
+    case FAM_INTERHT: case FAM_TRANS: {
+      const float nv = -score, o = c.rel_u;
+      const bool ts = c.family == FAM_TRANS;
+      const Pair2Norms nh = pair2_norms<Ctx, T>(c, h), nt = pair2_norms<Ctx, T>(c, t);
+      // pass 1: relation gradients and the projections x^ . dx^ of the four halves
+      float phm = 0.f, pha = 0.f, ptm = 0.f, pta = 0.f;
+      for (int k = l0; k < d; k += ls) {
+        const float hm = Ld<T>::f(h, k) * nh.im, ha = Ld<T>::f(h, d + k) * nh.ia;
+        const float tm = Ld<T>::f(t, k) * nt.im, ta = Ld<T>::f(t, d + k) * nt.ia;
+        const float rb = ts ? Ld<T>::f(r, d + k) : 0.f, rh = ts ? Ld<T>::f(r, 2 * d + k) : 0.f;
+        const float A = ta + o + rb, Bq = ha + o - rh;
+        const float de = -g * ndiff(p, hm * A - tm * Bq + Ld<T>::f(r, k), nv);
+        put(dr, k, de, add_r);
+        if (ts) { put(dr, d + k, de * hm, add_r); put(dr, 2 * d + k, de * tm, add_r); }
+        phm += hm * (de * A); pha += ha * (-de * tm); ptm += tm * (-de * Bq); pta += ta * (de * hm);
+      }
+      if (c.normalize) { phm = Ctx::sum(phm); pha = Ctx::sum(pha); ptm = Ctx::sum(ptm); pta = Ctx::sum(pta); }
+      for (int k = l0; k < d; k += ls) {
+        const float hm = Ld<T>::f(h, k) * nh.im, ha = Ld<T>::f(h, d + k) * nh.ia;
+        const float tm = Ld<T>::f(t, k) * nt.im, ta = Ld<T>::f(t, d + k) * nt.ia;
+        const float rb = ts ? Ld<T>::f(r, d + k) : 0.f, rh = ts ? Ld<T>::f(r, 2 * d + k) : 0.f;
+        const float A = ta + o + rb, Bq = ha + o - rh;
+        const float de = -g * ndiff(p, hm * A - tm * Bq + Ld<T>::f(r, k), nv);
+        put(dh, k, unnorm_grad(c.normalize, de * A, hm, phm, nh.nm, nh.im), add_h);
+        put(dh, d + k, unnorm_grad(c.normalize, -de * tm, ha, pha, nh.na, nh.ia), add_h);
+        put(dt, k, unnorm_grad(c.normalize, -de * Bq, tm, ptm, nt.nm, nt.im), add_t);
+        put(dt, d + k, unnorm_grad(c.normalize, de * hm, ta, pta, nt.na, nt.ia), add_t);
+      }
+      return;
+    }
     default: {  // FAM_BOXE
       for (int b = 0; b < 2; ++b) {
         const BoxNorm n = boxe_norm<Ctx, T>(c, r, b);
@@ -520,6 +601,27 @@ BESS_HD void prologue_fwd(const FamCfg& c, int mode, const T* x, const T* r, flo
       }
       return;
     }
+    case FAM_INTERHT: case FAM_TRANS: {
+      // residual e_k = qv0[k] * c^m_k + qv0[d + k] * c^a_k + qv1[k] over the candidate's
+      // normalised halves (scoring.py:1530-1572, 1700-1750):
+      //   tails (x = head):  e = -(h~ + o - r_hat) c^m + h c^a + h (o + r_bar) + r
+      //   heads (x = tail):  e =  (t~ + o + r_bar) c^m - t c^a + r - t (o - r_hat)
+      const Pair2Norms nx = pair2_norms<Ctx, T>(c, x);
+      const bool ts = c.family == FAM_TRANS;
+      const float o = c.rel_u;
+      for (int k = l0; k < d; k += ls) {
+        const float xm = Ld<T>::f(x, k) * nx.im, xa = Ld<T>::f(x, d + k) * nx.ia;
+        const float rb = ts ? Ld<T>::f(r, d + k) : 0.f, rh = ts ? Ld<T>::f(r, 2 * d + k) : 0.f;
+        const float rr = Ld<T>::f(r, k);
+        if (mode == MODE_TAILS) {
+          qv[k] = -(xa + o - rh); qv[d + k] = xm; qv[W + k] = xm * (o + rb) + rr;
+        } else {
+          qv[k] = xa + o + rb; qv[d + k] = -xm; qv[W + k] = rr - xm * (o - rh);
+        }
+        qv[W + d + k] = 0.f;
+      }
+      return;
+    }
     default: {  // FAM_BOXE
       for (int b = 0; b < 2; ++b) {
         const BoxNorm n = boxe_norm<Ctx, T>(c, r, b);
@@ -608,6 +710,38 @@ BESS_HD void prologue_bwd(const FamCfg& c, int mode, const T* x, const T* r, con
         float dxh = dqv[k] * (Ld<T>::f(r, own + k) + pl.u);
         if (c.normalize) dxh = nx > 1e-12f ? (dxh - xh * proj) * inv : dxh * inv;
         put(dx, k, dxh, add_x);
+      }
+      return;
+    }
+    case FAM_INTERHT: case FAM_TRANS: {
+      const Pair2Norms nx = pair2_norms<Ctx, T>(c, x);
+      const bool ts = c.family == FAM_TRANS;
+      const float o = c.rel_u;
+      float pm = 0.f, pa = 0.f;
+      for (int k = l0; k < d; k += ls) {
+        const float xm = Ld<T>::f(x, k) * nx.im, xa = Ld<T>::f(x, d + k) * nx.ia;
+        const float rb = ts ? Ld<T>::f(r, d + k) : 0.f, rh = ts ? Ld<T>::f(r, 2 * d + k) : 0.f;
+        const float g0 = dqv[k], g1 = dqv[d + k], gz = dqv[W + k];
+        float dxm, dxa;
+        if (mode == MODE_TAILS) {
+          dxa = -g0; dxm = g1 + gz * (o + rb);
+          if (ts) { put(dr, 2 * d + k, g0, add_r); put(dr, d + k, gz * xm, add_r); }
+        } else {
+          dxa = g0; dxm = -g1 - gz * (o - rh);
+          if (ts) { put(dr, d + k, g0, add_r); put(dr, 2 * d + k, gz * xm, add_r); }
+        }
+        put(dr, k, gz, add_r);
+        pm += xm * dxm; pa += xa * dxa;
+      }
+      if (c.normalize) { pm = Ctx::sum(pm); pa = Ctx::sum(pa); }
+      for (int k = l0; k < d; k += ls) {
+        const float xm = Ld<T>::f(x, k) * nx.im, xa = Ld<T>::f(x, d + k) * nx.ia;
+        const float rb = ts ? Ld<T>::f(r, d + k) : 0.f, rh = ts ? Ld<T>::f(r, 2 * d + k) : 0.f;
+        const float g0 = dqv[k], g1 = dqv[d + k], gz = dqv[W + k];
+        const float dxa = mode == MODE_TAILS ? -g0 : g0;
+        const float dxm = mode == MODE_TAILS ? g1 + gz * (o + rb) : -g1 - gz * (o - rh);
+        put(dx, k, unnorm_grad(c.normalize, dxm, xm, pm, nx.nm, nx.im), add_x);
+        put(dx, d + k, unnorm_grad(c.normalize, dxa, xa, pa, nx.na, nx.ia), add_x);
       }
       return;
     }

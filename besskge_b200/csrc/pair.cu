@@ -960,11 +960,38 @@ static PairArgs make_pair_args(const FamCfg& f, int dtype, int rot, const float*
   return a;
 }
 
+// InterHT / TranS (two candidate elements per coordinate): kernels in pair2.cu
+namespace bess {
+int pair2_shared_fwd(const bess_score_cfg_t*, int, const float*, int, bess_rows_t, const float*, int, float*,
+                     bess_rowmap_t, int64_t, int, cudaStream_t);
+int pair2_shared_bwd_query(const bess_score_cfg_t*, int, const float*, int, bess_rows_t, const float*, int,
+                           const float*, const float*, bess_rowmap_t, int64_t, int, float*, cudaStream_t);
+int64_t pair2_bwd_cand_workspace(const bess_score_cfg_t*, int, int);
+int pair2_shared_bwd_cand(const bess_score_cfg_t*, int, const float*, int, bess_rows_t, const float*, int,
+                          const float*, const float*, bess_rowmap_t, int64_t, int, bess_rows_t, int, void*,
+                          cudaStream_t);
+int pair2_pertriple_fwd(const bess_score_cfg_t*, int, const float*, int, bess_rows_t, int64_t, int, float*,
+                        bess_rowmap_t, int64_t, int, cudaStream_t);
+int pair2_pertriple_bwd(const bess_score_cfg_t*, int, const float*, int, bess_rows_t, int64_t, int,
+                        const float*, const float*, bess_rowmap_t, int64_t, int, float*, bess_rows_t,
+                        cudaStream_t);
+}  // namespace bess
+static int check_pair2(const bess_score_cfg_t* cfg) {
+  BESS_CHECK_ARG(cfg->d > 0 && (cfg->norm_p == 1 || cfg->norm_p == 2),
+                 "InterHT / TranS need embedding_size > 0 and scoring_norm 1 or 2");
+  return BESS_OK;
+}
+
 extern "C" int bess_score_shared_fwd(const bess_score_cfg_t* cfg, int dtype, int mode,
                                      const float* qv, int n_query, bess_rows_t cand,
                                      const float* cand_scale, int n_cand, float* out,
                                      bess_rowmap_t score_map, int64_t ld_out, int col0, float* aux,
                                      void* stream) {
+  if (is_pair2(cfg->family)) {
+    if (int e = check_pair2(cfg)) return e;
+    return pair2_shared_fwd(cfg, dtype, qv, n_query, cand, cand_scale, n_cand, out, score_map, ld_out, col0,
+                            (cudaStream_t)stream);
+  }
   FamCfg f; int op, rot;
   if (int e = check_pair(cfg, mode, f, op, rot)) return e;
   if (n_query == 0 || n_cand == 0) return BESS_OK;
@@ -997,6 +1024,11 @@ extern "C" int bess_score_shared_bwd_query(const bess_score_cfg_t* cfg, int dtyp
                                            const float* d_score, bess_rowmap_t score_map,
                                            int64_t ld, int col0, const float* aux, float* d_qv,
                                            void* stream) {
+  if (is_pair2(cfg->family)) {
+    if (int e = check_pair2(cfg)) return e;
+    return pair2_shared_bwd_query(cfg, dtype, qv, n_query, cand, cand_scale, n_cand, score, d_score,
+                                  score_map, ld, col0, d_qv, (cudaStream_t)stream);
+  }
   FamCfg f; int op, rot;
   if (int e = check_pair(cfg, mode, f, op, rot)) return e;
   if (n_query == 0) return BESS_OK;
@@ -1032,6 +1064,7 @@ static int choose_split(int n_query, int n_cand, int W) {
 
 extern "C" int64_t bess_shared_bwd_cand_workspace(const bess_score_cfg_t* cfg, int n_query,
                                                   int n_cand) {
+  if (is_pair2(cfg->family)) return pair2_bwd_cand_workspace(cfg, n_query, n_cand);
   const FamCfg f = to_cfg(cfg);
   const int W = ent_width(f);
   return (int64_t)choose_split(n_query, n_cand, W) * n_cand * W * sizeof(float);
@@ -1044,6 +1077,11 @@ extern "C" int bess_score_shared_bwd_cand(const bess_score_cfg_t* cfg, int dtype
                                           int64_t ld, int col0, const float* aux,
                                           bess_rows_t d_cand, int add_cand, void* workspace,
                                           void* stream) {
+  if (is_pair2(cfg->family)) {
+    if (int e = check_pair2(cfg)) return e;
+    return pair2_shared_bwd_cand(cfg, dtype, qv, n_query, cand, cand_scale, n_cand, score, d_score, score_map,
+                                 ld, col0, d_cand, add_cand, workspace, (cudaStream_t)stream);
+  }
   FamCfg f; int op, rot;
   if (int e = check_pair(cfg, mode, f, op, rot)) return e;
   if (n_cand == 0) return BESS_OK;
@@ -1084,6 +1122,11 @@ extern "C" int bess_score_pertriple_fwd(const bess_score_cfg_t* cfg, int dtype, 
                                         int64_t cand_q_stride, int n_per, float* out,
                                         bess_rowmap_t score_map, int64_t ld_out, int col0,
                                         float* aux, void* stream) {
+  if (is_pair2(cfg->family)) {
+    if (int e = check_pair2(cfg)) return e;
+    return pair2_pertriple_fwd(cfg, dtype, qv, n_query, cand, cand_q_stride, n_per, out, score_map, ld_out,
+                               col0, (cudaStream_t)stream);
+  }
   FamCfg f; int op, rot;
   if (int e = check_pair(cfg, mode, f, op, rot)) return e;
   if (n_query == 0 || n_per == 0) return BESS_OK;
@@ -1118,6 +1161,11 @@ extern "C" int bess_score_pertriple_bwd(const bess_score_cfg_t* cfg, int dtype, 
                                         const float* d_score, bess_rowmap_t score_map, int64_t ld,
                                         int col0, const float* aux, float* d_qv,
                                         bess_rows_t d_cand, void* stream) {
+  if (is_pair2(cfg->family)) {
+    if (int e = check_pair2(cfg)) return e;
+    return pair2_pertriple_bwd(cfg, dtype, qv, n_query, cand, cand_q_stride, n_per, score, d_score, score_map,
+                               ld, col0, d_qv, d_cand, (cudaStream_t)stream);
+  }
   FamCfg f; int op, rot;
   if (int e = check_pair(cfg, mode, f, op, rot)) return e;
   if (n_query == 0) return BESS_OK;

@@ -269,10 +269,11 @@ static inline int elem_size(int dtype) { return dtype == BESS_F32 ? 4 : 2; }
 
 static int check_cfg(const bess_score_cfg_t* cfg) {
   BESS_CHECK_ARG(cfg != nullptr, "null score config");
-  BESS_CHECK_ARG(cfg->family >= 0 && cfg->family <= BESS_TRIPLERE, "unknown family %d", cfg->family);
+  BESS_CHECK_ARG(cfg->family >= 0 && cfg->family <= BESS_TRANS, "unknown family %d", cfg->family);
   BESS_CHECK_ARG(cfg->d > 0, "embedding_size must be positive");
   if (cfg->family == BESS_TRANSE || cfg->family == BESS_ROTATE || cfg->family == BESS_PAIRRE ||
-      cfg->family == BESS_BOXE || cfg->family == BESS_TRIPLERE)
+      cfg->family == BESS_BOXE || cfg->family == BESS_TRIPLERE || cfg->family == BESS_INTERHT ||
+      cfg->family == BESS_TRANS)
     BESS_CHECK_ARG(cfg->norm_p == 1 || cfg->norm_p == 2, "scoring_norm %d not supported (1 or 2)",
                    cfg->norm_p);
   return BESS_OK;

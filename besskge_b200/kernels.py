@@ -127,6 +127,45 @@ def cand_norm_bwd(dt: int, cand: Rows, n: int, width: int, inv_norm: torch.Tenso
     call("bess_cand_norm_bwd", dt, cand, n, width, inv_norm.data_ptr(), d_cand, _st(inv_norm))
 
 
+# families whose candidates are L2-normalised before scoring: PairRE / TripleRE normalise the
+# whole row (one inverse norm per candidate), InterHT / TranS the two halves [main | aux]
+# separately (two inverse norms per candidate, stored [main norms | aux norms])
+def needs_cand_scale(cfg: ScoreCfg) -> bool:
+    return bool(cfg.normalize) and cfg.family in (L.PAIRRE, L.TRIPLERE, L.INTERHT, L.TRANS)
+
+
+def cand_scale_len(cfg: ScoreCfg, n: int) -> int:
+    return 2 * n if cfg.family in (L.INTERHT, L.TRANS) else n
+
+
+def _shift_rows(r: Rows, elems: int, elem_bytes: int) -> Rows:
+    return Rows(r.base + elems * elem_bytes, r.idx, r.map, r.pitch)
+
+
+def cand_scales(cfg: ScoreCfg, dt: int, cand: Rows, n: int, width: int,
+                out: torch.Tensor) -> torch.Tensor:
+    """inverse norms of the n candidate rows -> out[:cand_scale_len(cfg, n)] (returned)."""
+    out = out[:cand_scale_len(cfg, n)]
+    if cfg.family in (L.INTERHT, L.TRANS):
+        d, es = width // 2, (4 if dt == L.F32 else 2)
+        cand_inv_norm(dt, cand, n, d, out[:n])
+        cand_inv_norm(dt, _shift_rows(cand, d, es), n, d, out[n:])
+    else:
+        cand_inv_norm(dt, cand, n, width, out)
+    return out
+
+
+def cand_scales_bwd(cfg: ScoreCfg, dt: int, cand: Rows, n: int, width: int, scale: torch.Tensor,
+                    d_cand: Rows) -> None:
+    """chain rule of the candidate normalisation, in place on the fp32 gradient rows."""
+    if cfg.family in (L.INTERHT, L.TRANS):
+        d, es = width // 2, (4 if dt == L.F32 else 2)
+        cand_norm_bwd(dt, cand, n, d, scale[:n], d_cand)
+        cand_norm_bwd(dt, _shift_rows(cand, d, es), n, d, scale[n:], _shift_rows(d_cand, d, 4))
+    else:
+        cand_norm_bwd(dt, cand, n, width, scale, d_cand)
+
+
 def shared_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
                cand_scale: Optional[torch.Tensor], n_cand: int, out: torch.Tensor,
                score_map: RowMap, ld: int, col0: int, aux: Optional[torch.Tensor]) -> None:

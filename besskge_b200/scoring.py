@@ -112,9 +112,9 @@ class BaseScoreFunction(torch.nn.Module, ABC):
             out = torch.empty(nq, nc, dtype=torch.float32, device=x.device)
             aux = torch.empty_like(out) if need_aux else None
             scale = None
-            if self._family in (L.PAIRRE, L.TRIPLERE) and cfg.normalize:
-                scale = torch.empty(nc, dtype=torch.float32, device=x.device)
-                K.cand_inv_norm(dt, L.rows(flat), nc, W, scale)
+            if K.needs_cand_scale(cfg):
+                scale = K.cand_scales(cfg, dt, L.rows(flat), nc, W,
+                                      torch.empty(2 * nc, dtype=torch.float32, device=x.device))
             K.shared_fwd(cfg, dt, mode, qv, nq, L.rows(flat), scale, nc, out, L.IDENT, nc, 0, aux)
         else:
             if c.shape[0] != nq:
@@ -323,6 +323,64 @@ class TripleRE(DistanceBasedScoreFunction):
         # the reference adds rel_u only when u > 0 (scoring.py:692-694); u <= 0 means "no offset"
         self.u = float(u) if self.use_v2 else 0.0
         self.register_buffer("rel_u", torch.tensor([u], dtype=self.entity_embedding.dtype))
+
+
+class _AuxEntityScoreFunction(DistanceBasedScoreFunction):
+    """Shared constructor of InterHT and TranS: entity rows [main | auxiliary] of
+    2 * embedding_size elements, each half L2-normalised before use (`normalize_entities`), the
+    auxiliary halves shifted by `offset`.  Negative scoring runs on csrc/pair2.cu."""
+
+    _relation_parts = 1
+
+    def __init__(
+        self,
+        negative_sample_sharing: bool,
+        scoring_norm: int,
+        sharding: Sharding,
+        n_relation_type: int,
+        embedding_size: int,
+        entity_initializer: Initializer = [init_KGE_uniform],
+        relation_initializer: Initializer = [init_KGE_uniform],
+        normalize_entities: bool = True,
+        offset: float = 1.0,
+        inverse_relations: bool = False,
+    ) -> None:
+        super().__init__(negative_sample_sharing, scoring_norm)
+        self.normalize = normalize_entities
+        if isinstance(entity_initializer, list):
+            entity_initializer = 2 * entity_initializer
+        if isinstance(relation_initializer, list):
+            relation_initializer = self._relation_parts * relation_initializer
+        self._build_tables(sharding, n_relation_type, inverse_relations, entity_initializer,
+                           relation_initializer, [embedding_size, embedding_size],
+                           self._relation_parts * [embedding_size])
+        name = type(self).__name__
+        assert (
+            self.entity_embedding.shape[-1] == 2 * embedding_size
+            and self.relation_embedding.shape[-1] == self._relation_parts * embedding_size
+        ), (
+            f"{name} requires `2*embedding_size` embedding parameters for each entity and "
+            f"`{self._relation_parts}*embedding_size` embedding parameters for each relation"
+        )
+        self.embedding_size = embedding_size
+        self.u = float(offset)  # travels to the kernels in the cfg's `rel_u` slot
+        self.register_buffer("offset", torch.tensor([offset], dtype=self.entity_embedding.dtype))
+
+
+class InterHT(_AuxEntityScoreFunction):
+    """-||h^ o (t~^ + offset) + r - t^ o (h~^ + offset)||_p (scoring.py:1418-1572): entity rows
+    [e | e~], relation rows [r]."""
+
+    _family = L.INTERHT
+    _relation_parts = 1
+
+
+class TranS(_AuxEntityScoreFunction):
+    """-||h^ o (t~^ + offset + r_bar) - t^ o (h~^ + offset - r_hat) + r||_p
+    (scoring.py:1575-1750): entity rows [e | e~], relation rows [r | r_bar | r_hat]."""
+
+    _family = L.TRANS
+    _relation_parts = 3
 
 
 class DistMult(MatrixDecompositionScoreFunction):

@@ -37,7 +37,13 @@ typedef enum { BESS_F32 = 0, BESS_F16 = 1, BESS_BF16 = 2, BESS_F16X3 = 3 } bess_
 typedef enum {
   BESS_TRANSE = 0, BESS_ROTATE = 1, BESS_DISTMULT = 2,
   BESS_COMPLEX = 3, BESS_PAIRRE = 4, BESS_BOXE = 5,
-  BESS_TRIPLERE = 6 /* scoring.py:596-743: PairRE kernels + a relation offset row */
+  BESS_TRIPLERE = 6, /* scoring.py:596-743: PairRE kernels + a relation offset row */
+  /* scoring.py:1418-1572 / 1575-1750: entity rows [main | aux] of 2 d elements,
+   * residual h^ (t~^ + o (+ r_bar)) - t^ (h~^ + o (- r_hat)) + r; `rel_u` carries the offset o;
+   * relation rows [r] (InterHT) / [r | r_bar | r_hat] (TranS); own kernels in csrc/pair2.cu.
+   * For shared negatives `cand_scale` holds 2 * n_cand inverse norms: main halves, then aux. */
+  BESS_INTERHT = 7,
+  BESS_TRANS = 8
 } bess_family;
 
 /* which entity the candidates replace: score_tails / score_heads */

@@ -182,6 +182,15 @@ def score_triple(cfg: Dict[str, Any], h: torch.Tensor, rel_table: torch.Tensor, 
         if cfg.get("normalize", True):
             h, t = _normalize(h), _normalize(t)
         return -_norm(h * rh - t * rt + rm, p)
+    if fam in ("InterHT", "TranS"):  # scoring.py:1495-1527, 1665-1697
+        hm, ha, tm, ta = h[..., :d], h[..., d:], t[..., :d], t[..., d:]
+        if cfg.get("normalize", True):
+            hm, ha, tm, ta = _normalize(hm), _normalize(ha), _normalize(tm), _normalize(ta)
+        o = cfg.get("rel_u", 1.0)  # the constructors' `offset`
+        if fam == "InterHT":
+            return -_norm(hm * (ta + o) + re - tm * (ha + o), p)
+        rr, rb, rh = re[..., :d], re[..., d:2 * d], re[..., 2 * d:]
+        return -_norm(hm * (ta + o + rb) - tm * (ha + o - rh) + rr, p)
     if fam == "BoxE":  # scoring.py:1342-1363
         center, width, size = torch.split(re, 2 * d, dim=-1)
         bumped = h.view(-1, 2, d) + t.view(-1, 2, d)[:, [1, 0]]
@@ -230,6 +239,21 @@ def score_candidates(cfg: Dict[str, Any], mode: str, fixed: torch.Tensor, rel_ta
         if mode == "t":
             return -_norm(cand * rt.unsqueeze(1) - (fixed * rh + rm).unsqueeze(1), p)
         return -_norm(cand * rh.unsqueeze(1) - (fixed * rt - rm).unsqueeze(1), p)
+    if fam in ("InterHT", "TranS"):  # scoring.py:1530-1572, 1700-1750
+        fm, fa, cm, ca = fixed[..., :d], fixed[..., d:], cand[..., :d], cand[..., d:]
+        if cfg.get("normalize", True):
+            fm, fa, cm, ca = _normalize(fm), _normalize(fa), _normalize(cm), _normalize(ca)
+        if shared:
+            cm, ca = cm.reshape(1, -1, d), ca.reshape(1, -1, d)
+        o = cfg.get("rel_u", 1.0)
+        if fam == "InterHT":
+            rr, rb, rh = re, 0.0, 0.0
+        else:
+            rr, rb, rh = re[..., :d], re[..., d:2 * d].unsqueeze(1), re[..., 2 * d:].unsqueeze(1)
+        fm, fa, rr = fm.unsqueeze(1), fa.unsqueeze(1), rr.unsqueeze(1)
+        if mode == "t":  # fixed = head, candidates = tails
+            return -_norm(fm * (ca + o + rb) - cm * (fa + o - rh) + rr, p)
+        return -_norm(cm * (fa + o + rb) - fm * (ca + o - rh) + rr, p)
     if fam == "BoxE":  # scoring.py:1366-1415
         center, width, size = torch.split(re, 2 * d, dim=-1)
         if shared:

@@ -154,6 +154,8 @@ FAMILIES = {
     "PairRE": dict(cls="PairRE", norm=True, ew=1, rw=lambda d: 2 * d),
     "BoxE": dict(cls="BoxE", norm=True, ew=2, rw=lambda d: 4 * d + 2),
     "TripleRE": dict(cls="TripleRE", norm=True, ew=1, rw=lambda d: 3 * d),
+    "InterHT": dict(cls="InterHT", norm=True, ew=2, rw=lambda d: d),
+    "TranS": dict(cls="TranS", norm=True, ew=2, rw=lambda d: 3 * d),
 }
 
 
@@ -190,6 +192,10 @@ def golden_scores(ref, only=None) -> None:
             variants += [dict(p=1, u=0.5), dict(p=2, normalize_entities=False, u=1.25)]
         if fam == "BoxE":
             variants += [dict(p=2, apply_tanh=False), dict(p=1, dist_func_per_dim=False)]
+        if fam == "InterHT":
+            variants.append(dict(p=1, normalize_entities=False, offset=0.5))
+        if fam == "TranS":
+            variants.append(dict(p=2, normalize_entities=False, offset=0.25))
         ent, rel = tables(fam, sh, n_rel, d, gen)
         W = ent.shape[-1]
         h = torch.randn(b, W, generator=gen)
@@ -276,7 +282,7 @@ def golden_bess(ref, only=None) -> None:
     sh = ref.sharding.Sharding.create(n_entity, n_shard, seed=SEED)
     combos = [
         ("TransE", 1), ("TransE", 2), ("RotatE", 1), ("DistMult", 0), ("ComplEx", 0),
-        ("PairRE", 1), ("BoxE", 1), ("BoxE", 2), ("TripleRE", 1),
+        ("PairRE", 1), ("BoxE", 1), ("BoxE", 2), ("TripleRE", 1), ("InterHT", 1), ("TranS", 2),
     ]
     if only is not None:
         combos = [c for c in combos if c[0] in only]
@@ -350,6 +356,12 @@ def golden_train(ref, only=None) -> None:
         dict(fam="TripleRE", p=1, n_shard=4, scheme="t", flat=True, n_neg=6, shard_bs=16,
              loss=("logsigmoid", dict(margin=3.0, negative_adversarial_sampling=True)),
              opt=dict(kind="sgd", lr=0.05), kw=dict(u=0.5)),
+        dict(fam="InterHT", p=1, n_shard=4, scheme="t", flat=True, n_neg=6, shard_bs=16,
+             loss=("logsigmoid", dict(margin=3.0, negative_adversarial_sampling=True)),
+             opt=dict(kind="sgd", lr=0.05)),
+        dict(fam="TranS", p=2, n_shard=2, scheme="ht", flat=False, n_neg=3, shard_bs=16,
+             loss=("margin_ranking", dict(margin=2.0, negative_adversarial_sampling=True)),
+             opt=dict(kind="sgd", lr=0.05), kw=dict(offset=0.5)),
     ]
     for si, sp in enumerate(specs):
         if only is not None and sp["fam"] not in only:
@@ -553,11 +565,22 @@ GENERATORS = dict(host=golden_host, dataset=golden_dataset, scores=golden_scores
 
 
 def main() -> None:
-    """`python tests/golden/make_golden.py [name ...]` — all generators, or the named ones."""
+    """`python tests/golden/make_golden.py [name ...] [--only Family,...]` — all generators, or
+    the named ones; --only restricts scores / bess / train to the given score-function families
+    (how fixtures of a newly added family are generated without touching the others)."""
     ref = ref_loader.load_reference()
-    for name in (sys.argv[1:] or list(GENERATORS)):
+    args = sys.argv[1:]
+    only = None
+    if "--only" in args:
+        i = args.index("--only")
+        only = args[i + 1].split(",")
+        args = args[:i] + args[i + 2:]
+    for name in (args or list(GENERATORS)):
         torch.manual_seed(SEED)
-        GENERATORS[name](ref)
+        if only is not None and name in ("scores", "bess", "train"):
+            GENERATORS[name](ref, only=only)
+        else:
+            GENERATORS[name](ref)
 
 
 if __name__ == "__main__":

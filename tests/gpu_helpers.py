@@ -16,7 +16,7 @@ def T(a):
 def score_cfg(fam, d, p=2, **kw):
     return dict(family=fam, d=d, norm_p=p or 2, normalize=kw.get("normalize", True),
                 apply_tanh=kw.get("apply_tanh", True), per_dim=kw.get("per_dim", True), eps=1e-6,
-                rel_u=kw.get("u", 0.0))
+                rel_u=kw.get("u", kw.get("offset", 1.0 if fam in ("InterHT", "TranS") else 0.0)))
 
 
 def make_score_fn(fam, sharing, p, sh, n_rel, d, ent, rel, dtype=torch.float32, **kw):

@@ -76,6 +76,14 @@ void hc_candidates_fwd(int family, int p, int d, int normalize, int apply_tanh, 
     prologue_fwd<HostCtx, float>(c, mode, fixed + (int64_t)i * W, rel_table + (int64_t)r[i] * Wr, qv.data());
     for (int j = 0; j < nc; ++j) {
       const float* cr = shared ? cand + (int64_t)j * W : cand + ((int64_t)i * nc + j) * W;
+      if (op == OP_PAIR2) {  // host restatement of csrc/pair2.cu
+        const Pair2Norms nn = pair2_norms<HostCtx, float>(c, cr);
+        float acc = 0.f;
+        for (int k = 0; k < d; ++k)
+          acc += nacc(p, qv[k] * cr[k] * nn.im + qv[d + k] * cr[d + k] * nn.ia + qv[W + k]);
+        out[(int64_t)i * nc + j] = -nfin(p, acc);
+        continue;
+      }
       float scale = 1.f;
       if (op == OP_PAIRRE && normalize) {
         float a = 0.f; for (int k = 0; k < W; ++k) a += cr[k] * cr[k];
@@ -105,6 +113,30 @@ void hc_candidates_bwd(int family, int p, int d, int normalize, int apply_tanh, 
     for (int j = 0; j < nc; ++j) {
       const float* cr = shared ? cand + (int64_t)j * W : cand + ((int64_t)i * nc + j) * W;
       float* dc = shared ? d_cand + (int64_t)j * W : d_cand + ((int64_t)i * nc + j) * W;
+      if (op == OP_PAIR2) {
+        const Pair2Norms nn = pair2_norms<HostCtx, float>(c, cr);
+        float acc = 0.f;
+        for (int k = 0; k < d; ++k)
+          acc += nacc(p, qv[k] * cr[k] * nn.im + qv[d + k] * cr[d + k] * nn.ia + qv[W + k]);
+        const float sc2 = -nfin(p, acc), gg2 = g[(int64_t)i * nc + j];
+        const float cf = p == 1 ? -gg2 : (sc2 != 0.f ? gg2 / sc2 : 0.f);
+        float pm = 0.f, pa = 0.f;
+        for (int k = 0; k < d; ++k) {
+          const float cm = cr[k] * nn.im, ca = cr[d + k] * nn.ia;
+          const float e = qv[k] * cm + qv[d + k] * ca + qv[W + k];
+          const float de = p == 1 ? cf * fsign(e) : cf * e;
+          dqv[k] += de * cm; dqv[d + k] += de * ca; dqv[W + k] += de;
+          pm += cm * de * qv[k]; pa += ca * de * qv[d + k];
+        }
+        for (int k = 0; k < d; ++k) {
+          const float cm = cr[k] * nn.im, ca = cr[d + k] * nn.ia;
+          const float e = qv[k] * cm + qv[d + k] * ca + qv[W + k];
+          const float de = p == 1 ? cf * fsign(e) : cf * e;
+          dc[k] += unnorm_grad(c.normalize, de * qv[k], cm, pm, nn.nm, nn.im);
+          dc[d + k] += unnorm_grad(c.normalize, de * qv[d + k], ca, pa, nn.na, nn.ia);
+        }
+        continue;
+      }
       float scale = 1.f, nrm = 1.f;
       if (op == OP_PAIRRE && normalize) {
         float a = 0.f; for (int k = 0; k < W; ++k) a += cr[k] * cr[k];

@@ -18,11 +18,12 @@ from oracle import besskge_oracle as O
 
 ROOT = Path(__file__).resolve().parents[1]
 FAM_ID = {"TransE": 0, "RotatE": 1, "DistMult": 2, "ComplEx": 3, "PairRE": 4, "BoxE": 5,
-          "TripleRE": 6}
-EW = {"TransE": 1, "RotatE": 2, "DistMult": 1, "ComplEx": 2, "PairRE": 1, "BoxE": 2, "TripleRE": 1}
+          "TripleRE": 6, "InterHT": 7, "TranS": 8}
+EW = {"TransE": 1, "RotatE": 2, "DistMult": 1, "ComplEx": 2, "PairRE": 1, "BoxE": 2, "TripleRE": 1,
+      "InterHT": 2, "TranS": 2}
 RW = {"TransE": lambda d: d, "RotatE": lambda d: d, "DistMult": lambda d: d,
       "ComplEx": lambda d: 2 * d, "PairRE": lambda d: 2 * d, "BoxE": lambda d: 4 * d + 2,
-      "TripleRE": lambda d: 3 * d}
+      "TripleRE": lambda d: 3 * d, "InterHT": lambda d: d, "TranS": lambda d: 3 * d}
 
 
 @pytest.fixture(scope="module")
@@ -44,6 +45,10 @@ VARIANTS = [
     ("BoxE", dict(p=1)), ("BoxE", dict(p=2)), ("BoxE", dict(p=2, apply_tanh=False)),
     ("TripleRE", dict(p=1)), ("TripleRE", dict(p=2, rel_u=0.5)),
     ("TripleRE", dict(p=1, normalize=False, rel_u=1.25)),
+    ("InterHT", dict(p=1, rel_u=1.0)), ("InterHT", dict(p=2, rel_u=0.5)),
+    ("InterHT", dict(p=2, normalize=False, rel_u=1.0)),
+    ("TranS", dict(p=1, rel_u=1.0)), ("TranS", dict(p=2, rel_u=0.25)),
+    ("TranS", dict(p=1, normalize=False, rel_u=1.0)),
 ]
 
 

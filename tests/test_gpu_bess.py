@@ -311,6 +311,8 @@ def test_l2_tensor_core_path_matches_tile_path_and_oracle(fam, scheme):
     ("TransE", 2, "ht", False, True, "sgd", "logsigmoid"),    # non-flat SHARED negatives
     ("ComplEx", 2, "t", False, True, "sgd", "softmax_ce"),
     ("BoxE", 1, "t", True, True, "sgd", "logsigmoid"),
+    ("InterHT", 2, "t", True, True, "sgd", "logsigmoid"),
+    ("TranS", 1, "h", False, False, "sgd", "logsigmoid"),
 ])
 def test_score_moving_training_vs_oracle(fam, p, scheme, flat, shared, opt_kind, loss_kind):
     """ScoreMovingBessKGE is a full BessKGE in the reference (bess.py:471-603 + the loss of
@@ -324,8 +326,8 @@ def test_score_moving_training_vs_oracle(fam, p, scheme, flat, shared, opt_kind,
     n, p_part, Nn, d, n_rel, n_ent = 2, 6, 5, 16, 4, 80
     sh = Sharding.create(n_ent, n, seed=3)
     gen = torch.Generator().manual_seed(17)
-    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
-    rw = {"ComplEx": 2 * d, "PairRE": 2 * d, "BoxE": 4 * d + 2}.get(fam, d)
+    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE", "InterHT", "TranS") else 1
+    rw = {"ComplEx": 2 * d, "PairRE": 2 * d, "BoxE": 4 * d + 2, "TranS": 3 * d}.get(fam, d)
     ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen) * 0.5
     rel = torch.randn(n_rel, rw, generator=gen) * 0.5
     S = n * p_part

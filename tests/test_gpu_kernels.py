@@ -11,7 +11,7 @@ from .conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE", "TripleRE"]
+FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE", "TripleRE", "InterHT", "TranS"]
 
 
 def _imports():
@@ -93,6 +93,8 @@ def test_score_functions_vs_reference_golden(fam):
             kw["dist_func_per_dim"] = v["dist_func_per_dim"]
         if "u" in v:
             kw["u"] = v["u"]
+        if "offset" in v:
+            kw["offset"] = v["offset"]
         for sharing in (True, False):
             sf = H.make_score_fn(fam, sharing, v["p"], sh, cfg["n_rel"], d, ent, rel, **kw)
             assert_close(sf.score_triple(h, r, t).cpu(), H.T(g[f"v{vi}_triple"]), rtol=1e-5,
@@ -107,7 +109,8 @@ def test_score_functions_vs_reference_golden(fam):
 
 
 @pytest.mark.parametrize("fam,p", [("TransE", 1), ("TransE", 2), ("RotatE", 1), ("DistMult", 2),
-                                   ("ComplEx", 2), ("PairRE", 2), ("BoxE", 1), ("TripleRE", 1)])
+                                   ("ComplEx", 2), ("PairRE", 2), ("BoxE", 1), ("TripleRE", 1),
+                                   ("InterHT", 1), ("InterHT", 2), ("TranS", 1), ("TranS", 2)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_score_shared_tiles_vs_oracle(fam, p, dtype):
     """multi-tile shapes (ragged edges) in every table dtype; 1e-5 (fp32) / 1e-2 (half)."""
@@ -116,9 +119,9 @@ def test_score_shared_tiles_vs_oracle(fam, p, dtype):
     d, nq, nc, n_rel = 48, 300, 517, 9
     sh = Sharding.create(64, 1, seed=1)
     g = torch.Generator().manual_seed(5)
-    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
+    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE", "InterHT", "TranS") else 1
     rw = {"TransE": d, "RotatE": d, "DistMult": d, "ComplEx": 2 * d, "PairRE": 2 * d,
-          "BoxE": 4 * d + 2, "TripleRE": 3 * d}[fam]
+          "BoxE": 4 * d + 2, "TripleRE": 3 * d, "InterHT": d, "TranS": 3 * d}[fam]
     ent = torch.randn(1, 64, ew * d, generator=g)
     rel = (torch.randn(n_rel, rw, generator=g)).to(dtype).float()
     h = torch.randn(nq, ew * d, generator=g).to(dtype)

@@ -10,7 +10,7 @@ from oracle import besskge_oracle as O
 
 from .conftest import golden_names, load_golden
 
-FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE", "TripleRE"]
+FAMS = ["TransE", "RotatE", "DistMult", "ComplEx", "PairRE", "BoxE", "TripleRE", "InterHT", "TranS"]
 
 
 def T(a):
@@ -21,7 +21,8 @@ def score_cfg(fam, d, v):
     return dict(family=fam, d=d, norm_p=v.get("p", 2) or 2,
                 normalize=v.get("normalize_entities", True),
                 apply_tanh=v.get("apply_tanh", True), per_dim=v.get("dist_func_per_dim", True),
-                eps=1e-6, rel_u=v.get("u", 0.0))
+                eps=1e-6,
+                rel_u=v.get("u", v.get("offset", 1.0 if fam in ("InterHT", "TranS") else 0.0)))
 
 
 def test_sharding_oracle():
