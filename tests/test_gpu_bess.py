@@ -358,4 +358,6 @@ def test_score_moving_training_vs_oracle(fam, p, scheme, flat, shared, opt_kind,
     torch.cuda.synchronize()
     tol = dict(rtol=1e-4, atol=2e-5) if adam else dict(rtol=1e-5, atol=2e-6)
     assert_close(sf.entity_embedding.detach().cpu(), want["ent"], **tol)
+    if fam == "BoxE":  # width gradients pass through the log / exp of the geometric-mean normalisation
+        tol = dict(rtol=1e-4, atol=3e-5)
     assert_close(sf.relation_embedding.detach().cpu(), want["rel"], **tol)
