@@ -171,6 +171,28 @@ def test_loss_wide_rows_vs_oracle():
         assert_close(dneg.cpu(), n_.grad, rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("N", [1024, 2048, 4096])
+@pytest.mark.parametrize("adversarial", [True, False])
+def test_loss_full_rows_fast_path_vs_oracle(N, adversarial):
+    """Rows of exactly 16 scores per thread take the predicate-free LogSigmoid path
+    (approx SFU ops, folded constants): same tolerances as the generic path."""
+    L, K, H = _imports()
+    g = torch.Generator().manual_seed(N)
+    S = 150
+    pos = torch.randn(S, generator=g) * 4
+    neg = torch.randn(S, N, generator=g) * 4
+    w = torch.rand(S, generator=g)
+    case = dict(kind="logsigmoid", margin=6.0, negative_adversarial_sampling=adversarial,
+                negative_adversarial_scale=0.7, loss_scale=1.5)
+    p_, n_ = pos.clone().requires_grad_(True), neg.clone().requires_grad_(True)
+    want = O.loss_value(H.oracle_loss_cfg(case), p_, n_, w)
+    want.backward()
+    lossv, dpos, dneg = H.make_loss(case).fwd_bwd(pos.cuda(), neg.clone().cuda(), w.cuda())
+    assert_close(lossv.cpu(), want.detach(), rtol=1e-5, atol=1e-4)
+    assert_close(dpos.cpu(), p_.grad, rtol=1e-4, atol=1e-6)
+    assert_close(dneg.cpu(), n_.grad, rtol=1e-4, atol=1e-7)
+
+
 def test_metrics_vs_reference_golden():
     L, K, H = _imports()
     from besskge_b200.metric import Evaluation
