@@ -64,6 +64,9 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the wikikg2 secondary workload and the shard_bs 65536 points")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--stage-timing", action="store_true",
+                    help="per-stage device times of the captured step on every rank (%%globaltimer "
+                         "stamps between the stages; adds ~8 tiny launches per step)")
     ap.add_argument("--step-only", action="store_true",
                     help="only the timed steps (no stand-alone kernel timings, secondary workload, "
                          "parity check or CPU baseline): the command the ncu launch list is taken on")
@@ -713,6 +716,8 @@ def run_scoremoving(args) -> None:
 def main() -> None:
     global _REAL_STDOUT
     args = parse()
+    if args.stage_timing:
+        os.environ["BESS_STAGE_STAMPS"] = "1"
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
@@ -753,6 +758,9 @@ def main() -> None:
 
     if args.step_only:
         args.no_parity = args.no_secondary = args.no_cpu_baseline = True
+    if "stage_us" in res and rank == 0:
+        print(json.dumps({"stage_us": res["stage_us"], "ms_per_step": res["ms_per_step"],
+                          "n_gpus": world, "workload": args.workload}), file=sys.stderr)
     line = None
     if rank == 0 and args.step_only:
         line = {"metric": "train_triples_per_sec", "value": res["value"], "unit": "triples/s",
@@ -913,6 +921,25 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
                       "h2d_bytes_per_step": staged[0].h2d_bytes, "d2h_bytes_per_step": d2h,
                       "ms_per_step": t_e2e / steps * 1e3}
     out["workspace_mb"] = model._ws.bytes() / 1e6
+    if os.environ.get("BESS_STAGE_STAMPS") == "1":
+        import besskge_b200.bess as bess_mod
+        samples = []
+        for i in range(warmup, min(total, warmup + 8)):
+            step.run_staged(staged[i])
+            torch.cuda.synchronize()
+            st_ = model._ws.get("stage_stamps", (1, len(bess_mod.STAGE_NAMES)), torch.int64)[0].cpu()
+            samples.append((st_[1:] - st_[:-1]).double() / 1e3)
+            barrier()
+        med = torch.stack(samples).median(0).values.tolist()
+        mine = dict(zip([f"{a} -> {b}" for a, b in zip(bess_mod.STAGE_NAMES[:-1],
+                                                       bess_mod.STAGE_NAMES[1:])], med))
+        mine["step (first -> last stamp)"] = float(sum(med))
+        allr = [None] * world
+        if world > 1:
+            torch.distributed.all_gather_object(allr, mine)
+        else:
+            allr = [mine]
+        out["stage_us"] = {f"rank{r}": v for r, v in enumerate(allr)}
     del staged, step, model
     return out
 

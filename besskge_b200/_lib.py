@@ -132,6 +132,7 @@ SIGNATURES = {
     "bess_peer_unmap": [_P],
     "bess_take_along_rows": [_P, _I, _L, _I, _P, _I, _I, _P, _P],
     "bess_complex_mul": [_I, _P, _P, _I, _I, _I, _P, _P],
+    "bess_stamp": [_P, _P],
     "bess_fill_f32": [_P, _L, _F, _P],
     "bess_fill_i32": [_P, _L, C.c_int32, _P],
     "bess_cast_from_f32": [_P, _P, _I, _L, _P],

@@ -248,6 +248,10 @@ class _Pass:
 # (csrc/gemm_tc.cu).  The exact-fp32 CUDA-core tile kernel (csrc/pair.cu)
 # computes the same thing and is kept selectable for A/B parity tests only.
 USE_TENSOR_CORES = True
+# profiling aid: %globaltimer stamps between the stages of a (captured) training step
+STAGE_STAMPS = os.environ.get("BESS_STAGE_STAMPS", "0") == "1"
+STAGE_NAMES = ["start", "gather+local prologue", "rows arrived", "scores", "loss", "backward",
+               "gradients exchanged", "updated"]
 # fp32 tables on the tensor cores: 3xFP16 (scaled fp16 hi / lo pairs, csrc/gemm_tc.cu) instead of
 # 3xTF32 for the DistMult / ComplEx training contractions.  BESS_F16X3=0 selects 3xTF32.
 USE_F16X3 = os.environ.get("BESS_F16X3", "1") != "0"
@@ -845,6 +849,15 @@ class EmbeddingMovingBessKGE(BessKGE):
         flat = self.negative_sampler.flat_negative_format
         scheme = self.negative_sampler.corruption_scheme
 
+        # optional per-stage device timestamps (BESS_STAGE_STAMPS=1; bench --stage-timing)
+        stamps = None
+        if STAGE_STAMPS and train:
+            stamps = ws.get("stage_stamps", (bps, len(STAGE_NAMES)), torch.int64)
+
+        def stamp(s_, name):
+            if stamps is not None:
+                K.stamp(stamps[s_, STAGE_NAMES.index(name)])
+
         side = self._side_stream(dev) if train else None
         # score_triple (forward and backward) only touches rows that the negative-scoring
         # kernels never write — unless augment_negative makes the micro-batch's own heads /
@@ -865,6 +878,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     if not rows_this_step.is_contiguous() or len(step_rows) != R:
                         rows_this_step = rows_this_step.contiguous()
                     K.sort_keys(rows_this_step.view(-1), R * S, rel_bits, rk, rp, sort_ws)
+            stamp(s, "start")
             # ================= gather (+ exchange) =================
             for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                 table = ent[shard]
@@ -892,9 +906,14 @@ class EmbeddingMovingBessKGE(BessKGE):
                         q0 = tc_q[0] = _TcOperand(ws, "q0", ps0.n_query, W, tdt, train, gdt)
                         q0.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
                     pre_done = True
+                stamp(s, "gather+local prologue")
                 px.wait(0)
             elif pl.distributed:
+                stamp(s, "gather+local prologue")
                 pl.all_to_all(TN[0], SEND)
+            else:
+                stamp(s, "gather+local prologue")
+            stamp(s, "rows arrived")
 
             for li, row in enumerate(step_rows):
                 o = s * R + li
@@ -966,6 +985,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                                         None if aux is None else aux[li])
                 if overlap:
                     torch.cuda.current_stream(dev).wait_stream(aux_st)  # positive scores ready
+                stamp(s, "scores")
                 # ================= masks (bess.py:182-245) =================
                 self._apply_masks(neg, S, N, p, B, Nn, n, nmask[row] if nmask is not None else None,
                                   flat, scheme)
@@ -999,6 +1019,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     self._finish_metrics({}, pos, neg, tmask[row] if tmask is not None else None,
                                          acc)
 
+                stamp(s, "loss")
                 # ================= backward =================
                 if train:
                     score_for_bwd = neg
@@ -1137,6 +1158,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     if cfg.family == L.BOXE:
                         K.boxe_rel_finalize(cfg, dt, rel_table, rel[row], S, dRq[li])
 
+            stamp(s, "backward")
             # ================= reverse exchange + update =================
             if px is not None and not train:
                 px.handshake(1)  # every rank is done reading its receive buffer
@@ -1150,6 +1172,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                 hyper = self._hyper(bps)[s]  # filled by TrainingModel before this call / replay
                 main = torch.cuda.current_stream(dev)
                 main.wait_stream(side)  # join: permutations ready (and the early gradient push)
+                stamp(s, "gradients exchanged")
                 # relation table (replicated): reduce per-query rows of all local replicas, then
                 # its all-reduce over peer memory — on the side stream, under the entity scatter
                 mean = getattr(optimizer, "relation_grad_reduction", "mean") == "mean"
@@ -1204,6 +1227,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                         self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
                 else:
                     self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
+                stamp(s, "updated")
 
         out: Dict[str, Any] = {}
         if want_scores:

@@ -78,6 +78,10 @@ __global__ void peer_wait_kernel(const int32_t* counter, const int32_t* my_flags
   __threadfence_system();
 }
 
+// Stage stamp: one thread stores %globaltimer (ns).  Placed between the kernels of a captured step
+// it gives per-stage device timings of a multi-rank run without a profiler (bench --stage-timing).
+__global__ void stamp_kernel(unsigned long long* out) { *out = globaltimer_ns(); }
+
 // block (j, *) copies src + j * src_stride_bytes -> dst[j], bytes_each bytes (16-byte multiples)
 __global__ void __launch_bounds__(256) peer_push_kernel(const uint8_t* __restrict__ src,
                                                         int64_t src_stride_bytes, PeerPtrs dst,
@@ -129,6 +133,12 @@ extern "C" int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, i
   BESS_CHECK_ARG(n >= 1 && n <= 32, "bess_peer_wait: n=%d out of range", n);
   peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter, my_flags, n,
                                                       timeout_ms * 1000000LL);
+  BESS_CHECK_LAUNCH();
+  return BESS_OK;
+}
+
+extern "C" int bess_stamp(uint64_t* out, void* stream) {
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(out));
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

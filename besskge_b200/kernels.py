@@ -522,6 +522,11 @@ def peer_import(handle: bytes, device: torch.device) -> int:
     return int(p.value)
 
 
+def stamp(slot: torch.Tensor) -> None:
+    """slot (int64, 1 element) <- %globaltimer when the current stream gets here."""
+    call("bess_stamp", slot.data_ptr(), _st(slot))
+
+
 def fill_f32(t: torch.Tensor, v: float) -> None:
     call("bess_fill_f32", t.data_ptr(), t.numel(), float(v), _st(t))
 

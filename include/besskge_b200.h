@@ -485,6 +485,9 @@ int bess_take_along_rows(const void* x, int a, int64_t e, int elem_bytes, const 
 int bess_complex_mul(int dtype, const void* v1, const void* v2, int n, int e, int rotate, void* out,
                      void* stream);
 
+/* profiling aid: out[0] <- %globaltimer (ns) when the stream reaches this point */
+int bess_stamp(uint64_t* out, void* stream);
+
 /* utility */
 int bess_fill_f32(float* p, int64_t n, float v, void* stream);
 int bess_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);
