@@ -58,6 +58,10 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--optimizer", default="sgd", choices=["sgd", "sgdm", "adamw"],
                     help="sgd: SGD(1e-3) (sparse-exact update); sgdm: SGD(1e-3, momentum 0.95) "
                          "(nb3 cell 18); adamw: AdamW(1e-3) (nb1 cell 28) - both dense passes")
+    ap.add_argument("--batches-per-step", type=int, default=4,
+                    help="micro-batches per training call = per captured CUDA graph (the reference's "
+                         "ShardedBatchSampler(batches_per_step) / PopTorch deviceIterations: nb1 uses 8, "
+                         "nb3 100); one bench 'step' is ONE micro-batch, a call runs this many")
     ap.add_argument("--n-triple", type=int, default=1 << 21,
                     help="synthetic training triples (sampled with replacement)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -129,7 +133,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------
 def build_problem(workload: str, n_shard: int, shard_bs: int = 0, negatives: int = 0,
-                  n_triple: int = 1 << 21):
+                  n_triple: int = 1 << 21, bps: int = 1):
     """Synthetic graph of the named shape + sharding + samplers (host side)."""
     from besskge_b200.batch_sampler import RandomShardedBatchSampler
     from besskge_b200.dataset import synthetic_kg
@@ -143,9 +147,10 @@ def build_problem(workload: str, n_shard: int, shard_bs: int = 0, negatives: int
     sh = Sharding.create(ds.n_entity, n_shard, seed=1234)
     pts = PartitionedTripleSet.create_from_dataset(ds, "train", sh)
     ns = RandomShardedNegativeSampler(max(negatives // n_shard, 1), sh, 1234, "t", False, True)
-    bs = RandomShardedBatchSampler(pts, ns, shard_bs=shard_bs, batches_per_step=1, seed=1234)
+    bs = RandomShardedBatchSampler(pts, ns, shard_bs=shard_bs, batches_per_step=bps, seed=1234)
     return dict(workload=workload, ds=ds, sh=sh, ns=ns, bs=bs, fam=fam, d=d, p=p, dtype=dt,
-                shard_bs=shard_bs, negatives=max(negatives // n_shard, 1) * n_shard, shape=shape)
+                shard_bs=shard_bs, negatives=max(negatives // n_shard, 1) * n_shard, shape=shape,
+                bps=bps)
 
 
 OPTIMIZERS = {"sgd": "SGD(1e-3)", "sgdm": "SGD(1e-3, momentum=0.95)", "adamw": "AdamW(1e-3)"}
@@ -167,7 +172,7 @@ def workload_config(prob, n_shard: int, optimizer: str) -> dict:
             "n_entity": prob["ds"].n_entity, "n_shard": n_shard, "shard_bs": prob["shard_bs"],
             "negatives_per_triple": prob["negatives"], "loss": "LogSigmoid(12, adversarial)",
             "optimizer": OPTIMIZERS[optimizer], "score_fn": prob["fam"],
-            "embedding_size": prob["d"],
+            "embedding_size": prob["d"], "batches_per_step": prob.get("bps", 1),
             "l2": "no flush: the per-step working set (index lists, gathered rows, the "
                   "[shard_bs, negatives] score matrix and its gradient) exceeds the 126 MB L2, and "
                   "every step draws a new batch"}
@@ -424,8 +429,12 @@ def cpu_port_steps(prob, n_steps: int, threads: int, optimizer: str = "sgd"):
     lcfg = dict(kind="logsigmoid", margin=12.0, adversarial=True, adv_scale=1.0)
     w = torch.tensor([1.0])
     times = []
+    bps = prob.get("bps", 1)
+    call = None
     for i in range(n_steps):
-        b = {k: v[0] for k, v in bs[[i]].items()}
+        if i % bps == 0:
+            call = bs[[i // bps]]
+        b = {k: v[i % bps] for k, v in call.items()}
         t0 = time.perf_counter()
         opt.zero_grad()
         pos, neg = O.embedding_moving_forward(cfg, ent, rel, b["head"], b["relation"], b["tail"],
@@ -444,7 +453,10 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     n = max(args.gpus, 1)
-    prob = build_problem(args.workload, n, args.shard_bs, args.negatives, args.n_triple)
+    bps = args.batches_per_step
+    while args.steps % bps:
+        bps //= 2
+    prob = build_problem(args.workload, n, args.shard_bs, args.negatives, args.n_triple, bps)
     threads = os.cpu_count() or 1
     times = cpu_port_steps(prob, args.warmup + args.steps, threads, args.optimizer)
     t = float(np.mean(times[args.warmup:]))
@@ -752,7 +764,10 @@ def main() -> None:
 
     pk = peaks()
     ctx = dict(world=world, rank=rank, dev=dev, local_rank=local_rank, pk=pk)
-    prob = build_problem(args.workload, world, args.shard_bs, args.negatives, args.n_triple)
+    bps = args.batches_per_step
+    while args.steps % bps:
+        bps //= 2
+    prob = build_problem(args.workload, world, args.shard_bs, args.negatives, args.n_triple, bps)
     res = train_leg(ctx, prob, args.optimizer, args.steps, args.warmup, sample_clocks=True)
     S, N = prob["shard_bs"], prob["negatives"]
 
@@ -788,6 +803,7 @@ def main() -> None:
             "gather": gather,
             "scatter": scatter,
             "workspace_mb": res["workspace_mb"],
+            "warmup_steps_run": res["warmup_steps_run"],
         }
         if opt_dense is not None:
             line["opt_dense"] = opt_dense
@@ -804,12 +820,12 @@ def main() -> None:
     # ---- secondary workload + the shard_bs 65536 points of SURVEY 8(d) --------------------
     if not args.no_secondary and args.workload == "biokg-distmult-d256-fp32":
         sec_name = "wikikg2-transe-l1-d256-bf16"  # north_star's scaling workload (configs[3])
-        sprob = build_problem(sec_name, world, 0, 0, args.n_triple)
+        sprob = build_problem(sec_name, world, 0, 0, args.n_triple, bps)
         sres = train_leg(ctx, sprob, "sgd", args.steps, args.warmup)
         points = []
         for name, sbs in ((args.workload, 65536), (sec_name, 65536)):
-            pprob = build_problem(name, world, sbs, 0, args.n_triple)
-            pres = train_leg(ctx, pprob, "sgd", max(args.steps // 2, 3), 3, want_e2e=False)
+            pprob = build_problem(name, world, sbs, 0, args.n_triple, 2)
+            pres = train_leg(ctx, pprob, "sgd", 8, 3, want_e2e=False)
             if rank == 0:
                 points.append({"workload": name, "shard_bs": sbs,
                                "negatives_per_triple": pprob["negatives"],
@@ -857,9 +873,16 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
     model, sf, _ = make_model(prob, dev)
     step = training_model(model, make_optimizer(optimizer))
     S = prob["shard_bs"]
+    # one call = `bps` micro-batches (one captured graph); a bench step = one micro-batch.
+    # Warm-up: at least `warmup` steps and at least 3 calls (eager sizing, capture, replay).
+    bps = prob["bps"]
+    assert steps % bps == 0, f"--steps {steps} must be a multiple of --batches-per-step {bps}"
+    warm_calls = max(-(-warmup // bps), 3)
+    timed_calls = steps // bps
+    steps_arg, warmup, steps = steps, warm_calls, timed_calls  # loop counters below are CALLS
     total = warmup + steps
     host_batches = []
-    for i in range(total):  # every rank draws the same batches (same seeds); one per step
+    for i in range(total):  # every rank draws the same batches (same seeds); one per call
         b = flat_batch(prob["bs"][[i]])
         host_batches.append({k: v.pin_memory() for k, v in b.items()})
 
@@ -895,8 +918,10 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
     barrier()
     clocks = sampler.stop() if sampler else None
     t_dev = max_over_ranks(st.elapsed_time(en) * 1e-3)
+    steps = steps_arg  # back to micro-batches
+    launches_per_step = launches_per_step / bps
     out = dict(value=world * S * steps / t_dev, ms_per_step=t_dev / steps * 1e3, clocks=clocks,
-               launches_per_step=launches_per_step, sf=sf, e2e=None)
+               launches_per_step=launches_per_step, sf=sf, e2e=None, warmup_steps_run=warm_calls * bps)
 
     # -------- end-to-end leg: host batch in, loss out, every step -------------
     if want_e2e:
@@ -907,7 +932,7 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
         # asynchronous D2H copy per step, stream-ordered before the next step overwrites the
         # static output; the host only blocks at the end, as a training loop would)
         n_loss = step(**host_batches[0])["loss"].numel()
-        loss_host = torch.empty(steps, n_loss, dtype=torch.float32, pin_memory=True)
+        loss_host = torch.empty(timed_calls, n_loss, dtype=torch.float32, pin_memory=True)
         barrier()
         st.record()
         for i in range(warmup, total):
@@ -915,10 +940,10 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
         en.record()
         barrier()
         assert bool(torch.isfinite(loss_host).all())
-        d2h = n_loss * 4
+        d2h = n_loss * 4 // bps
         t_e2e = max_over_ranks(st.elapsed_time(en) * 1e-3)
         out["e2e"] = {"value": world * S * steps / t_e2e, "unit": "triples/s",
-                      "h2d_bytes_per_step": staged[0].h2d_bytes, "d2h_bytes_per_step": d2h,
+                      "h2d_bytes_per_step": staged[0].h2d_bytes // bps, "d2h_bytes_per_step": d2h,
                       "ms_per_step": t_e2e / steps * 1e3}
     out["workspace_mb"] = model._ws.bytes() / 1e6
     if os.environ.get("BESS_STAGE_STAMPS") == "1":
@@ -927,13 +952,18 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
         for i in range(warmup, min(total, warmup + 8)):
             step.run_staged(staged[i])
             torch.cuda.synchronize()
-            st_ = model._ws.get("stage_stamps", (1, len(bess_mod.STAGE_NAMES)), torch.int64)[0].cpu()
-            samples.append((st_[1:] - st_[:-1]).double() / 1e3)
+            st_ = model._ws.get("stage_stamps", (bps, len(bess_mod.STAGE_NAMES)), torch.int64).cpu()
+            for row_ in st_:
+                samples.append((row_[1:] - row_[:-1]).double() / 1e3)
+            if bps > 1:  # gap between consecutive micro-batches inside one graph
+                gaps_in_graph = (st_[1:, 0] - st_[:-1, -1]).double().mean().item() / 1e3
             barrier()
         med = torch.stack(samples).median(0).values.tolist()
         mine = dict(zip([f"{a} -> {b}" for a, b in zip(bess_mod.STAGE_NAMES[:-1],
                                                        bess_mod.STAGE_NAMES[1:])], med))
         mine["step (first -> last stamp)"] = float(sum(med))
+        if bps > 1:
+            mine["gap between micro-batches inside a graph"] = gaps_in_graph
         allr = [None] * world
         if world > 1:
             torch.distributed.all_gather_object(allr, mine)
@@ -958,7 +988,7 @@ def parity_check(ctx, prob, optimizer: str) -> dict:
     o = make_optimizer(optimizer)
     o.lr = lr
     step = training_model(model, o, cuda_graph=False)
-    batch = prob["bs"][[0]]
+    batch = {k: v[:1] for k, v in prob["bs"][[0]].items()}  # the first micro-batch only
     res = step(**flat_batch(batch))
     torch.cuda.synchronize()
     got_loss = res["loss"].cpu()

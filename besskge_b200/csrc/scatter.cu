@@ -380,13 +380,17 @@ __global__ void set_hyper_kernel(float* hyper, HyperVals h) {
   if (threadIdx.x < BESS_HYPER_COUNT) hyper[threadIdx.x] = h.v[threadIdx.x];
 }
 
-// Relation-table gradient: CTA (relation r, 128-column block) reduces the sorted
-// run of per-query rows with 8 warps in a fixed interleaved order.
-__global__ void __launch_bounds__(256) relation_reduce_kernel(const float* rows, int width,
-                                                               const int32_t* sorted_rel,
-                                                               const int32_t* perm, int n,
-                                                               float* d_table) {
-  __shared__ float part[8][128];
+// Relation-table gradient: CTA (relation r, 128-column block) reduces the sorted run of
+// per-query rows with RR_WARPS warps in a fixed interleaved order (warp w takes rows w,
+// w + RR_WARPS, ... of the run; the per-warp sums are added in warp order): deterministic.
+// The loop is a chain of dependent perm -> row loads (the rows sit anywhere in the [S, Wr]
+// buffer), so latency rules: 16 warps x 8 rows in flight each (was 8 x 4: ~21 us per launch
+// at biokg's 51 relations x 321 rows, now a few round trips).
+constexpr int RR_WARPS = 16, RR_FLIGHT = 8;
+__global__ void __launch_bounds__(RR_WARPS * 32) relation_reduce_kernel(
+    const float* rows, int width, const int32_t* sorted_rel, const int32_t* perm, int n,
+    float* d_table) {
+  __shared__ float part[RR_WARPS][128];
   const int r = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // run [lo, hi) of relation r by binary search (warp-uniform)
@@ -401,22 +405,16 @@ __global__ void __launch_bounds__(256) relation_reduce_kernel(const float* rows,
   if (k0 < width) {
     int i = start + w;
     if ((width & 3) == 0) {
-      // four rows of this warp's interleaved sequence in flight (the loop was a chain of
-      // dependent perm -> row loads: ~40 serial round trips per warp at biokg's 51 relations);
-      // they are added in sequence order, so the sum is the same as the one-at-a-time loop's
-      for (; i + 24 < end; i += 32) {
-        const int p0 = perm[i], p1 = perm[i + 8], p2 = perm[i + 16], p3 = perm[i + 24];
-        const float4 v0 = *reinterpret_cast<const float4*>(rows + (int64_t)p0 * width + k0);
-        const float4 v1 = *reinterpret_cast<const float4*>(rows + (int64_t)p1 * width + k0);
-        const float4 v2 = *reinterpret_cast<const float4*>(rows + (int64_t)p2 * width + k0);
-        const float4 v3 = *reinterpret_cast<const float4*>(rows + (int64_t)p3 * width + k0);
-        s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
-        s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
-        s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
-        s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+      for (; i + (RR_FLIGHT - 1) * RR_WARPS < end; i += RR_FLIGHT * RR_WARPS) {
+        float4 v[RR_FLIGHT];
+#pragma unroll
+        for (int u = 0; u < RR_FLIGHT; ++u)
+          v[u] = *reinterpret_cast<const float4*>(rows + (int64_t)perm[i + u * RR_WARPS] * width + k0);
+#pragma unroll
+        for (int u = 0; u < RR_FLIGHT; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
       }
     }
-    for (; i < end; i += 8) {
+    for (; i < end; i += RR_WARPS) {
       const float* row = rows + (int64_t)perm[i] * width + k0;
       if ((width & 3) == 0) {  // rows 16-byte aligned
         const float4 v = *reinterpret_cast<const float4*>(row);
@@ -437,7 +435,7 @@ __global__ void __launch_bounds__(256) relation_reduce_kernel(const float* rows,
     if (k < width) {
       float t = 0.f;
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) t += part[ww][threadIdx.x];
+      for (int ww = 0; ww < RR_WARPS; ++ww) t += part[ww][threadIdx.x];
       d_table[(int64_t)r * width + k] = t;
     }
   }
@@ -608,8 +606,8 @@ extern "C" int bess_relation_grad_reduce(const float* d_rel_rows, int width,
                                          int n_rel, float* d_table, void* stream) {
   if (n_rel == 0) return BESS_OK;
   dim3 grid(n_rel, ceil_div(width, 128));
-  relation_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_rel_rows, width, sorted_rel,
-                                                                 perm, n, d_table);
+  relation_reduce_kernel<<<grid, RR_WARPS * 32, 0, (cudaStream_t)stream>>>(d_rel_rows, width,
+                                                                           sorted_rel, perm, n, d_table);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
 }

@@ -1,7 +1,16 @@
-set -x
-cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out
-N=${1:-2}
-timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 tests/dist_gpu_worker.py > gpurun_out/dist_parity_$N.log 2>&1; echo "dist parity exit $?"; tail -8 gpurun_out/dist_parity_$N.log
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench exit $?"; tail -5 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29553 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --workload wikikg2-transe-l1-d256-bf16 > gpurun_out/bench_wiki_n$N.json 2> gpurun_out/bench_wiki_n$N.err; echo "bench exit $?"; tail -5 gpurun_out/bench_wiki_n$N.err; cat gpurun_out/bench_wiki_n$N.json
+#!/bin/bash
+# usage: scripts/gpu_multi.sh N TAG [bench args...] — torchrun bench on N GPUs of one box
+N=$1; TAG=$2; shift 2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+  bench.py --gpus $N --steps 20 --warmup 5 "$@" > gpurun_out/${TAG}_n${N}.json 2> gpurun_out/${TAG}_n${N}.err
+rc=$?
+grep stage_us gpurun_out/${TAG}_n${N}.err > gpurun_out/${TAG}_n${N}_stages.json
+python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/${TAG}_n${N}.json"))
+    print("${TAG} N=$N", "value", round(d["value"]/1e6,2), "ms", round(d["ms_per_step"],4), "e2e ms", round((d.get("e2e") or {}).get("ms_per_step",0),4), "sec", (d.get("secondary") or {}).get("ms_per_step"), "parity", (d.get("parity_check") or {}).get("ok"))
+except Exception as e:
+    print("${TAG} N=$N failed", e, open("gpurun_out/${TAG}_n${N}.err").read()[-1500:])
+PY
+exit $rc
