@@ -1431,7 +1431,29 @@ class ScoreMovingBessKGE(BessKGE):
         neg_out = torch.empty(n_out * S, N, dtype=torch.float32, device=dev)
         loss_out = (torch.empty(n_out, dtype=torch.float32, device=dev)
                     if self.loss_fn is not None else None)
-        if dist:
+        # Distributed inference over peer memory (no collective library inside the step): the
+        # query rows are stored straight into every rank's replicated query arrays, and the
+        # scoring kernels store each owner's block of scores straight into that owner's score
+        # matrix over NVLink — compute and exchange are one kernel.  Two flag handshakes per
+        # micro-batch.  Training keeps the collective path below.
+        peer = bool(dist and USE_PEER_EXCHANGE and not train and S % 4 == 0)
+        px: Optional[_PeerExchange] = None
+        if peer:
+            if self._px is None:
+                self._px = _PeerExchange(dev, n, pl.rank)
+            px = self._px
+            es = ent.element_size()
+            h_bytes = _up(n * S * W * es)
+            px.ensure(h_bytes + n * S * W * es, S * N * 4, n * S * 4)
+            H = px.view(px.off_tn, (n, S, W), tdt)
+            T = px.view(px.off_tn + h_bytes, (n, n, p, W), tdt)
+            sc_sym = px.view(px.off_grad, (S, N), torch.float32)
+            rel_all = px.view(px.off_rel, (n * S,), torch.int32)
+            off_H, off_T = px.off_tn, px.off_tn + h_bytes
+            rep_h = ws.get("sm_rep_h", (n, S), torch.int32)
+            if need_aux:
+                aux = ws.get("aux", (S, N), torch.float32)
+        elif dist:
             SEND_T = ws.get("SEND", (n, p, W), tdt)
             sc_local = ws.get("sc_local", (n * S, X), torch.float32)
             sc_recv = ws.get("sc_recv", (n, S, X), torch.float32)
@@ -1453,7 +1475,29 @@ class ScoreMovingBessKGE(BessKGE):
         acc: Dict[str, List] = {}
 
         for s in range(bps):
-            if dist:
+            if peer:
+                row0, me = s, pl.rank
+                es = ent.element_size()
+                # my heads -> H[me] on EVERY rank; my tails for replica j -> T[j][me] on rank j
+                # (on every rank when the tails are the query side): remote stores over NVLink
+                rep_h.copy_(gidx[row0][:S].unsqueeze(0).expand(n, S))
+                K.gather_route(ent[me], rep_h.view(-1), 0, S, None, [q + off_H for q in px.ptrs], me)
+                t_idx = gidx[row0][S:]
+                blk = n * p * W * es  # one replica's [n(src), p, W] block of T
+                if scheme == "t":
+                    K.gather_route(ent[me], t_idx, 0, p, None,
+                                   [px.ptrs[j] + off_T + j * blk for j in range(n)], me)
+                else:
+                    for k in range(n):
+                        K.gather_route(ent[me], t_idx, 0, p, None,
+                                       [px.ptrs[k] + off_T + j * blk for j in range(n)], me)
+                K.peer_push(rel[row0], 0, [q + px.off_rel + me * S * 4 for q in px.ptrs], S * 4)
+                px.handshake(0)
+                pos = pos_out[s * S:(s + 1) * S]
+                K.triple_fwd(cfg, dt, L.rows(H[me]), L.rows(T[me].view(S, W)), rel_table, rel[row0],
+                             L.IDENT, S, pos, L.IDENT)
+                score_buf, scorers = sc_sym, [(me, row0, me * X)]
+            elif dist:
                 row0 = s
                 me = pl.rank
                 # own heads -> H[me]; tails routed to the replica that scores the positive
@@ -1522,6 +1566,20 @@ class ScoreMovingBessKGE(BessKGE):
                 if is_shared and need_scale:
                     scale = K.cand_scales(cfg, dt, cand, n_c, W,
                                           ws.get("cand_scale", (2 * n_c,), torch.float32))
+                if not backward and peer:
+                    # block j of the (owner-major) queries is scored into rank j's score matrix
+                    nqj = nq // n
+                    for j in range(n):
+                        dst = px.ptrs[j] + px.off_grad
+                        qv_j = qv[j * nqj:]
+                        if is_shared:
+                            K.shared_fwd(cfg, dt, mode, qv_j, nqj, cand, scale, n_c, score_buf, qmap,
+                                         N, col0, aux, out_ptr=dst)
+                        else:
+                            cand_j = L.rows(table, idx=sel[j * S * Nn:])
+                            K.pertriple_fwd(cfg, dt, mode, qv_j, nqj, cand_j, Nn, Nn, score_buf,
+                                            qmap, N, col0, aux, out_ptr=dst)
+                    return None
                 if not backward:
                     if is_shared:
                         K.shared_fwd(cfg, dt, mode, qv, nq, cand, scale, n_c, score_buf, qmap,
@@ -1556,7 +1614,11 @@ class ScoreMovingBessKGE(BessKGE):
                                qmap, nq, qv)
                 for shard, row, col0 in scorers:
                     score_group(gi, shard, row, col0, False)
-            if dist:
+            if peer:
+                px.handshake(1)  # every scoring rank has stored its columns of my score matrix
+                neg_out[s * S:(s + 1) * S].copy_(sc_sym)
+                finals = [(s, s, pos_out[s * S:(s + 1) * S], neg_out[s * S:(s + 1) * S])]
+            elif dist:
                 # scores back to the shards that own the queries (bess.py:583-592)
                 torch.distributed.all_to_all_single(sc_recv.view(-1), sc_local.view(-1))
                 neg_out[s * S:(s + 1) * S].view(S, n, X).copy_(sc_recv.transpose(0, 1))

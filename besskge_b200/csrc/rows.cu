@@ -133,6 +133,23 @@ __global__ void __launch_bounds__(256) complex_mul_kernel(const T* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// DistMult on fp32 tables (BASELINE configs[1]): 128-bit versions of the three row functions.
+// The generic family code reads one element per lane per instruction; these rows are 1 KiB and
+// the kernels pure streams, so the instruction count decides the achieved HBM fraction.
+// Same arithmetic, same per-lane summation order per 4-element group as the scalar code is
+// NOT guaranteed (the dot product is re-associated), within fp32 rounding.
+// ---------------------------------------------------------------------------
+BESS_D bool aligned16(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; }
+BESS_D float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+BESS_D void st4(float* p, const float4& v, int add) {
+  float4 o = v;
+  if (add) { const float4 c = ld4(p); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+  *reinterpret_cast<float4*>(p) = o;
+}
+BESS_D float4 mul4(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+BESS_D float4 scl4(float s, const float4& a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+
+// ---------------------------------------------------------------------------
 // score_triple
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -146,6 +163,19 @@ __global__ void __launch_bounds__(256) triple_fwd_kernel(FamCfg cfg, bess_rows_t
   const T* h = static_cast<const T*>(head.base) + src_row(head, w) * head.pitch;
   const T* t = static_cast<const T*>(tail.base) + src_row(tail, w) * tail.pitch;
   const T* r = rel_table + (int64_t)__ldg(rel_id + map_row(rel_map, w)) * rel_pitch;
+  if constexpr (sizeof(T) == 4) {
+    if (cfg.family == FAM_DISTMULT && (cfg.d & 3) == 0 && aligned16(h) && aligned16(t) && aligned16(r)) {
+      const int lane = threadIdx.x & 31;
+      float acc = 0.f;
+      for (int k = lane * 4; k < cfg.d; k += 128) {
+        const float4 a = ld4((const float*)h + k), b = ld4((const float*)r + k), c = ld4((const float*)t + k);
+        acc += a.x * b.x * c.x + a.y * b.y * c.y + a.z * b.z * c.z + a.w * b.w * c.w;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) score[map_row(score_map, w)] = acc;
+      return;
+    }
+  }
   const float s = triple_fwd<WarpCtx, T>(cfg, h, r, t);
   if ((threadIdx.x & 31) == 0) score[map_row(score_map, w)] = s;
 }
@@ -165,6 +195,19 @@ __global__ void __launch_bounds__(256) triple_bwd_kernel(
   float* dt = static_cast<float*>(const_cast<void*>(d_tail.base)) + src_row(d_tail, w) * d_tail.pitch;
   float* dr = d_rel + (int64_t)map_row(rel_map, w) * rel_width;
   const int sr = map_row(score_map, w);
+  if constexpr (sizeof(T) == 4) {
+    if (cfg.family == FAM_DISTMULT && (cfg.d & 3) == 0 && aligned16(h) && aligned16(t) && aligned16(r) &&
+        aligned16(dh) && aligned16(dt) && aligned16(dr)) {
+      const float g = d_score[sr];
+      for (int k = (threadIdx.x & 31) * 4; k < cfg.d; k += 128) {
+        const float4 a = ld4((const float*)h + k), b = ld4((const float*)r + k), c = ld4((const float*)t + k);
+        st4(dh + k, scl4(g, mul4(b, c)), add_h);
+        st4(dt + k, scl4(g, mul4(a, b)), add_t);
+        st4(dr + k, scl4(g, mul4(a, c)), add_r);
+      }
+      return;
+    }
+  }
   triple_bwd<WarpCtx, T>(cfg, h, r, t, score[sr], d_score[sr], dh, dr, dt, add_h, add_r, add_t);
 }
 
@@ -181,6 +224,14 @@ __global__ void __launch_bounds__(256) prologue_fwd_kernel(FamCfg cfg, int mode,
   if (w >= n) return;
   const T* x = static_cast<const T*>(fixed.base) + src_row(fixed, w) * fixed.pitch;
   const T* r = rel_table + (int64_t)__ldg(rel_id + map_row(rel_map, w)) * rel_pitch;
+  if constexpr (sizeof(T) == 4) {
+    float* q = qv + (int64_t)w * qv_row;
+    if (cfg.family == FAM_DISTMULT && (cfg.d & 3) == 0 && aligned16(x) && aligned16(r) && aligned16(q)) {
+      for (int k = (threadIdx.x & 31) * 4; k < cfg.d; k += 128)
+        st4(q + k, mul4(ld4((const float*)x + k), ld4((const float*)r + k)), 0);
+      return;
+    }
+  }
   prologue_fwd<WarpCtx, T>(cfg, mode, x, r, qv + (int64_t)w * qv_row);
 }
 
@@ -195,6 +246,19 @@ __global__ void __launch_bounds__(256) prologue_bwd_kernel(
   const int rrow = map_row(rel_map, w);
   const T* r = rel_table + (int64_t)__ldg(rel_id + rrow) * rel_pitch;
   float* dx = static_cast<float*>(const_cast<void*>(d_fixed.base)) + src_row(d_fixed, w) * d_fixed.pitch;
+  if constexpr (sizeof(T) == 4) {
+    const float* dq = d_qv + (int64_t)w * qv_row;
+    float* dr = d_rel + (int64_t)rrow * rel_width;
+    if (cfg.family == FAM_DISTMULT && (cfg.d & 3) == 0 && aligned16(x) && aligned16(r) && aligned16(dq) &&
+        aligned16(dx) && aligned16(dr)) {
+      for (int k = (threadIdx.x & 31) * 4; k < cfg.d; k += 128) {
+        const float4 g = ld4(dq + k);
+        st4(dx + k, mul4(g, ld4((const float*)r + k)), add_x);
+        st4(dr + k, mul4(g, ld4((const float*)x + k)), add_r);
+      }
+      return;
+    }
+  }
   prologue_bwd<WarpCtx, T>(cfg, mode, x, r, d_qv + (int64_t)w * qv_row, dx,
                            d_rel + (int64_t)rrow * rel_width, add_x, add_r);
 }

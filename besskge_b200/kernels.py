@@ -168,9 +168,12 @@ def cand_scales_bwd(cfg: ScoreCfg, dt: int, cand: Rows, n: int, width: int, scal
 
 def shared_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
                cand_scale: Optional[torch.Tensor], n_cand: int, out: torch.Tensor,
-               score_map: RowMap, ld: int, col0: int, aux: Optional[torch.Tensor]) -> None:
+               score_map: RowMap, ld: int, col0: int, aux: Optional[torch.Tensor],
+               out_ptr: Optional[int] = None) -> None:
+    """`out_ptr`: raw device address of the score matrix instead of `out` (a peer GPU's buffer)."""
     call("bess_score_shared_fwd", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
-         ptr(cand_scale), n_cand, out.data_ptr(), score_map, ld, col0, ptr(aux), _st(out))
+         ptr(cand_scale), n_cand, out.data_ptr() if out_ptr is None else out_ptr, score_map, ld,
+         col0, ptr(aux), _st(qv))
 
 
 def shared_bwd_query(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
@@ -277,9 +280,10 @@ def dot_gemm(dt: int, a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], lda: int
 
 def pertriple_fwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
                   q_stride: int, n_per: int, out: torch.Tensor, score_map: RowMap, ld: int,
-                  col0: int, aux: Optional[torch.Tensor]) -> None:
+                  col0: int, aux: Optional[torch.Tensor], out_ptr: Optional[int] = None) -> None:
     call("bess_score_pertriple_fwd", C.byref(cfg), dt, mode, qv.data_ptr(), n_query, cand,
-         q_stride, n_per, out.data_ptr(), score_map, ld, col0, ptr(aux), _st(out))
+         q_stride, n_per, out.data_ptr() if out_ptr is None else out_ptr, score_map, ld, col0,
+         ptr(aux), _st(qv))
 
 
 def pertriple_bwd(cfg: ScoreCfg, dt: int, mode: int, qv: torch.Tensor, n_query: int, cand: Rows,
