@@ -717,7 +717,11 @@ def run_scoremoving(args) -> None:
                          "unit": "GB/s", "traffic": None, "frac": kbytes / t_k / 1e9 / pk["hbm"],
                          "launch_us": t_k * 1e6, "rows_per_launch": Q * Nn,
                          "step_share": t_k * local / (t_dev / args.steps),
-                         "peak_source": pk["source"]},
+                         "peak_source": pk["source"],
+                         "note": "read-only stream of randomly placed rows (one launch reads "
+                                 f"{kbytes / 1e9:.1f} GB, no reuse); the peak is the driver's COPY "
+                                 "bandwidth (half reads, half writes), which a pure read stream can "
+                                 "exceed - frac > 1 means 'above copy bandwidth', not above HBM"},
             "cpu_baseline": None,
         }
         emit(line)
@@ -987,6 +991,15 @@ def parity_check(ctx, prob, optimizer: str) -> dict:
     lr = 0.05
     o = make_optimizer(optimizer)
     o.lr = lr
+    # Step 1 of Adam moves a coordinate by lr * g / (|g| + eps): at torch's default eps = 1e-8
+    # that is sign(g) for every coordinate whose gradient cancels to ~1e-8, and the last-ulp
+    # difference between two fp32 summation orders flips it (error = one whole update, seen on
+    # a handful of coordinates of 24 M).  The check therefore runs AdamW at eps = 1e-4, where
+    # the update is a well-conditioned function of the gradient (the same choice as
+    # tests/test_gpu_training_runtime.py); the timed legs keep the default eps.
+    adam_eps = 1e-4
+    if optimizer == "adamw":
+        o.eps = adam_eps
     step = training_model(model, o, cuda_graph=False)
     batch = {k: v[:1] for k, v in prob["bs"][[0]].items()}  # the first micro-batch only
     res = step(**flat_batch(batch))
@@ -997,7 +1010,7 @@ def parity_check(ctx, prob, optimizer: str) -> dict:
     out = None
     if rank == 0:
         ocfg = {"sgd": dict(kind="sgd", lr=lr), "sgdm": dict(kind="sgd", lr=lr, momentum=0.95),
-                "adamw": dict(kind="adamw", lr=lr)}[optimizer]
+                "adamw": dict(kind="adamw", lr=lr, eps=adam_eps)}[optimizer]
         t0 = time.perf_counter()
         want = O.training_steps(
             dict(family=prob["fam"], d=prob["d"], norm_p=prob["p"]),
@@ -1012,8 +1025,10 @@ def parity_check(ctx, prob, optimizer: str) -> dict:
         tol = 1e-5 if prob["dtype"] == "fp32" else 1e-2
         errs = dict(loss=rel_err(got_loss, want_loss), entity_table=rel_err(got_ent, want_ent),
                     relation_table=rel_err(got_rel, want["rel"]))
-        out = dict(what="step 1 on randn(0.3) tables vs the oracle (fp32 CPU autograd + torch.optim)",
-                   max_rel_err=errs, tolerance=tol, ok=bool(max(errs.values()) <= tol * 4),
+        what = "step 1 on randn(0.3) tables vs the oracle (fp32 CPU autograd + torch.optim)"
+        if optimizer == "adamw":
+            what += f"; AdamW eps={adam_eps:g} for this check (see parity_check)"
+        out = dict(what=what, max_rel_err=errs, tolerance=tol, ok=bool(max(errs.values()) <= tol * 4),
                    loss=float(got_loss.sum()), oracle_s=time.perf_counter() - t0)
     del step, model, sf
     if world > 1:
