@@ -654,21 +654,41 @@ def run_scoremoving(args) -> None:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    tick = torch.zeros(1, device=dev)
+
     def timed(read_back: bool):
+        """read_back=False: `value`, the batches already resident in HBM (this rank's rows are
+        sliced and copied device-to-device by the call); True: `e2e`, pinned host batches in,
+        the metrics read back every step."""
+        feed = batches
+        if not read_back:
+            feed = [{k: v.to(dev) for k, v in b.items()} for b in batches]
         for i in range(args.warmup):
-            model(**batches[i])
+            model(**feed[i])
         barrier()
         c0 = L_.call("bess_launch_count")
         st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            torch.distributed.all_reduce(tick)  # device-side alignment of the ranks' start
         st.record()
         d2h = 0
+        host_out = None
         for i in range(args.warmup, total):
-            out = model(**batches[i])
+            out = model(**feed[i])
             if read_back:
-                m = out["metrics"].cpu()
+                # every step's metrics go to pinned host memory (asynchronous copy, stream-ordered
+                # after the step; the host blocks once at the end, as an evaluation loop would)
+                m = out["metrics"]
+                if host_out is None:
+                    host_out = torch.empty((args.steps,) + tuple(m.shape), dtype=m.dtype,
+                                           pin_memory=True)
+                host_out[i - args.warmup].copy_(m, non_blocking=True)
                 d2h = m.numel() * m.element_size()
         en.record()
         barrier()
+        if host_out is not None:
+            assert bool(torch.isfinite(host_out.float()).all())
+        del feed
         t = torch.tensor([st.elapsed_time(en) * 1e-3], device=dev)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -680,6 +700,23 @@ def run_scoremoving(args) -> None:
     t_dev, _, launches = timed(False)
     clocks = sampler.stop() if rank == 0 else None
     t_e2e, d2h, _ = timed(True)
+    if os.environ.get("BESS_STAGE_STAMPS") == "1" and world > 1:
+        import besskge_b200.bess as bess_mod
+        names = bess_mod.SM_STAGE_NAMES
+        samples = []
+        for i in range(args.warmup, min(total, args.warmup + 8)):
+            model(**batches[i])
+            torch.cuda.synchronize()
+            st_ = model._ws.get("stage_stamps", (1, len(names)), torch.int64).cpu()[0]
+            samples.append((st_[1:] - st_[:-1]).double() / 1e3)
+            barrier()
+        med = torch.stack(samples).median(0).values.tolist()
+        mine = dict(zip([f"{a} -> {b}" for a, b in zip(names[:-1], names[1:])], med))
+        allr = [None] * world
+        torch.distributed.all_gather_object(allr, mine)
+        if rank == 0:
+            print(json.dumps({"stage_us": {f"rank{r}": v for r, v in enumerate(allr)}}),
+                  file=sys.stderr)
     if rank == 0:
         # dominant kernel alone: the fused gather + score stream of one step on this GPU
         cfg = sf.kernel_cfg()
@@ -901,6 +938,17 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    tick = torch.zeros(1, device=dev)
+
+    def align():
+        """After the host-side barrier the ranks' processes leave it up to a few hundred
+        microseconds apart, and with a 20-step (~8 ms) timed region that skew would be charged
+        to the steps (the first exchange waits for the last rank).  A device-side all-reduce
+        queued right in front of the start event makes every rank's timed region begin when the
+        LAST rank gets there."""
+        if world > 1 and os.environ.get("BESS_BENCH_ALIGN", "1") != "0":
+            torch.distributed.all_reduce(tick)
+
     # -------- kernel-only leg: inputs resident in HBM ------------------------
     staged = [step.stage(**b) for b in host_batches]
     torch.cuda.synchronize()
@@ -915,6 +963,7 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
     if sampler:
         sampler.start()
     st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align()
     st.record()
     for i in range(warmup, total):
         step.run_staged(staged[i])
@@ -938,6 +987,7 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
         n_loss = step(**host_batches[0])["loss"].numel()
         loss_host = torch.empty(timed_calls, n_loss, dtype=torch.float32, pin_memory=True)
         barrier()
+        align()
         st.record()
         for i in range(warmup, total):
             loss_host[i - warmup].copy_(step(**host_batches[i])["loss"], non_blocking=True)
@@ -953,18 +1003,21 @@ def train_leg(ctx, prob, optimizer: str, steps: int, warmup: int, want_e2e: bool
     if os.environ.get("BESS_STAGE_STAMPS") == "1":
         import besskge_b200.bess as bess_mod
         samples = []
+        names = bess_mod.STAGE_NAMES
         for i in range(warmup, min(total, warmup + 8)):
             step.run_staged(staged[i])
             torch.cuda.synchronize()
-            st_ = model._ws.get("stage_stamps", (bps, len(bess_mod.STAGE_NAMES)), torch.int64).cpu()
+            st_ = model._ws.get("stage_stamps", (bps, len(names)), torch.int64).cpu()
+            keep = [j for j in range(len(names)) if int(st_[0, j]) != 0]  # stages this path stamps
+            st_ = st_[:, keep]
             for row_ in st_:
                 samples.append((row_[1:] - row_[:-1]).double() / 1e3)
             if bps > 1:  # gap between consecutive micro-batches inside one graph
                 gaps_in_graph = (st_[1:, 0] - st_[:-1, -1]).double().mean().item() / 1e3
             barrier()
         med = torch.stack(samples).median(0).values.tolist()
-        mine = dict(zip([f"{a} -> {b}" for a, b in zip(bess_mod.STAGE_NAMES[:-1],
-                                                       bess_mod.STAGE_NAMES[1:])], med))
+        kept = [names[j] for j in keep]
+        mine = dict(zip([f"{a} -> {b}" for a, b in zip(kept[:-1], kept[1:])], med))
         mine["step (first -> last stamp)"] = float(sum(med))
         if bps > 1:
             mine["gap between micro-batches inside a graph"] = gaps_in_graph

@@ -124,6 +124,7 @@ SIGNATURES = {
     "bess_peer_signal": [_P, C.POINTER(_P), _I, _I, _P],
     "bess_peer_wait": [_P, _P, _I, _L, _P],
     "bess_peer_push": [_P, _L, C.POINTER(_P), _I, _L, _P],
+    "bess_peer_copy": [_P, _P, _L, _P],
     "bess_peer_reduce": [_P, _I, _L, _F, _P, _P],
     "bess_peer_alloc": [_L, C.POINTER(_P)],
     "bess_peer_free": [_P],

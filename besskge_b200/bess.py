@@ -250,11 +250,23 @@ class _Pass:
 USE_TENSOR_CORES = True
 # profiling aid: %globaltimer stamps between the stages of a (captured) training step
 STAGE_STAMPS = os.environ.get("BESS_STAGE_STAMPS", "0") == "1"
-STAGE_NAMES = ["start", "gather+local prologue", "rows arrived", "scores", "loss", "backward",
+STAGE_NAMES = ["start", "gather+local prologue", "rows arrived", "scores", "loss",
+               "bwd: 1st contraction", "bwd: 2nd contraction", "backward",
                "gradients exchanged", "updated"]
+SM_STAGE_NAMES = ["start", "query rows stored", "query rows arrived", "scored", "scores arrived",
+                  "masks+metrics"]  # ScoreMoving distributed inference over peer memory
 # fp32 tables on the tensor cores: 3xFP16 (scaled fp16 hi / lo pairs, csrc/gemm_tc.cu) instead of
 # 3xTF32 for the DistMult / ComplEx training contractions.  BESS_F16X3=0 selects 3xTF32.
 USE_F16X3 = os.environ.get("BESS_F16X3", "1") != "0"
+# distributed training: the gather of the rows that travel to other GPUs runs on a second
+# stream, next to the gather of the local head rows and the query prologue (A/B: BESS_SPLIT_GATHER=0)
+SPLIT_EXCHANGE_GATHER = os.environ.get("BESS_SPLIT_GATHER", "1") != "0"
+# ... and the blocks cross NVLink on the copy engines instead of by SM stores: the gather writes
+# a local send buffer, one memcpy per destination (spread over COPY_STREAMS streams) delivers it,
+# and the gradient blocks travel back the same way — no SM cycles, so the contractions that run
+# next to the transfer keep their speed (A/B: BESS_COPY_ENGINE=0 selects the remote-store kernels)
+USE_COPY_ENGINE = os.environ.get("BESS_COPY_ENGINE", "1") != "0"
+COPY_STREAMS = max(1, int(os.environ.get("BESS_COPY_STREAMS", "4")))
 # score_triple fwd / bwd and the relation-table reduce on a second stream, concurrent with the
 # negative-scoring / contraction kernels (A/B switch: BESS_OVERLAP=0)
 OVERLAP_SMALL_KERNELS = os.environ.get("BESS_OVERLAP", "1") != "0"
@@ -443,6 +455,30 @@ class BessKGE(torch.nn.Module, ABC):
         if getattr(self, "_aux", None) is None or self._aux.device != dev:
             self._aux = torch.cuda.Stream(dev)
         return self._aux
+
+    def _copy_streams(self, dev: torch.device) -> List["torch.cuda.Stream"]:
+        sts = getattr(self, "_ce_streams", None)
+        if sts is None or sts[0].device != dev or len(sts) != COPY_STREAMS:
+            sts = self._ce_streams = [torch.cuda.Stream(dev) for _ in range(COPY_STREAMS)]
+        return sts
+
+    def _ce_blocks(self, dev: torch.device, src_ptr: int, stride: int, dst_ptrs: Sequence[int],
+                   nbytes: int, rank: int) -> None:
+        """dst_ptrs[j] <- src_ptr + j * stride (nbytes each) on the copy engines: forked from the
+        current stream over the copy streams and joined back into it (under capture: parallel
+        memcpy nodes).  Destinations are visited starting after this rank, so that at any moment
+        the ranks write to different peers."""
+        cur = torch.cuda.current_stream(dev)
+        n = len(dst_ptrs)
+        sts = self._copy_streams(dev)[:max(1, min(COPY_STREAMS, n))]
+        for st in sts:
+            st.wait_stream(cur)
+        for t in range(n):
+            j = (rank + 1 + t) % n
+            if dst_ptrs[j]:  # 0: nothing to deliver to this rank (block already in place)
+                K.peer_copy(src_ptr + j * stride, dst_ptrs[j], nbytes, sts[t % len(sts)])
+        for st in sts:
+            cur.wait_stream(st)
 
     # -------------------------------------------------------------- forward
     def forward(
@@ -852,7 +888,7 @@ class EmbeddingMovingBessKGE(BessKGE):
         # optional per-stage device timestamps (BESS_STAGE_STAMPS=1; bench --stage-timing)
         stamps = None
         if STAGE_STAMPS and train:
-            stamps = ws.get("stage_stamps", (bps, len(STAGE_NAMES)), torch.int64)
+            stamps = ws.get_zeroed("stage_stamps", (bps, len(STAGE_NAMES)), torch.int64)
 
         def stamp(s_, name):
             if stamps is not None:
@@ -864,6 +900,15 @@ class EmbeddingMovingBessKGE(BessKGE):
         # tails candidates as well — so it runs on a second stream next to them
         overlap = OVERLAP_SMALL_KERNELS and not self.augment_negative
         aux_st = self._aux_stream(dev) if overlap else None
+        # The relation-table update of micro-batch s (reduce -> all-reduce over peer memory ->
+        # optimizer, all on the side stream) is joined only where micro-batch s+1 first reads the
+        # table, so its tail runs under the next gather instead of extending this step.
+        rel_pending: List[Any] = []
+
+        def join_relation_update():
+            while rel_pending:  # an event, not the stream: the side stream has newer work queued
+                torch.cuda.current_stream(dev).wait_event(rel_pending.pop())
+
         for s, step_rows in enumerate(self._step_rows(pl, bps)):
             if train:
                 # The sort permutations of the scatter depend only on the step's indices:
@@ -880,6 +925,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     K.sort_keys(rows_this_step.view(-1), R * S, rel_bits, rk, rp, sort_ws)
             stamp(s, "start")
             # ================= gather (+ exchange) =================
+            xch_st = None
             for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                 table = ent[shard]
                 if px is not None:  # rows go straight into every peer's receive buffer
@@ -891,13 +937,37 @@ class EmbeddingMovingBessKGE(BessKGE):
                 else:
                     dst = [TN[j].data_ptr() for j in range(n)]
                     slot = li
-                K.gather_route(table, gidx[row], n_loc_rows, per, H[li], dst, slot)
+                if px is not None and SPLIT_EXCHANGE_GATHER:
+                    # The rows that travel (remote stores over NVLink: latency-bound, few SM
+                    # cycles) go to a second stream together with their signal; the local head
+                    # rows and everything that only needs them stay on this one.
+                    main = torch.cuda.current_stream(dev)
+                    xch_st = self._aux_stream(dev)
+                    xch_st.wait_stream(main)
+                    with torch.cuda.stream(xch_st):
+                        if USE_COPY_ENGINE:
+                            rb = per * W * ent.element_size()
+                            sendx = ws.get("SENDX", (n, per, W), tdt)
+                            stage_dst = [sendx[j].data_ptr() for j in range(n)]
+                            stage_dst[pl.rank] = dst[pl.rank] + pl.rank * rb  # own block: in place
+                            K.gather_route(table, gidx[row][n_loc_rows:], 0, per, None, stage_dst, 0)
+                            self._ce_blocks(dev, sendx.data_ptr(), rb,
+                                            [dst[j] + pl.rank * rb if j != pl.rank else 0
+                                             for j in range(n)], rb, pl.rank)
+                        else:
+                            K.gather_route(table, gidx[row][n_loc_rows:], 0, per, None, dst, slot)
+                        px.signal(0)
+                    K.gather_route(table, gidx[row][:n_loc_rows], n_loc_rows, 0, H[li], [], 0)
+                else:
+                    K.gather_route(table, gidx[row], n_loc_rows, per, H[li], dst, slot)
+            join_relation_update()
             pre_done = False
             if px is not None:
                 # Signal at once, wait as late as possible: the query prologue and its operand
                 # split read only LOCAL rows (own heads, replicated relation table), so they run
                 # while the peers' tail / negative rows are still arriving over NVLink.
-                px.signal(0)
+                if xch_st is None:
+                    px.signal(0)
                 if R == 1 and len(passes) == 1 and passes[0].fixed_from_head:
                     ps0, row0 = passes[0], step_rows[0]
                     K.prologue_fwd(cfg, dt, ps0.mode, L.rows(H[0], rmap=ps0.fixed_map), rel_table,
@@ -907,6 +977,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                         q0.fill(L.F32, L.rows(qv.view(-1, W)), dt, None, dev)
                     pre_done = True
                 stamp(s, "gather+local prologue")
+                if xch_st is not None:
+                    torch.cuda.current_stream(dev).wait_stream(xch_st)  # own block of TN stored
                 px.wait(0)
             elif pl.distributed:
                 stamp(s, "gather+local prologue")
@@ -1051,12 +1123,11 @@ class EmbeddingMovingBessKGE(BessKGE):
                                        a_mn_major=True, a_offset_elems=ps.col0,
                                        a_scale=ds_scale, b_scale=tc_q[pi].scale)
                         join_triple_bwd()
+                        stamp(s, "bwd: 1st contraction")  # dC (+ score_triple's backward)
                         main = torch.cuda.current_stream(dev)
                         side.wait_stream(main)
                         with torch.cuda.stream(side):
-                            blk = per * W * 4
-                            K.peer_push(dTN[0], blk,
-                                        [q + px.off_grad + pl.rank * blk for q in px.ptrs], blk)
+                            self._push_gradients(dev, px, pl, dTN, per * W * 4)
                             px.handshake(1)
                     for pi, ps in enumerate(passes):
                         fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
@@ -1077,6 +1148,8 @@ class EmbeddingMovingBessKGE(BessKGE):
                                            ps.n_query, W, ps.n_cand, d_qv, L.IDENT, W, 0, False,
                                            gemm_ws, a_offset_elems=ps.col0, a_scale=ds_scale,
                                            b_scale=c_op.scale)
+                                stamp(s, "bwd: 2nd contraction" if early_push
+                                      else "bwd: 1st contraction")  # dQ
                                 if not early_push:
                                     K.dot_gemm(gdt, ds_hi, ds_lo, ldN, q_op.hit, q_op.lot, q_op.ldt,
                                                ps.n_cand, W, ps.n_query, d_qv, d_cand.map,
@@ -1084,6 +1157,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                                                out_ptr=d_cand.base, a_mn_major=True,
                                                a_offset_elems=ps.col0, a_scale=ds_scale,
                                                b_scale=q_op.scale)
+                                    stamp(s, "bwd: 2nd contraction")  # dC
                             else:
                                 ds = _TcOperand(ws, "ds", ps.n_query, ps.n_cand, tdt, True, gdt)
                                 ds.fill(L.F32, L.rows(d_neg[li], rmap=ps.qmap, pitch=N,
@@ -1164,8 +1238,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                 px.handshake(1)  # every rank is done reading its receive buffer
             if train:
                 if px is not None and not early_push:
-                    blk = per * W * 4
-                    K.peer_push(dTN[0], blk, [q + px.off_grad + pl.rank * blk for q in px.ptrs], blk)
+                    self._push_gradients(dev, px, pl, dTN, per * W * 4)
                     px.handshake(1)
                 elif pl.distributed and px is None:
                     pl.all_to_all(dBACK, dTN[0])
@@ -1198,6 +1271,13 @@ class EmbeddingMovingBessKGE(BessKGE):
                             d_rel_table.mul_(1.0 / n)
                 acc_k = self._accum_k
                 acc_phase = (self._accum_phase0 + s) % acc_k
+                defer_rel = rel_st is not main and acc_k == 1
+                if defer_rel:
+                    with torch.cuda.stream(rel_st):
+                        self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
+                        done = torch.cuda.Event()
+                        done.record(rel_st)
+                    rel_pending.append(done)
                 for li, (row, shard) in enumerate(zip(step_rows, pl.shards)):
                     if pl.distributed:
                         g_dst, stride_rows = dBACK.data_ptr(), per
@@ -1211,9 +1291,13 @@ class EmbeddingMovingBessKGE(BessKGE):
                     else:
                         self._update_entity(optimizer, ent[shard], shard, sk[li], sp[li], G,
                                             n_loc_rows, per, dH[li], g_dst, stride_rows, hyper, ws)
-                if rel_st is not main:
+                if defer_rel:
+                    pass  # joined by the next micro-batch (or after the last one)
+                elif rel_st is not main:
                     main.wait_stream(rel_st)  # relation gradient reduced (and all-reduced)
-                if acc_k > 1:
+                if defer_rel:
+                    pass
+                elif acc_k > 1:
                     # relation table: one slot per micro-batch of the cycle, summed in slot
                     # order on the last one (deterministic), then one optimizer step
                     cnt = d_rel_table.numel()
@@ -1228,6 +1312,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                 else:
                     self._update_relation(optimizer, rel_table, d_rel_table, hyper, ws)
                 stamp(s, "updated")
+        join_relation_update()
 
         out: Dict[str, Any] = {}
         if want_scores:
@@ -1242,6 +1327,16 @@ class EmbeddingMovingBessKGE(BessKGE):
         return out
 
     # ---- helpers -------------------------------------------------------------
+    def _push_gradients(self, dev, px: _PeerExchange, pl: _Placement, dTN: torch.Tensor,
+                        blk: int) -> None:
+        """block j of this replica's fp32 gradient buffer -> slot [rank] of rank j's gradient
+        receive buffer (the reverse of the forward exchange, bess.py:348-350 under autograd)."""
+        dst = [q + px.off_grad + pl.rank * blk for q in px.ptrs]
+        if USE_COPY_ENGINE:
+            self._ce_blocks(dev, dTN[0].data_ptr(), blk, dst, blk, pl.rank)
+        else:
+            K.peer_push(dTN[0], blk, dst, blk)
+
     @staticmethod
     def _cand_rows(ps: _Pass, Hl: torch.Tensor, TNl: torch.Tensor, local: bool) -> L.Rows:
         if ps.cand_from_head or (local and not ps.aug):
@@ -1473,8 +1568,16 @@ class ScoreMovingBessKGE(BessKGE):
             key_bits = max(1, int(ent.shape[1] - 1).bit_length())
             rel_bits = max(1, int(rel_table.shape[0] - 1).bit_length())
         acc: Dict[str, List] = {}
+        stamps = None
+        if STAGE_STAMPS and peer:
+            stamps = ws.get_zeroed("stage_stamps", (bps, len(SM_STAGE_NAMES)), torch.int64)
+
+        def stamp(s_, name):
+            if stamps is not None:
+                K.stamp(stamps[s_, SM_STAGE_NAMES.index(name)])
 
         for s in range(bps):
+            stamp(s, "start")
             if peer:
                 row0, me = s, pl.rank
                 es = ent.element_size()
@@ -1492,7 +1595,9 @@ class ScoreMovingBessKGE(BessKGE):
                         K.gather_route(ent[me], t_idx, 0, p, None,
                                        [px.ptrs[k] + off_T + j * blk for j in range(n)], me)
                 K.peer_push(rel[row0], 0, [q + px.off_rel + me * S * 4 for q in px.ptrs], S * 4)
+                stamp(s, "query rows stored")
                 px.handshake(0)
+                stamp(s, "query rows arrived")
                 pos = pos_out[s * S:(s + 1) * S]
                 K.triple_fwd(cfg, dt, L.rows(H[me]), L.rows(T[me].view(S, W)), rel_table, rel[row0],
                              L.IDENT, S, pos, L.IDENT)
@@ -1614,8 +1719,10 @@ class ScoreMovingBessKGE(BessKGE):
                                qmap, nq, qv)
                 for shard, row, col0 in scorers:
                     score_group(gi, shard, row, col0, False)
+            stamp(s, "scored")
             if peer:
                 px.handshake(1)  # every scoring rank has stored its columns of my score matrix
+                stamp(s, "scores arrived")
                 neg_out[s * S:(s + 1) * S].copy_(sc_sym)
                 finals = [(s, s, pos_out[s * S:(s + 1) * S], neg_out[s * S:(s + 1) * S])]
             elif dist:
@@ -1640,6 +1747,7 @@ class ScoreMovingBessKGE(BessKGE):
                 if self.evaluation is not None:
                     self._finish_metrics({}, pos_r, neg_r,
                                          tmask[row] if tmask is not None else None, acc)
+            stamp(s, "masks+metrics")
             if not train:
                 continue
 

@@ -18,6 +18,7 @@
 // Waits are bounded in wall-clock time (caller-chosen, minutes by default): a peer that never
 // arrives traps the launch instead of hanging the GPU for ever.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -82,7 +83,11 @@ __global__ void peer_wait_kernel(const int32_t* counter, const int32_t* my_flags
 // it gives per-stage device timings of a multi-rank run without a profiler (bench --stage-timing).
 __global__ void stamp_kernel(unsigned long long* out) { *out = globaltimer_ns(); }
 
-// block (j, *) copies src + j * src_stride_bytes -> dst[j], bytes_each bytes (16-byte multiples)
+// block (j, *) copies src + j * src_stride_bytes -> dst[j], bytes_each bytes (16-byte multiples).
+// Four 16-byte loads are in flight per thread before the first remote store: the launcher keeps
+// the grid at ~2 blocks per SM so that a persistent GEMM on another stream still finds room on
+// every SM (a grid that fills all 2048 thread slots serialises the two), and the unrolling is
+// what keeps NVLink full from that small footprint.
 __global__ void __launch_bounds__(256) peer_push_kernel(const uint8_t* __restrict__ src,
                                                         int64_t src_stride_bytes, PeerPtrs dst,
                                                         int64_t bytes_each) {
@@ -90,9 +95,17 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const uint8_t* __restric
   const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)j * src_stride_bytes);
   uint4* d = reinterpret_cast<uint4*>(dst.p[j]);
   const int64_t n16 = bytes_each >> 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
-       i += (int64_t)gridDim.x * blockDim.x)
-    st_stream(d + i, ld_stream(s + i));
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    const uint4 a = ld_stream(s + i), b = ld_stream(s + i + stride);
+    const uint4 c = ld_stream(s + i + 2 * stride), e = ld_stream(s + i + 3 * stride);
+    st_stream(d + i, a);
+    st_stream(d + i + stride, b);
+    st_stream(d + i + 2 * stride, c);
+    st_stream(d + i + 3 * stride, e);
+  }
+  for (; i < n16; i += stride) st_stream(d + i, ld_stream(s + i));
 }
 
 // out[i] = scale * sum_j slots[j * count + i], j ascending (same order on every rank)
@@ -143,6 +156,16 @@ extern "C" int bess_stamp(uint64_t* out, void* stream) {
   return BESS_OK;
 }
 
+// blocks per SM of the push grid (all destinations together); BESS_PUSH_BLOCKS_PER_SM overrides
+static int push_blocks_per_sm() {
+  static int v = [] {
+    const char* e = getenv("BESS_PUSH_BLOCKS_PER_SM");
+    const int x = e != nullptr ? atoi(e) : 2;
+    return x < 1 ? 1 : (x > 8 ? 8 : x);
+  }();
+  return v;
+}
+
 extern "C" int bess_peer_push(const void* src, int64_t src_stride_bytes, void* const* dst, int n,
                               int64_t bytes_each, void* stream) {
   if (bytes_each <= 0) return BESS_OK;
@@ -152,13 +175,25 @@ extern "C" int bess_peer_push(const void* src, int64_t src_stride_bytes, void* c
                  "bess_peer_push: 16-byte alignment required");
   const int64_t n16 = bytes_each >> 4;
   int bx = (int)((n16 + 255) / 256);
-  const int cap = (8 * kNumSM + n - 1) / n;
+  const int cap = (push_blocks_per_sm() * kNumSM + n - 1) / n;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   peer_push_kernel<<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, src_stride_bytes,
                                                                  pp, bytes_each);
   BESS_CHECK_LAUNCH();
   return BESS_OK;
+}
+
+extern "C" int bess_peer_copy(const void* src, void* dst, int64_t bytes, void* stream) {
+  if (bytes <= 0) return BESS_OK;
+  BESS_CHECK_ARG(src != nullptr && dst != nullptr, "bess_peer_copy: null pointer");
+  const cudaError_t e =
+      cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    bess_set_error("bess_peer_copy: %s", cudaGetErrorString(e));
+    return BESS_ERR_CUDA;
+  }
+  return BESS_OK;  // a memcpy node, not a kernel: bess_launch_count() does not move
 }
 
 extern "C" int bess_peer_reduce(const float* slots, int n, int64_t count, float scale, float* out,

@@ -493,6 +493,11 @@ def peer_push(src: torch.Tensor, src_stride_bytes: int, dst_ptrs: Sequence[int],
          bytes_each, _st(src))
 
 
+def peer_copy(src_ptr: int, dst_ptr: int, nbytes: int, stream: "torch.cuda.Stream") -> None:
+    """copy-engine transfer of one contiguous block (local or peer-mapped destination)."""
+    call("bess_peer_copy", src_ptr, dst_ptr, nbytes, stream.cuda_stream)
+
+
 def peer_reduce(slots: torch.Tensor, n: int, count: int, scale: float, out: torch.Tensor) -> None:
     call("bess_peer_reduce", slots.data_ptr(), n, count, float(scale), out.data_ptr(), _st(out))
 

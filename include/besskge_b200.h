@@ -452,7 +452,12 @@ int bess_pairs_set(float* mat, int64_t ld, const int32_t* rows, const int32_t* c
  *   wait  : until all n local flags >= *counter (acquire.sys).  timeout_ms > 0 bounds the
  *           spin in wall-clock time (%globaltimer): on expiry the launch prints the
  *           missing rank and traps; timeout_ms <= 0 waits for ever
- *   push  : dst[j] <- src + j * src_stride_bytes, bytes_each bytes, for j < n
+ *   push  : dst[j] <- src + j * src_stride_bytes, bytes_each bytes, for j < n (an SM kernel:
+ *           remote stores)
+ *   copy  : the same transfer for destination j alone, issued to a copy engine
+ *           (cudaMemcpyAsync, a memcpy node under stream capture): no SM is involved, so it
+ *           does not slow a GEMM that runs next to it; the caller spreads the destinations
+ *           over a few streams to keep several engines busy
  *   reduce: out[i] = scale * sum_j slots[j * count + i], j ascending */
 int bess_peer_signal(int32_t* counter, void* const* peer_flags /* host array [n] */, int my_rank,
                      int n, void* stream);
@@ -460,6 +465,7 @@ int bess_peer_wait(const int32_t* counter, const int32_t* my_flags, int n, int64
                    void* stream);
 int bess_peer_push(const void* src, int64_t src_stride_bytes, void* const* dst /* host array [n] */,
                    int n, int64_t bytes_each, void* stream);
+int bess_peer_copy(const void* src, void* dst, int64_t bytes, void* stream);
 int bess_peer_reduce(const float* slots, int n, int64_t count, float scale, float* out, void* stream);
 
 /* Peer-mapped receive buffers through CUDA IPC (no framework involved): alloc (zero-filled,
