@@ -265,8 +265,19 @@ SPLIT_EXCHANGE_GATHER = os.environ.get("BESS_SPLIT_GATHER", "1") != "0"
 # a local send buffer, one memcpy per destination (spread over COPY_STREAMS streams) delivers it,
 # and the gradient blocks travel back the same way — no SM cycles, so the contractions that run
 # next to the transfer keep their speed (A/B: BESS_COPY_ENGINE=0 selects the remote-store kernels)
-USE_COPY_ENGINE = os.environ.get("BESS_COPY_ENGINE", "1") != "0"
+# Measured (cfg 2, 16.5 MB per rank and direction): at 2 ranks the copy engines win (0.394 vs
+# 0.409 ms per step); at 8 ranks seven 2.4 MB copies take ~90 us (~180 GB/s aggregate) and are
+# no longer hidden, while the remote-store kernels deliver the same bytes in ~35 us at the price
+# of ~20 us of contention (0.417 vs 0.439 ms).  "auto" picks by the number of ranks.
+COPY_ENGINE = os.environ.get("BESS_COPY_ENGINE", "auto")
+COPY_ENGINE_MAX_RANKS = int(os.environ.get("BESS_COPY_ENGINE_MAX_RANKS", "2"))
 COPY_STREAMS = max(1, int(os.environ.get("BESS_COPY_STREAMS", "4")))
+
+
+def _use_copy_engine(n_rank: int) -> bool:
+    if COPY_ENGINE == "auto":
+        return n_rank <= COPY_ENGINE_MAX_RANKS
+    return COPY_ENGINE != "0"
 # score_triple fwd / bwd and the relation-table reduce on a second stream, concurrent with the
 # negative-scoring / contraction kernels (A/B switch: BESS_OVERLAP=0)
 OVERLAP_SMALL_KERNELS = os.environ.get("BESS_OVERLAP", "1") != "0"
@@ -610,20 +621,27 @@ class EmbeddingMovingBessKGE(BessKGE):
                 n_col = n * Nn
         elif scheme == "ht":
             half = p // 2
-            if not flat and shared:
-                raise NotImplementedError(
-                    "'ht' corruption with non-flat shared negatives is not implemented"
-                )
             for k, (mode, from_head) in enumerate(((L.MODE_HEADS, False), (L.MODE_TAILS, True))):
                 qmap = rm(half, p, k * half)
                 fixed_map = rm(half, p, k * half) if from_head else rm(half, per, k * half)
+                if not flat and shared:
+                    # every query of the group against the negatives of ALL its queries
+                    # (bess.py:423-429 + the shared broadcast of scoring.py): candidate
+                    # ((i, q'), j, kk) is the kk-th negative from shard j of query b = i*p + k*half
+                    # + q'.  One pass per partition i keeps the candidate map two-level.
+                    blk = half * n * Nn
+                    for i in range(n):
+                        cmap = rm(Nn, neg_stride, neg_off + (i * p + k * half) * Nn, n * Nn, Nn)
+                        passes.append(_Pass(mode, n * half, qmap, from_head, fixed_map, True, blk,
+                                            cmap, 0, i * blk))
+                    continue
                 if flat:
                     passes.append(_Pass(mode, n * half, qmap, from_head, fixed_map, True, n * Nn,
                                         rm(Nn, neg_stride, neg_off + k * Nn), 0, 0))
                 else:
                     passes.append(_Pass(mode, n * half, qmap, from_head, fixed_map, False, n * Nn,
                                         rm(Nn, neg_stride, neg_off), Nn, 0))
-            n_col = n * Nn
+            n_col = n * half * n * Nn if (not flat and shared) else n * Nn
         else:
             raise ValueError(f"unknown corruption scheme {scheme}")
         if self.augment_negative:
@@ -631,8 +649,6 @@ class EmbeddingMovingBessKGE(BessKGE):
                 raise NotImplementedError(
                     "augment_negative needs flat_negative_format=True and local_sampling=False"
                 )
-            if self.score_fn._family in (L.PAIRRE, L.TRIPLERE) and getattr(self.score_fn, "normalize", False):
-                raise NotImplementedError("augment_negative with normalised PairRE")
             # the micro-batch's own heads / tails come first (bess.py:369-394, 430-448)
             aug: List[_Pass] = []
             for ps in passes:
@@ -945,7 +961,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     xch_st = self._aux_stream(dev)
                     xch_st.wait_stream(main)
                     with torch.cuda.stream(xch_st):
-                        if USE_COPY_ENGINE:
+                        if _use_copy_engine(n):
                             rb = per * W * ent.element_size()
                             sendx = ws.get("SENDX", (n, per, W), tdt)
                             stage_dst = [sendx[j].data_ptr() for j in range(n)]
@@ -1210,10 +1226,19 @@ class EmbeddingMovingBessKGE(BessKGE):
                             cand_st = aux_st if (overlap and not need_scale) else main
                             if cand_st is not main:
                                 cand_st.wait_stream(torch.cuda.current_stream(dev))
+                            # augmented candidates are the micro-batch's own head / tail rows,
+                            # whose gradient rows also collect other terms: with a candidate
+                            # normalisation, this pass's term goes through the chain rule in a
+                            # buffer of its own before it is added
+                            via_tmp = bool(ps.aug and need_scale)
+                            d_target = d_cand
+                            if via_tmp:
+                                d_cand = L.rows(ws.get("aug_dcand", (ps.n_cand, W), torch.float32))
                             with torch.cuda.stream(cand_st):
                                 K.shared_bwd_cand(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
                                                   ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
-                                                  ps.col0, a, d_cand, cand_ws, add=ps.aug)
+                                                  ps.col0, a, d_cand, cand_ws,
+                                                  add=ps.aug and not via_tmp)
                             K.shared_bwd_query(cfg, dt, ps.mode, qv, ps.n_query, cand, scale,
                                                ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
                                                ps.col0, a, d_qv)
@@ -1221,6 +1246,10 @@ class EmbeddingMovingBessKGE(BessKGE):
                                 tb_joined = False  # more work on the second stream: join again
                             if need_scale:
                                 K.cand_scales_bwd(cfg, dt, cand, ps.n_cand, W, scale, d_cand)
+                            if via_tmp:
+                                ones = ws.get("ones_rows", (ps.n_cand,), torch.float32)
+                                ones.fill_(1.0)
+                                K.rows_axpy(L.F32, ones, 1.0, d_cand, d_target, ps.n_cand, W)
                         else:
                             K.pertriple_bwd(cfg, dt, ps.mode, qv, ps.n_query, cand, ps.q_stride,
                                             ps.n_cand, score_for_bwd, d_neg[li], ps.qmap, N,
@@ -1332,7 +1361,7 @@ class EmbeddingMovingBessKGE(BessKGE):
         """block j of this replica's fp32 gradient buffer -> slot [rank] of rank j's gradient
         receive buffer (the reverse of the forward exchange, bess.py:348-350 under autograd)."""
         dst = [q + px.off_grad + pl.rank * blk for q in px.ptrs]
-        if USE_COPY_ENGINE:
+        if _use_copy_engine(len(dst)):
             self._ce_blocks(dev, dTN[0].data_ptr(), blk, dst, blk, pl.rank)
         else:
             K.peer_push(dTN[0], blk, dst, blk)
@@ -1347,6 +1376,11 @@ class EmbeddingMovingBessKGE(BessKGE):
                      nmask: Optional[torch.Tensor], flat: bool, scheme: str) -> None:
         """BAD_NEGATIVE_SCORE on padding negatives and, with augment_negative, on
         each triple's own head/tail column (bess.py:182-245)."""
+        if (nmask is not None and not flat
+                and bool(self.score_fn.negative_sample_sharing)):
+            raise ValueError("negative_mask cannot be combined with non-flat shared negatives: "
+                             "the mask is [B, n_shard * Nn] and the scores [B, B * n_shard * Nn] "
+                             "(the reference fails on the same shapes, bess.py:182-245)")
         if self.augment_negative:
             half = p // 2 if scheme == "ht" else 0
             n_aug = N - n * Nn

@@ -324,6 +324,41 @@ def golden_bess(ref, only=None) -> None:
                          ranks=res["ranks"], metrics=res["metrics"])
 
 
+def golden_bess_shared(ref) -> None:
+    """Non-flat negatives WITH negative_sample_sharing (every query of a group is scored against
+    the negatives of all its queries: bess.py:400-466 / 523-566 with scoring.py's shared
+    broadcasting) — the combination the `bess_` grid above leaves out, because the triple-based
+    sampler there carries a padding mask that the reference cannot combine with sharing."""
+    n_entity, n_rel, n_shard, n_triple, shard_bs, n_neg, d = 200, 6, 4, 400, 16, 3, 16
+    sh = ref.sharding.Sharding.create(n_entity, n_shard, seed=SEED)
+    for model_name in ("EmbeddingMoving", "ScoreMoving"):
+        for fam, p in (("TransE", 1), ("DistMult", 0), ("RotatE", 2)):
+            for scheme in ("h", "t", "ht"):
+                rng = np.random.default_rng(SEED + 13)
+                ds = make_dataset(ref, n_entity, n_rel, n_triple, 4, rng)
+                pts = ref.sharding.PartitionedTripleSet.create_from_dataset(
+                    ds, "test", sh, "ht_shardpair")
+                gen = torch.Generator().manual_seed(SEED)
+                ent, rel = tables(fam, sh, n_rel, d, gen)
+                sf = build_score_fn(ref, fam, True, p, sh, n_rel, d, ent, rel)
+                ns = ref.negative_sampler.RandomShardedNegativeSampler(
+                    n_negative=n_neg, sharding=sh, seed=SEED, corruption_scheme=scheme,
+                    local_sampling=False, flat_negative_format=False)
+                bs = ref.batch_sampler.RandomShardedBatchSampler(pts, ns, shard_bs=shard_bs,
+                                                                 batches_per_step=1, seed=SEED)
+                cls = getattr(ref.bess, model_name + "BessKGE")
+                model = cls(negative_sampler=ns, score_fn=sf, return_scores=True)
+                batch = bs[[0]]
+                with torch.no_grad():
+                    res = ref_loader.run_replicated(model, batch, n_shard, 1)
+                save(f"shbess_{model_name}_{fam}{p}_{scheme}",
+                     dict(model=model_name, family=fam, p=p, scheme=scheme, flat=False, shared=True,
+                          d=d, n_rel=n_rel, n_entity=n_entity, n_shard=n_shard, bps=1,
+                          shard_bs=shard_bs, seed=SEED),
+                     ent=ent, rel=rel, **{f"in_{k}": v for k, v in batch.items()},
+                     positive_score=res["positive_score"], negative_score=res["negative_score"])
+
+
 def golden_train(ref, only=None) -> None:
     """reference forward -> torch.autograd -> dense torch.optim, n_shard 4 and 1."""
     n_entity, n_rel, n_triple, d, n_step = 200, 6, 600, 16, 3
@@ -561,7 +596,7 @@ def golden_dataset(ref) -> None:
 
 GENERATORS = dict(host=golden_host, dataset=golden_dataset, scores=golden_scores, loss=golden_loss,
                   metric=golden_metric, bess=golden_bess, train=golden_train, topk=golden_topk,
-                  pipeline=golden_pipeline)
+                  pipeline=golden_pipeline, bess_shared=golden_bess_shared)
 
 
 def main() -> None:

@@ -57,6 +57,28 @@ def test_bess_forward_vs_reference_golden(name):
     assert_close((1.0 / ranks[~near]).sum(), (1.0 / want[~near]).sum(), rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("name", golden_names("shbess_"))
+def test_bess_forward_shared_nonflat_vs_reference_golden(name):
+    """non-flat negatives with negative_sample_sharing (h / t / ht; both BESS variants) against
+    the reference's own outputs (bess.py:400-466, 523-566)."""
+    B, H = _imports()
+    from besskge_b200.sharding import Sharding
+    cfg, g = load_golden(name)
+    sh = Sharding.create(cfg["n_entity"], cfg["n_shard"], seed=cfg["seed"])
+    sf = H.make_score_fn(cfg["family"], True, cfg["p"], sh, cfg["n_rel"], cfg["d"],
+                         H.T(g["ent"]), H.T(g["rel"]))
+    ns = H.fake_sampler(cfg["scheme"], False, triple_based=False)
+    cls = getattr(B.bess, cfg["model"] + "BessKGE")
+    model = cls(negative_sampler=ns, score_fn=sf, return_scores=True)
+    batch = {k[3:]: H.T(v).flatten(end_dim=1) for k, v in g.items() if k.startswith("in_")}
+    res = model(**batch)
+    torch.cuda.synchronize()
+    want_neg = H.T(g["negative_score"])
+    assert res["negative_score"].shape == want_neg.shape
+    assert_close(res["positive_score"].cpu(), H.T(g["positive_score"]), rtol=1e-5, atol=5e-5)
+    assert_close(res["negative_score"].cpu(), want_neg, rtol=1e-5, atol=5e-5)
+
+
 @pytest.mark.parametrize("name", golden_names("train_"))
 def test_training_vs_reference_golden(name):
     B, H = _imports()
@@ -91,6 +113,11 @@ def test_training_vs_reference_golden(name):
     ("TransE", 2, "h", False, True, "logsigmoid"),
     ("DistMult", 2, "t", False, False, "margin_ranking"),
     ("ComplEx", 2, "ht", True, True, "logsigmoid"),
+    ("TransE", 1, "ht", False, True, "logsigmoid"),       # 'ht' with non-flat SHARED negatives
+    ("DistMult", 2, "ht", False, True, "margin_ranking"),
+    ("RotatE", 1, "ht", False, True, "logsigmoid"),
+    ("PairRE", 1, "t", True, True, "logsigmoid"),         # augment + normalised candidates
+    ("InterHT", 2, "ht", True, True, "logsigmoid"),
 ])
 @pytest.mark.parametrize("augment", [False, True])
 def test_training_vs_oracle_extra(fam, p, scheme, flat, shared, loss_kind, augment):
@@ -105,8 +132,8 @@ def test_training_vs_oracle_extra(fam, p, scheme, flat, shared, loss_kind, augme
     n, p_part, Nn, d, n_rel, n_ent = 2, 6, 5, 16, 4, 60
     sh = Sharding.create(n_ent, n, seed=3)
     gen = torch.Generator().manual_seed(11)
-    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE") else 1
-    rw = 2 * d if fam == "ComplEx" else d
+    ew = 2 if fam in ("RotatE", "ComplEx", "BoxE", "InterHT", "TranS") else 1
+    rw = {"ComplEx": 2 * d, "PairRE": 2 * d, "BoxE": 4 * d + 2, "TranS": 3 * d}.get(fam, d)
     ent = torch.randn(n, sh.max_entity_per_shard, ew * d, generator=gen) * 0.5
     rel = torch.randn(n_rel, rw, generator=gen) * 0.5
     S = n * p_part

@@ -129,6 +129,26 @@ def test_bess_forward_oracle(name):
     assert_close(torch.cat(neg_all), T(g["negative_score"]), rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("name", golden_names("shbess_"))
+def test_bess_forward_shared_nonflat_oracle(name):
+    """non-flat negatives with negative_sample_sharing (h / t / ht, both BESS variants): the
+    reference's outputs from tests/golden/make_golden.py::golden_bess_shared."""
+    cfg, g = load_golden(name)
+    n, bps, ins = bess_inputs(cfg, g)
+    c = score_cfg(cfg["family"], cfg["d"], dict(p=cfg["p"]))
+    ent, rel = T(g["ent"]), T(g["rel"])
+    kw = dict(scheme=cfg["scheme"], flat=False, shared=True, negative_mask=None)
+    if cfg["model"] == "EmbeddingMoving":
+        pos, neg = O.embedding_moving_forward(c, ent, rel, ins["head"][0], ins["relation"][0],
+                                              ins["tail"][0], ins["negative"][0], **kw)
+    else:
+        pos, neg = O.score_moving_forward(c, ent, rel, ins["head"][0], ins["relation"][0],
+                                          ins["tail"][0], ins["negative"][0], triple_based=False,
+                                          **kw)
+    assert_close(pos.flatten(), T(g["positive_score"]), rtol=1e-5, atol=1e-4)
+    assert_close(neg.flatten(end_dim=1), T(g["negative_score"]), rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("name", golden_names("train_"))
 def test_training_oracle(name):
     cfg, g = load_golden(name)
