@@ -265,18 +265,23 @@ SPLIT_EXCHANGE_GATHER = os.environ.get("BESS_SPLIT_GATHER", "1") != "0"
 # a local send buffer, one memcpy per destination (spread over COPY_STREAMS streams) delivers it,
 # and the gradient blocks travel back the same way — no SM cycles, so the contractions that run
 # next to the transfer keep their speed (A/B: BESS_COPY_ENGINE=0 selects the remote-store kernels)
-# Measured (cfg 2, 16.5 MB per rank and direction): at 2 ranks the copy engines win (0.394 vs
-# 0.409 ms per step); at 8 ranks seven 2.4 MB copies take ~90 us (~180 GB/s aggregate) and are
-# no longer hidden, while the remote-store kernels deliver the same bytes in ~35 us at the price
-# of ~20 us of contention (0.417 vs 0.439 ms).  "auto" picks by the number of ranks.
+# Measured (cfg 2, 16.5 MB per rank and direction; ms per step, copy engines vs remote stores):
+# 2 ranks 0.394 vs 0.409, 4 ranks 0.395 vs 0.407, 8 ranks 0.438 vs 0.420 — seven 2.4 MB copies
+# take ~90 us (~180 GB/s aggregate) and are no longer hidden under the contractions, while the
+# remote-store kernels deliver the same bytes in ~35 us at the price of ~20 us of contention.
+# "auto" picks by the number of ranks.
 COPY_ENGINE = os.environ.get("BESS_COPY_ENGINE", "auto")
-COPY_ENGINE_MAX_RANKS = int(os.environ.get("BESS_COPY_ENGINE_MAX_RANKS", "2"))
+COPY_ENGINE_MAX_RANKS = int(os.environ.get("BESS_COPY_ENGINE_MAX_RANKS", "4"))
 COPY_STREAMS = max(1, int(os.environ.get("BESS_COPY_STREAMS", "4")))
 
 
-def _use_copy_engine(n_rank: int) -> bool:
+def _use_copy_engine(n_rank: int, overlapped: bool) -> bool:
+    """`overlapped`: the step has contractions to hide the copies under (the tensor-core step
+    that pushes its gradients early).  Where the transfer is exposed — e.g. the CUDA-core
+    distance families, whose push follows the whole backward — the remote-store kernels are the
+    faster way to move the same bytes (wikikg2 TransE-L1 at 2 ranks: 0.40 vs 0.42 ms)."""
     if COPY_ENGINE == "auto":
-        return n_rank <= COPY_ENGINE_MAX_RANKS
+        return overlapped and n_rank <= COPY_ENGINE_MAX_RANKS
     return COPY_ENGINE != "0"
 # score_triple fwd / bwd and the relation-table reduce on a second stream, concurrent with the
 # negative-scoring / contraction kernels (A/B switch: BESS_OVERLAP=0)
@@ -884,6 +889,7 @@ class EmbeddingMovingBessKGE(BessKGE):
         # handshake go to the side stream and overlap that remaining compute.
         early_push = bool(px is not None and direct_ds and R == 1
                           and all(ps.fixed_from_head for ps in passes))
+        use_ce = bool(px is not None and _use_copy_engine(n, early_push))
         # operand format of the DOT contractions (fp32 tables: scaled fp16 pairs, 3xFP16); the
         # norm-expanded L2 path keeps tf32 pairs
         gdt = _operand_format(tdt) if use_tc else dt
@@ -961,7 +967,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                     xch_st = self._aux_stream(dev)
                     xch_st.wait_stream(main)
                     with torch.cuda.stream(xch_st):
-                        if _use_copy_engine(n):
+                        if use_ce:
                             rb = per * W * ent.element_size()
                             sendx = ws.get("SENDX", (n, per, W), tdt)
                             stage_dst = [sendx[j].data_ptr() for j in range(n)]
@@ -1143,7 +1149,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                         main = torch.cuda.current_stream(dev)
                         side.wait_stream(main)
                         with torch.cuda.stream(side):
-                            self._push_gradients(dev, px, pl, dTN, per * W * 4)
+                            self._push_gradients(dev, px, pl, dTN, per * W * 4, use_ce)
                             px.handshake(1)
                     for pi, ps in enumerate(passes):
                         fixed = (L.rows(Hl, rmap=ps.fixed_map) if ps.fixed_from_head
@@ -1267,7 +1273,7 @@ class EmbeddingMovingBessKGE(BessKGE):
                 px.handshake(1)  # every rank is done reading its receive buffer
             if train:
                 if px is not None and not early_push:
-                    self._push_gradients(dev, px, pl, dTN, per * W * 4)
+                    self._push_gradients(dev, px, pl, dTN, per * W * 4, use_ce)
                     px.handshake(1)
                 elif pl.distributed and px is None:
                     pl.all_to_all(dBACK, dTN[0])
@@ -1357,11 +1363,11 @@ class EmbeddingMovingBessKGE(BessKGE):
 
     # ---- helpers -------------------------------------------------------------
     def _push_gradients(self, dev, px: _PeerExchange, pl: _Placement, dTN: torch.Tensor,
-                        blk: int) -> None:
+                        blk: int, use_ce: bool) -> None:
         """block j of this replica's fp32 gradient buffer -> slot [rank] of rank j's gradient
         receive buffer (the reverse of the forward exchange, bess.py:348-350 under autograd)."""
         dst = [q + px.off_grad + pl.rank * blk for q in px.ptrs]
-        if _use_copy_engine(len(dst)):
+        if use_ce:
             self._ce_blocks(dev, dTN[0].data_ptr(), blk, dst, blk, pl.rank)
         else:
             K.peer_push(dTN[0], blk, dst, blk)
