@@ -405,11 +405,13 @@ def kernel_rooflines(sf, prob, pk, optimizer: str):
     return roof, gather, scatter, opt_dense
 
 
-def cpu_port_steps(prob, n_steps: int, threads: int, optimizer: str = "sgd"):
+def cpu_port_steps(prob, n_steps: int, threads: int, optimizer: str = "sgd",
+                   budget_s: float = 0.0, min_steps: int = 0):
     """The reference's plain-PyTorch CPU path (arithmetic of bess.py + scoring.py + loss.py with
     emulated cross-replica collectives, torch autograd, dense torch.optim) restated by the
     oracle, on the SAME sharded workload as the B200 arm (same n_shard, shard_bs, negatives);
-    returns seconds per step."""
+    returns seconds per step.  With a time budget the loop stops early (after at least
+    `min_steps` steps) once the budget is spent: the caller reports how many steps it timed."""
     from oracle import besskge_oracle as O
 
     torch.set_num_threads(threads)
@@ -445,7 +447,12 @@ def cpu_port_steps(prob, n_steps: int, threads: int, optimizer: str = "sgd"):
             rel.grad.div_(n)
         opt.step()
         times.append(time.perf_counter() - t0)
+        if budget_s > 0 and len(times) >= min_steps and sum(times) > budget_s:
+            break
     return times
+
+
+REFERENCE_BUDGET_S = float(os.environ.get("BESS_REFERENCE_BUDGET_S", "90"))
 
 
 def run_reference(args) -> None:
@@ -458,10 +465,17 @@ def run_reference(args) -> None:
         bps //= 2
     prob = build_problem(args.workload, n, args.shard_bs, args.negatives, args.n_triple, bps)
     threads = os.cpu_count() or 1
-    times = cpu_port_steps(prob, args.warmup + args.steps, threads, args.optimizer)
-    t = float(np.mean(times[args.warmup:]))
+    # bounded: a step of this port takes 0.2 s (n_shard = 1) to several seconds (n_shard = 8,
+    # the replicas run one after the other); at most REFERENCE_BUDGET_S of stepping, at least
+    # one warm-up step and two timed ones
+    warm = min(args.warmup, 2) if n > 1 else args.warmup
+    times = cpu_port_steps(prob, warm + args.steps, threads, args.optimizer,
+                           budget_s=REFERENCE_BUDGET_S, min_steps=warm + 2)
+    timed = len(times) - warm
+    t = float(np.mean(times[warm:]))
     value = n * prob["shard_bs"] / t
-    sample = (f"{args.steps} whole steps ({args.warmup} warm-up) of the same workload as the B200 arm: "
+    sample = (f"{timed} timed whole steps of the {args.steps} requested ({warm} warm-up; the loop "
+              f"stops after {REFERENCE_BUDGET_S:.0f} s of stepping) of the same workload as the B200 arm: "
               f"n_shard={n} replicas x shard_bs={prob['shard_bs']} triples x {prob['negatives']} shared "
               "negatives — oracle port of the reference's plain-PyTorch path (forward with emulated "
               f"collectives + autograd + dense torch.optim) on {threads} host threads")
