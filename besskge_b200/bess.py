@@ -17,11 +17,14 @@ Replica placement (the reference is single-controller with PopTorch replicas):
     AllToAll is folded into the gather, which writes every row straight into
     the receive buffer of the replica that scores it;
   * distributed mode — one process per GPU (`torch.distributed` for rendezvous
-    and the symmetric-memory allocation); this process owns shard `rank`; the
-    gather kernel stores every tail / negative row straight into the
-    destination GPU's receive buffer over NVLink (peer-mapped pointers) and a
-    flag handshake replaces the collective (csrc/peer.cu).  NCCL
-    `all_to_all_single` remains selectable for A/B runs (`USE_PEER_EXCHANGE`).
+    and the peer mapping: torch symmetric memory or this library's CUDA-IPC
+    calls); this process owns shard `rank`; tail / negative rows reach the
+    destination GPU's receive buffer over NVLink either by remote stores of
+    the gather kernel or by copy-engine transfers of a local send buffer
+    (`_use_copy_engine`), gradients travel back the same way, and flag
+    handshakes replace the collectives (csrc/peer.cu).  The whole distributed
+    training call is one CUDA graph per rank.  NCCL `all_to_all_single`
+    remains selectable for A/B runs (`USE_PEER_EXCHANGE`).
 Inputs keep the reference layout: a leading `batches_per_step * n_shard` axis
 (step-major, shard-minor); outputs are concatenated in the same order
 (tests/test_bess.py:181-196 of the reference).
